@@ -1,0 +1,182 @@
+/*
+ * msfwsi_b200 -- C ABI of the B200-native MSF-WSI SSL head + loss hot path.
+ *
+ * The reference (Dylan-H-Wang/msf-wsi) has no FFI / plugin boundary: its hot path is plain
+ * PyTorch inside `MSFWSI.forward` (src/models/backbone.py:129-222) and the loss block of
+ * `train` (tools/ssl_train.py:448-466).  This header is the boundary a maintainer would bind
+ * (ctypes stub in INTEGRATION.md); every entry point cites the reference lines it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all data pointers are DEVICE pointers unless a parameter
+ *     is documented as host memory; `stream` is a cudaStream_t passed as void*.
+ *   - the library never allocates, frees or synchronises the device: the caller owns every
+ *     buffer including workspaces (`msf_*_workspace_bytes`), and every call is asynchronous on
+ *     `stream`.
+ *   - return value: MSF_OK (0) or a negative msf_status; the message of the last failure on
+ *     the calling thread is available from msf_last_error().
+ *   - re-entrant: no global mutable state; callable from the autograd engine thread.
+ *   - row-major, contiguous tensors; base pointers 16-byte aligned; feature widths must be
+ *     multiples of 8 elements (the reference widths are 64..4608).
+ */
+#ifndef MSFWSI_B200_H_
+#define MSFWSI_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSF_ABI_VERSION 1
+
+typedef enum { MSF_F32 = 0, MSF_BF16 = 1, MSF_F16 = 2 } msf_dtype;
+
+typedef enum {
+  MSF_OK = 0,
+  MSF_ERR_INVALID = -1,     /* bad argument (null pointer, misalignment, bad shape) */
+  MSF_ERR_UNSUPPORTED = -2, /* shape / dtype / device outside what the kernels cover */
+  MSF_ERR_WORKSPACE = -3,   /* workspace too small */
+  MSF_ERR_CUDA = -4         /* a CUDA runtime / driver call failed */
+} msf_status;
+
+int msf_abi_version(void);
+/* Thread-local, never NULL. */
+const char* msf_last_error(void);
+/* Fills sm_count / compute-capability of the current device; MSF_ERR_UNSUPPORTED unless cc == 10.0. */
+int msf_device_check(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * A1  inverse-jigsaw gather + fuser concat, all levels and both views in one launch.
+ * Replaces src/models/backbone.py:147-158 (reshape + advanced-index gather) and :195-202
+ * (torch.cat of the context vector with the first n_keep shuffled target vectors).
+ *   tgt_sorted[b*K + j, :] = tgt_f[b*K + rev[b, j], :]
+ *   ms_f[b, :]             = [ ctx_f[b, :] | tgt_f[b*K + 0, :] | ... | tgt_f[b*K + n_keep-1, :] ]
+ * Exact copies (bit-exact for every dtype).  rev entries outside [-K, K) set bit 0 of
+ * *status_flag (device int32, may be NULL) and are clamped; the reference raises IndexError.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* tgt_f;    /* (B*K, d)  target vectors in the shuffled order the encoder saw */
+  const void* ctx_f;    /* (B, d) */
+  const int64_t* rev;   /* (B, K)    jigsaw_idx of this view */
+  void* tgt_sorted;     /* (B*K, d)  out */
+  void* ms_f;           /* (B, (n_keep+1)*d) out */
+  int32_t d;
+  int32_t reserved;
+} msf_gather_item;
+
+#define MSF_GATHER_MAX_ITEMS 16
+int msf_gather_concat_fwd(const msf_gather_item* items /*host*/, int n_items, int64_t B, int K, int n_keep,
+                          int dtype, int32_t* status_flag, void* stream);
+
+/* Backward of the above:
+ *   g_tgt_f[b*K + k, :] = g_sorted[b*K + inv(b)[k], :] + (k < n_keep ? g_ms[b, (1+k)*d : (2+k)*d] : 0)
+ *   g_ctx_f[b, :]       = g_ms[b, 0:d]
+ * with inv(b) the inverse permutation of rev[b, :].  g_sorted or g_ms may be NULL (treated as 0). */
+typedef struct {
+  const void* g_sorted; /* (B*K, d) or NULL */
+  const void* g_ms;     /* (B, (n_keep+1)*d) or NULL */
+  const int64_t* rev;   /* (B, K) */
+  void* g_tgt_f;        /* (B*K, d) out */
+  void* g_ctx_f;        /* (B, d)   out */
+  int32_t d;
+  int32_t reserved;
+} msf_gather_grad_item;
+int msf_gather_concat_bwd(const msf_gather_grad_item* items /*host*/, int n_items, int64_t B, int K, int n_keep,
+                          int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * L1 (cosine mode)  SimSiam negative-cosine loss over many (p, z) pairs in one launch.
+ * Replaces the 24 nn.CosineSimilarity(dim=1) + .mean() calls of tools/ssl_train.py:422,448-466:
+ *   *loss_out = sum_pairs coef_pair * mean_i cos(p_i, z_i),  cos with ATen's per-vector
+ *   clamp_min(||v||, eps); coef_pair = -0.5 * fuser_weight[level].
+ * Arithmetic is fp32 for every input dtype (CUDA autocast runs cosine_similarity in fp32);
+ * the reduction order is fixed (deterministic).  row_stats receives 4 floats per row
+ * {cos, 1/max(||p||,eps), 1/max(||z||,eps), ||p||>=eps} consumed by the backward.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* p;       /* (rows, dim) predictor output (receives gradient) */
+  const void* z;       /* (rows, dim) detached projector output */
+  float* row_stats;    /* (rows, 4) fp32 */
+  void* grad_p;        /* (rows, dim) out of the backward, dtype of p; unused by the forward */
+  int64_t rows;
+  int32_t dim;
+  float coef;
+} msf_cos_pair;
+
+#define MSF_COS_MAX_PAIRS 32
+size_t msf_cosine_loss_workspace_bytes(const msf_cos_pair* pairs /*host*/, int n_pairs);
+int msf_cosine_loss_fwd(const msf_cos_pair* pairs /*host*/, int n_pairs, int dtype, float eps, float* loss_out,
+                        void* workspace, size_t workspace_bytes, void* stream);
+/* grad_p[i,:] = *grad_out * coef/rows * d cos(p_i,z_i)/d p_i ; grad_out is a DEVICE fp32 scalar
+ * (GradScaler's non-unit upstream gradient, tools/ssl_train.py:472, without a host sync). */
+int msf_cosine_loss_bwd(const msf_cos_pair* pairs /*host*/, int n_pairs, int dtype, const float* grad_out,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * L1 (infonce mode)  flash-style fused InfoNCE (extension named by BASELINE.json:north_star; the
+ * reference has no such loss -- parity unpinned, oracle = oracle/msf_oracle.py:infonce_loss).
+ *   row_loss_i = logsumexp_j(q_hat_i . k_hat_j / tau) - q_hat_i . k_hat_{pos_offset+i} / tau
+ * Keys are detached (backbone.py:188-191): one pass over the keys yields the loss AND
+ * O_i = sum_j exp(.)_ij k_hat_j, from which the backward forms dq without touching the keys again.
+ * The N x N logits are never materialised.
+ *
+ * Step 1  msf_rownorm: x -> x_hat = x / max(||x||, eps) (bf16 or fp32 out) and 1/max(||x||,eps).
+ * Step 2  (multi-GPU) the caller all-gathers k_hat over NCCL; rank-major order.
+ * Step 3  msf_infonce_fwd: loss pieces + O partials into the workspace.
+ * Step 4  msf_infonce_bwd: grad_q (dtype of q) from the saved workspace.
+ *
+ * precision: MSF_F32  -> fp32 SIMT kernel (q_hat/k_hat fp32), for <=1e-5 parity.
+ *            MSF_BF16 -> TMA + tcgen05/TMEM kernel (q_hat/k_hat bf16), dim in {64,128,256}.
+ * tau must satisfy 2*log2(e)/tau <= 120 (tau >= 0.0241): the softmax uses the fixed bound
+ * max_j s_ij <= 1/tau that L2-normalised operands guarantee, so no running max is kept.
+ * ---------------------------------------------------------------------------------------- */
+int msf_rownorm(const void* x, int64_t rows, int dim, int in_dtype, float eps, void* x_hat, int out_dtype,
+                float* inv_norm, void* stream);
+
+size_t msf_infonce_workspace_bytes(int64_t nq, int64_t n_keys, int dim, int precision);
+/* loss_sum_out: device fp32 scalar that receives sum_i row_loss_i (NOT divided; the caller
+ * divides by the global row count).  row_lse (nq) may be NULL. */
+int msf_infonce_fwd(const void* q_hat, const void* k_hat, int64_t nq, int64_t n_keys, int dim,
+                    int64_t pos_offset, float tau, int precision, float* loss_sum_out, float* row_lse,
+                    void* workspace, size_t workspace_bytes, void* stream);
+/* grad_q = *grad_out * scale * J_normalize(q)^T [ (O_i / rowsum_i - k_hat_pos(i)) / tau ],
+ * scale = 1 / n_rows_global supplied by the caller. */
+int msf_infonce_bwd(const void* q_hat, const void* k_hat, const float* q_inv_norm, int64_t nq, int64_t n_keys,
+                    int dim, int64_t pos_offset, float tau, int precision, const float* grad_out, float scale,
+                    const void* workspace, size_t workspace_bytes, void* grad_q, int grad_dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * A2  feature-map crop to each tile's footprint + bilinear resample.
+ * Integer case reproduces src/models/hooknet.py:29-32 (`x[:, :, 12:20, 12:20]`) bit-exactly;
+ * the fractional / resampling case is an extension (F.interpolate bilinear, align_corners=False
+ * semantics on the crop; oracle/msf_oracle.py:crop_resample).
+ *   feat (B,C,H,W) NCHW ; boxes (B,K,4) fp32 [y0,x0,y1,x1) ; out (B,K,C,oh,ow)
+ * ---------------------------------------------------------------------------------------- */
+int msf_crop_resample_fwd(const void* feat, int64_t B, int C, int H, int W, const float* boxes, int K, int oh,
+                          int ow, int dtype, void* out, void* stream);
+/* grad_feat (B,C,H,W) fp32, must be zero-filled by the caller; accumulates with atomics. */
+int msf_crop_resample_bwd(const void* grad_out, int64_t B, int C, int H, int W, const float* boxes, int K, int oh,
+                          int ow, int dtype, float* grad_feat, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * E1  multi-tensor EMA  teacher <- m * teacher + (1 - m) * student   (extension: the reference
+ * keeps no momentum encoder, src/models/backbone.py:58-65; sized to its 60-tensor ResNet-18).
+ * `entries` and `chunk_prefix` are DEVICE arrays built once per parameter list:
+ * chunk_prefix[t] = number of MSF_EMA_CHUNK-element chunks in tensors [0, t), length n+1.
+ * msf_ema_plan fills a HOST chunk_prefix from HOST numels.
+ * ---------------------------------------------------------------------------------------- */
+#define MSF_EMA_CHUNK 8192
+typedef struct {
+  void* teacher;
+  const void* student;
+  int64_t numel;
+} msf_ema_entry;
+int msf_ema_plan(const int64_t* numels /*host*/, int n_tensors, int32_t* chunk_prefix /*host, n+1*/);
+int msf_ema_multi(const msf_ema_entry* entries /*device*/, const int32_t* chunk_prefix /*device*/, int n_tensors,
+                  int total_chunks, int teacher_dtype, int student_dtype, float momentum, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSFWSI_B200_H_ */

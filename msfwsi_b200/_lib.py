@@ -1,0 +1,110 @@
+"""ctypes binding of libmsfwsi_b200.so (the C ABI in include/msfwsi_b200.h).
+
+There is no CPU fallback: if the shared library is missing or a call fails this module
+raises, loudly.  Build it with ``python -m msfwsi_b200.build``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmsfwsi_b200.so")
+
+MSF_F32, MSF_BF16, MSF_F16 = 0, 1, 2
+MSF_GATHER_MAX_ITEMS = 16
+MSF_COS_MAX_PAIRS = 32
+MSF_EMA_CHUNK = 8192
+
+_DTYPE = {torch.float32: MSF_F32, torch.bfloat16: MSF_BF16, torch.float16: MSF_F16}
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    try:
+        return _DTYPE[dt]
+    except KeyError:
+        raise TypeError(f"msfwsi_b200 supports float32/bfloat16/float16 tensors, got {dt}") from None
+
+
+class GatherItem(C.Structure):
+    _fields_ = [("tgt_f", C.c_void_p), ("ctx_f", C.c_void_p), ("rev", C.c_void_p), ("tgt_sorted", C.c_void_p),
+                ("ms_f", C.c_void_p), ("d", C.c_int32), ("reserved", C.c_int32)]
+
+
+class GatherGradItem(C.Structure):
+    _fields_ = [("g_sorted", C.c_void_p), ("g_ms", C.c_void_p), ("rev", C.c_void_p), ("g_tgt_f", C.c_void_p),
+                ("g_ctx_f", C.c_void_p), ("d", C.c_int32), ("reserved", C.c_int32)]
+
+
+class CosPair(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("z", C.c_void_p), ("row_stats", C.c_void_p), ("grad_p", C.c_void_p),
+                ("rows", C.c_int64), ("dim", C.c_int32), ("coef", C.c_float)]
+
+
+class EmaEntry(C.Structure):
+    _fields_ = [("teacher", C.c_void_p), ("student", C.c_void_p), ("numel", C.c_int64)]
+
+
+_SIGS = {
+    "msf_abi_version": (C.c_int, []),
+    "msf_last_error": (C.c_char_p, []),
+    "msf_device_check": (C.c_int, [C.POINTER(C.c_int)] * 3),
+    "msf_gather_concat_fwd": (C.c_int, [C.POINTER(GatherItem), C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "msf_gather_concat_bwd": (C.c_int, [C.POINTER(GatherGradItem), C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "msf_cosine_loss_workspace_bytes": (C.c_size_t, [C.POINTER(CosPair), C.c_int]),
+    "msf_cosine_loss_fwd": (C.c_int, [C.POINTER(CosPair), C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "msf_cosine_loss_bwd": (C.c_int, [C.POINTER(CosPair), C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "msf_rownorm": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "msf_infonce_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int, C.c_int]),
+    "msf_infonce_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.c_float, C.c_int,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "msf_infonce_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.c_float,
+                                  C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]),
+    "msf_crop_resample_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.c_void_p, C.c_void_p]),
+    "msf_crop_resample_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.c_void_p, C.c_void_p]),
+    "msf_ema_plan": (C.c_int, [C.POINTER(C.c_int64), C.c_int, C.POINTER(C.c_int32)]),
+    "msf_ema_multi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+}
+EXPORTS = tuple(_SIGS)
+
+_lib = None
+launch_count = 0  # number of C-ABI compute calls made (bench.py reports kernel launches from it)
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: the CUDA extension is not built (run `python -m msfwsi_b200.build`). "
+                "msfwsi_b200 has no CPU or PyTorch fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(handle, name)  # AttributeError if the symbol is not exported
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().msf_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (status {rc}): {msg}")
+
+
+def stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def require_cuda(*tensors) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("msfwsi_b200 ops run on CUDA tensors only (there is no CPU fallback)")

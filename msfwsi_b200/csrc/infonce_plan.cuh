@@ -1,0 +1,73 @@
+// Work decomposition + workspace layout shared by the InfoNCE kernels (host side).
+#pragma once
+#include "common.cuh"
+
+namespace msf {
+
+struct NcePlan {
+  int tile_m;            // query rows per CTA
+  int tile_n;            // keys per inner tile
+  int64_t q_tiles;       // CTAs along the query rows
+  int64_t k_tiles;       // key tiles in total
+  int splits;            // key-range splits (partials are summed deterministically afterwards)
+  int64_t tiles_per_split;
+  int64_t nq_pad;        // q_tiles * tile_m
+  // workspace offsets in bytes
+  size_t off_rowsum;     // [splits][nq_pad] fp32   partial sum_j exp2(a*s_ij - c)
+  size_t off_o;          // [splits][nq_pad][dim] fp32 partial sum_j p_ij * k_hat_j
+  size_t off_pos;        // [nq] fp32 positive cosine s_ii
+  size_t off_sum;        // [nq] fp32 total row sum
+  size_t off_part;       // [part_cap] fp32 loss partials (one per finalize CTA)
+  size_t part_cap;
+  size_t total;
+};
+
+inline bool tc_dim_ok(int dim) { return dim == 64 || dim == 128 || dim == 256; }
+
+inline NcePlan make_nce_plan(int64_t nq, int64_t n_keys, int dim, int precision) {
+  NcePlan p{};
+  const bool tc = precision == MSF_BF16;
+  p.tile_m = tc ? 128 : 64;
+  p.tile_n = tc ? 128 : 64;
+  p.q_tiles = (nq + p.tile_m - 1) / p.tile_m;
+  p.k_tiles = (n_keys + p.tile_n - 1) / p.tile_n;
+  // choose the split count that minimises (waves x per-CTA tiles), the per-CTA prologue/epilogue
+  // counted as ~3 tile-times; ties go to fewer splits (less partial traffic)
+  int best = 1;
+  double best_cost = 1e300;
+  const int max_s = static_cast<int>(p.k_tiles < 32 ? (p.k_tiles > 0 ? p.k_tiles : 1) : 32);
+  for (int s = 1; s <= max_s; ++s) {
+    const int64_t per = (p.k_tiles + s - 1) / s;
+    const int64_t ctas = p.q_tiles * s;
+    const int64_t waves = (ctas + kNumSMs - 1) / kNumSMs;
+    const double cost = static_cast<double>(waves) * (static_cast<double>(per) + 3.0);
+    if (cost < best_cost * 0.999) {
+      best_cost = cost;
+      best = s;
+    }
+  }
+  p.splits = best;
+  p.tiles_per_split = (p.k_tiles + best - 1) / best;
+  p.nq_pad = p.q_tiles * p.tile_m;
+  auto align = [](size_t v) { return (v + 255) & ~static_cast<size_t>(255); };
+  size_t off = 0;
+  p.off_rowsum = off;
+  off = align(off + static_cast<size_t>(p.splits) * p.nq_pad * sizeof(float));
+  p.off_o = off;
+  off = align(off + static_cast<size_t>(p.splits) * p.nq_pad * dim * sizeof(float));
+  p.off_pos = off;
+  off = align(off + static_cast<size_t>(nq) * sizeof(float));
+  p.off_sum = off;
+  off = align(off + static_cast<size_t>(nq) * sizeof(float));
+  p.off_part = off;
+  p.part_cap = static_cast<size_t>(nq / 8 + 2);
+  off = align(off + p.part_cap * sizeof(float));
+  p.total = off;
+  return p;
+}
+
+// implemented in infonce_tc.cu: TMA + tcgen05/TMEM main loop (bf16 operands, dim in {64,128,256})
+int launch_infonce_tc(const void* q_hat, const void* k_hat, int64_t nq, int64_t n_keys, int dim, float tau,
+                      const NcePlan& plan, float* rowsum, float* o_part, cudaStream_t st);
+
+}  // namespace msf

@@ -1,0 +1,147 @@
+"""Drop-in for the reference's ``MSFWSI`` module (src/models/backbone.py:34-222) and the loss block of
+``train`` (tools/ssl_train.py:448-466).
+
+Same constructor, same ``forward(x1, x2, jigsaw_idx)`` signature and nested output, same
+parameter / buffer names (so ``convert_sync_batchnorm``, DDP, the ``context_/target_/inter_`` prefix
+filter of the optimizer at ssl_train.py:281-307 and checkpoints keep working).  What changes is the
+hot path after the encoder calls: the inverse-jigsaw gather + fuser concat run as one CUDA launch
+(``ops.gather_concat``) and the loss block as one fused launch (``ops.cosine_loss``) or the
+flash-style InfoNCE kernel (``ops.infonce_loss``).  Linear / BatchNorm1d of the heads stay on
+cuBLAS / ATen in this round (SURVEY 8f rank 1 is the next widening step).
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+PYRAMID_WIDTHS = (64, 128, 256, 512)  # pooled layer1..4 widths of the ResNet-18/34 encoders
+DEFAULT_FUSER_WEIGHTS = (0.1, 0.4, 0.7, 1.0)  # --fuser_weights default, tools/ssl_train.py:623-625
+
+
+def make_projector(in_dim: int, out_dim: int) -> nn.Sequential:
+    """3-layer projector, indices 0..7 as in backbone.py:12-22 (last BN has no affine)."""
+    layers = []
+    for width_out, affine, act in ((in_dim, True, True), (in_dim, True, True), (out_dim, False, False)):
+        layers.append(nn.Linear(in_dim, width_out, bias=False))
+        layers.append(nn.BatchNorm1d(width_out, affine=affine))
+        if act:
+            layers.append(nn.ReLU(inplace=True))
+    return nn.Sequential(*layers)
+
+
+def make_predictor(in_dim: int, hidden_dim: int) -> nn.Sequential:
+    """2-layer bottleneck predictor, indices 0..3 as in backbone.py:25-31."""
+    return nn.Sequential(nn.Linear(in_dim, hidden_dim, bias=False), nn.BatchNorm1d(hidden_dim), nn.ReLU(inplace=True),
+                         nn.Linear(hidden_dim, in_dim))
+
+
+def ssl_loss(outputs, fuser_weights: Sequence[float] = DEFAULT_FUSER_WEIGHTS, mode: str = "cosine", tau: float = 0.07,
+             group=None) -> torch.Tensor:
+    """The loss of ``train`` over the module's nested output.
+
+    mode="cosine"  -- reference-exact SimSiam negative cosine (ssl_train.py:448-466), ONE fused launch over
+                      all branches x levels x directions.
+    mode="infonce" -- extension: same (p, z) pairs, positives on the diagonal, global negatives (keys
+                      all-gathered over ``group``), temperature ``tau``; weights/0.5 factors as in cosine mode."""
+    ps, zs, coefs = [], [], []
+    for branch in outputs:
+        for lvl, (p1, p2, z1, z2) in enumerate(zip(*branch)):
+            ps += [p1, p2]
+            zs += [z2, z1]
+            coefs += [fuser_weights[lvl]] * 2
+    if mode == "cosine":
+        return ops.cosine_loss(ps, zs, [-0.5 * c for c in coefs])
+    if mode == "infonce":
+        total = None
+        for p, z, c in zip(ps, zs, coefs):
+            term = ops.infonce_loss(p, z, tau=tau, group=group) * (0.5 * c)
+            total = term if total is None else total + term
+        return total
+    raise ValueError(f"unknown loss mode {mode!r} (expected 'cosine' or 'infonce')")
+
+
+class MSFWSI(nn.Module):
+    """Multi-scale SSL model: two encoders + context / target / inter (fuser) heads."""
+
+    def __init__(self, base_encoder, scale, dim=2048, pred_dim=512, mask_ratio=0.5, use_checkpoint=False):
+        # ``dim`` / ``pred_dim`` are accepted and unused, exactly as in the reference (backbone.py:43-44)
+        super().__init__()
+        self.K = int(scale ** 2)
+        self.n_keep = int(self.K * (1 - mask_ratio))
+        self.context_encoder = base_encoder(zero_init_residual=True, pretrained=True, return_features=True)
+        self.target_encoder = base_encoder(zero_init_residual=True, pretrained=True, return_features=True)
+        self.context_encoder.fc = nn.Identity()
+        self.target_encoder.fc = nn.Identity()
+
+        self.inter_dim = torch.as_tensor(PYRAMID_WIDTHS)
+        self.ms_inter_dim = self.inter_dim * (self.n_keep + 1)
+        single = [int(d) for d in self.inter_dim]
+        fused = [int(d) for d in self.ms_inter_dim]
+        self.context_projector = nn.ModuleList(make_projector(d, d) for d in single)
+        self.target_projector = nn.ModuleList(make_projector(d, d) for d in single)
+        self.inter_projector = nn.ModuleList(make_projector(d, d) for d in fused)
+        self.context_predictor = nn.ModuleList(make_predictor(d, d // 4) for d in single)
+        self.target_predictor = nn.ModuleList(make_predictor(d, d // 4) for d in single)
+        self.inter_predictor = nn.ModuleList(make_predictor(d, d // 4) for d in fused)
+        self.validate_indices = False  # True: raise IndexError like the reference (costs a host sync)
+        if use_checkpoint:
+            self._apply_checkpoint()
+
+    def _apply_checkpoint(self):
+        from functools import partial
+
+        from torch.distributed.algorithms._checkpoint.checkpoint_wrapper import (CheckpointImpl, apply_activation_checkpointing,
+                                                                                  checkpoint_wrapper)
+        wrap = partial(checkpoint_wrapper, offload_to_cpu=False, checkpoint_impl=CheckpointImpl.NO_REENTRANT)
+        apply_activation_checkpointing(self, checkpoint_wrapper_fn=wrap,
+                                       check_fn=lambda m: isinstance(m, (nn.Conv2d, nn.Linear)))
+
+    # ---- hot path ----------------------------------------------------------------------------
+    def heads(self, context_f1, context_f2, target_f1, target_f2, jigsaw_idx):
+        """Everything after the encoder calls (backbone.py:147-222)."""
+        B, nl = context_f1[0].shape[0], len(context_f1)
+        dev = context_f1[0].device
+        if jigsaw_idx is None or len(jigsaw_idx) != 2:
+            raise AssertionError("jigsaw_idx must be [rev_view1, rev_view2]")
+        rev = [torch.as_tensor(r).to(device=dev, non_blocking=True) for r in jigsaw_idx]
+        for r in rev:
+            assert tuple(r.shape) == (B, self.K), "batch_idx.shape == jigsaw_idx shape"  # backbone.py:152
+        # one launch: un-shuffle 16 target vectors per sample + build the fuser inputs, 4 levels x 2 views
+        ctx_all = list(context_f1) + list(context_f2)
+        tgt_all = list(target_f1) + list(target_f2)
+        rev_all = [rev[0]] * nl + [rev[1]] * nl
+        sorted_all, ms_all = ops.gather_concat(ctx_all, tgt_all, rev_all, self.K, self.n_keep, self.validate_indices)
+        target_f1_sort, target_f2_sort = sorted_all[:nl], sorted_all[nl:]
+        ms_f1, ms_f2 = ms_all[:nl], ms_all[nl:]
+
+        def run(heads_, feats):
+            return tuple(h(f) for h, f in zip(heads_, feats))
+
+        context_z1, context_z2 = run(self.context_projector, context_f1), run(self.context_projector, context_f2)
+        target_z1, target_z2 = run(self.target_projector, target_f1_sort), run(self.target_projector, target_f2_sort)
+        context_p1, context_p2 = run(self.context_predictor, context_z1), run(self.context_predictor, context_z2)
+        target_p1, target_p2 = run(self.target_predictor, target_z1), run(self.target_predictor, target_z2)
+        ms_z1, ms_z2, ms_p1, ms_p2 = [], [], [], []
+        for i in range(nl):  # same call order as the reference so BN running stats see view 1 then view 2
+            ms_z1.append(self.inter_projector[i](ms_f1[i]))
+            ms_z2.append(self.inter_projector[i](ms_f2[i]))
+            ms_p1.append(self.inter_predictor[i](ms_z1[i]))
+            ms_p2.append(self.inter_predictor[i](ms_z2[i]))
+        det = lambda ts: tuple(t.detach() for t in ts)  # keys never receive gradient
+        return ((context_p1, context_p2, det(context_z1), det(context_z2)),
+                (target_p1, target_p2, det(target_z1), det(target_z2)),
+                (tuple(ms_p1), tuple(ms_p2), det(ms_z1), det(ms_z2)))
+
+    def forward(self, x1, x2, jigsaw_idx=None):
+        context_f1, context_f2 = self.context_encoder(x1[0]), self.context_encoder(x2[0])
+        target_f1, target_f2 = self.target_encoder(x1[1]), self.target_encoder(x2[1])
+        return self.heads(context_f1, context_f2, target_f1, target_f2, jigsaw_idx)
+
+    def forward_loss(self, x1, x2, jigsaw_idx, fuser_weights: Sequence[float] = DEFAULT_FUSER_WEIGHTS, mode: str = "cosine",
+                     tau: float = 0.07, group=None) -> torch.Tensor:
+        """``forward`` + the loss block of ssl_train.py:448-466 fused on the device (no .item() sync)."""
+        return ssl_loss(self.forward(x1, x2, jigsaw_idx), fuser_weights, mode, tau, group)

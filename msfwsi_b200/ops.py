@@ -1,0 +1,319 @@
+"""Host-side operators over the C ABI: torch.autograd.Functions that hand raw device pointers
+and the current CUDA stream to libmsfwsi_b200.so.  PyTorch is plumbing here (device memory,
+streams, autograd graph); every operator fails loudly without the CUDA library."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+
+COS_EPS = 1e-8  # nn.CosineSimilarity default (tools/ssl_train.py:422)
+
+
+def _contig(t: torch.Tensor) -> torch.Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------
+# A1: inverse-jigsaw gather + fuser concat      (src/models/backbone.py:147-158, 195-202)
+# ------------------------------------------------------------------------------------------
+class _GatherConcat(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, K: int, n_keep: int, n_items: int, validate: bool, *tensors):
+        ctx_f = [_contig(t) for t in tensors[:n_items]]
+        tgt_f = [_contig(t) for t in tensors[n_items:2 * n_items]]
+        rev = [_contig(t) for t in tensors[2 * n_items:3 * n_items]]
+        L.require_cuda(*ctx_f, *tgt_f, *rev)
+        dt = tgt_f[0].dtype
+        B = ctx_f[0].shape[0]
+        items = (L.GatherItem * n_items)()
+        outs_sorted, outs_ms = [], []
+        for i in range(n_items):
+            if tgt_f[i].dtype != dt or ctx_f[i].dtype != dt:
+                raise TypeError("gather_concat: all feature tensors must share one dtype")
+            d = ctx_f[i].shape[1]
+            if tgt_f[i].shape != (B * K, d) or ctx_f[i].shape != (B, d):
+                raise ValueError(f"gather_concat: item {i} has shapes {tuple(ctx_f[i].shape)} / {tuple(tgt_f[i].shape)}; "
+                                 f"expected ({B},{d}) / ({B * K},{d})")
+            if rev[i].shape != (B, K) or rev[i].dtype != torch.int64:
+                # the reference asserts batch_idx.shape == jigsaw_idx[v].shape (backbone.py:152)
+                raise AssertionError(f"jigsaw_idx must be int64 of shape ({B},{K}); got {rev[i].dtype} {tuple(rev[i].shape)}")
+            s = torch.empty_like(tgt_f[i])
+            m = torch.empty((B, (n_keep + 1) * d), dtype=dt, device=tgt_f[i].device)
+            outs_sorted.append(s)
+            outs_ms.append(m)
+            items[i] = L.GatherItem(L.ptr(tgt_f[i]), L.ptr(ctx_f[i]), L.ptr(rev[i]), L.ptr(s), L.ptr(m), d, 0)
+        flag = torch.zeros(1, dtype=torch.int32, device=tgt_f[0].device) if validate else None
+        L.check(L.lib().msf_gather_concat_fwd(items, n_items, B, K, n_keep, L.dtype_code(dt), L.ptr(flag), L.stream_ptr()),
+                "msf_gather_concat_fwd")
+        L.launch_count += 1
+        if validate and int(flag.item()) != 0:  # host sync: only on the validating path
+            raise IndexError(f"jigsaw_idx holds values outside [-{K}, {K})")
+        ctx.save_for_backward(*rev)
+        ctx.meta = (K, n_keep, n_items, B, dt, [t.shape[1] for t in ctx_f])
+        return (*outs_sorted, *outs_ms)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        K, n_keep, n_items, B, dt, dims = ctx.meta
+        rev = ctx.saved_tensors
+        g_sorted, g_ms = grads[:n_items], grads[n_items:]
+        items = (L.GatherGradItem * n_items)()
+        keep, g_ctx, g_tgt = [], [], []
+        for i in range(n_items):
+            gs = None if g_sorted[i] is None else _contig(g_sorted[i]).to(dt)
+            gm = None if g_ms[i] is None else _contig(g_ms[i]).to(dt)
+            keep += [gs, gm]
+            d = dims[i]
+            dev = rev[i].device
+            gt = torch.empty((B * K, d), dtype=dt, device=dev)
+            gc = torch.empty((B, d), dtype=dt, device=dev)
+            g_tgt.append(gt)
+            g_ctx.append(gc)
+            items[i] = L.GatherGradItem(L.ptr(gs), L.ptr(gm), L.ptr(rev[i]), L.ptr(gt), L.ptr(gc), d, 0)
+        L.check(L.lib().msf_gather_concat_bwd(items, n_items, B, K, n_keep, L.dtype_code(dt), L.stream_ptr()),
+                "msf_gather_concat_bwd")
+        L.launch_count += 1
+        return (None, None, None, None, *g_ctx, *g_tgt, *([None] * n_items))
+
+
+def gather_concat(ctx_f: Sequence[torch.Tensor], tgt_f: Sequence[torch.Tensor], rev: Sequence[torch.Tensor],
+                  K: int = 16, n_keep: int = 8, validate: bool = False):
+    """All items in one launch.  ``ctx_f[i]`` (B,d_i), ``tgt_f[i]`` (B*K,d_i) shuffled, ``rev[i]`` (B,K) int64
+    -> ``(tgt_sorted, ms_f)`` lists.  ``rev`` rows must be permutations (argsort(randperm), bcss.py:171-177)."""
+    n = len(ctx_f)
+    if not (n == len(tgt_f) == len(rev)) or n == 0 or n > L.MSF_GATHER_MAX_ITEMS:
+        raise ValueError("gather_concat: need 1..16 (ctx, tgt, rev) triples")
+    out = _GatherConcat.apply(K, n_keep, n, validate, *ctx_f, *tgt_f, *rev)
+    return list(out[:n]), list(out[n:])
+
+
+# ------------------------------------------------------------------------------------------
+# L1 cosine mode: the loss block of tools/ssl_train.py:448-466 in one launch
+# ------------------------------------------------------------------------------------------
+class _CosineLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, coefs: Tuple[float, ...], eps: float, *tensors):
+        n = len(coefs)
+        ps = [_contig(t) for t in tensors[:n]]
+        zs = [_contig(t.detach()) for t in tensors[n:]]
+        L.require_cuda(*ps, *zs)
+        dts = {t.dtype for t in ps} | {t.dtype for t in zs}
+        dt = ps[0].dtype if len(dts) == 1 else torch.float32  # mixed inputs: exact up-cast, fp32 kernel
+        ps_k = [t.to(dt) for t in ps]
+        zs_k = [t.to(dt) for t in zs]
+        dev = ps[0].device
+        pairs = (L.CosPair * n)()
+        total_rows = sum(p.shape[0] for p in ps_k)
+        stats = torch.empty((max(total_rows, 1), 4), dtype=torch.float32, device=dev)
+        off = 0
+        for i in range(n):
+            if ps_k[i].shape != zs_k[i].shape or ps_k[i].dim() != 2:
+                raise ValueError(f"cosine_loss: pair {i} shapes {tuple(ps_k[i].shape)} vs {tuple(zs_k[i].shape)}")
+            rows, dim = ps_k[i].shape
+            pairs[i] = L.CosPair(L.ptr(ps_k[i]), L.ptr(zs_k[i]), stats[off:].data_ptr(), 0, rows, dim, float(coefs[i]))
+            off += rows
+        ws_bytes = L.lib().msf_cosine_loss_workspace_bytes(pairs, n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        L.check(L.lib().msf_cosine_loss_fwd(pairs, n, L.dtype_code(dt), eps, L.ptr(loss), L.ptr(ws), ws_bytes, L.stream_ptr()),
+                "msf_cosine_loss_fwd")
+        L.launch_count += 2
+        ctx.save_for_backward(stats, *ps_k, *zs_k)
+        ctx.meta = (coefs, n, dt, [t.dtype for t in ps])
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        coefs, n, dt, orig_dt = ctx.meta
+        stats, *rest = ctx.saved_tensors
+        ps, zs = rest[:n], rest[n:]
+        g = _contig(grad_out.to(torch.float32))
+        pairs = (L.CosPair * n)()
+        grads = []
+        off = 0
+        for i in range(n):
+            rows, dim = ps[i].shape
+            gp = torch.empty_like(ps[i])
+            grads.append(gp)
+            pairs[i] = L.CosPair(L.ptr(ps[i]), L.ptr(zs[i]), stats[off:].data_ptr(), L.ptr(gp), rows, dim, float(coefs[i]))
+            off += rows
+        L.check(L.lib().msf_cosine_loss_bwd(pairs, n, L.dtype_code(dt), L.ptr(g), L.stream_ptr()), "msf_cosine_loss_bwd")
+        L.launch_count += 1
+        grads = [gp.to(orig_dt[i]) for i, gp in enumerate(grads)]
+        return (None, None, *grads, *([None] * n))
+
+
+def cosine_loss(ps: Sequence[torch.Tensor], zs: Sequence[torch.Tensor], coefs: Sequence[float], eps: float = COS_EPS):
+    """``sum_i coefs[i] * mean_rows cos(ps[i], zs[i])`` (fp32 scalar); zs are treated as detached."""
+    n = len(ps)
+    if not (n == len(zs) == len(coefs)) or n == 0 or n > L.MSF_COS_MAX_PAIRS:
+        raise ValueError("cosine_loss: need 1..32 (p, z, coef) triples")
+    return _CosineLoss.apply(tuple(float(c) for c in coefs), float(eps), *ps, *zs)
+
+
+# ------------------------------------------------------------------------------------------
+# L1 infonce mode (extension): fused flash-style InfoNCE with global negatives
+# ------------------------------------------------------------------------------------------
+def rownorm(x: torch.Tensor, out_dtype: torch.dtype, eps: float = COS_EPS):
+    """x (rows, dim) -> (x / max(||x||, eps) in out_dtype, 1/max(||x||, eps) fp32)."""
+    x = _contig(x)
+    L.require_cuda(x)
+    rows, dim = x.shape
+    xh = torch.empty((rows, dim), dtype=out_dtype, device=x.device)
+    inv = torch.empty((rows,), dtype=torch.float32, device=x.device)
+    L.check(L.lib().msf_rownorm(L.ptr(x), rows, dim, L.dtype_code(x.dtype), eps, L.ptr(xh), L.dtype_code(out_dtype), L.ptr(inv),
+                                L.stream_ptr()), "msf_rownorm")
+    L.launch_count += 1
+    return xh, inv
+
+
+def infonce_precision_for(dim: int, dtype: torch.dtype) -> torch.dtype:
+    """bf16 tcgen05 path where it exists (16-bit inputs, dim in {64,128,256}); fp32 SIMT otherwise."""
+    return torch.bfloat16 if (dtype in (torch.bfloat16, torch.float16) and dim in (64, 128, 256)) else torch.float32
+
+
+def all_gather_keys(k_hat: torch.Tensor, group=None) -> Tuple[torch.Tensor, int]:
+    """Rank-major all-gather of the normalised keys.  Returns (keys_all, pos_offset)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return k_hat, 0
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    out = torch.empty((world * k_hat.shape[0], k_hat.shape[1]), dtype=k_hat.dtype, device=k_hat.device)
+    dist.all_gather_into_tensor(out, k_hat, group=group)
+    return out, rank * k_hat.shape[0]
+
+
+class _InfoNCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p, z, tau: float, precision: torch.dtype, eps: float, group):
+        L.require_cuda(p, z)
+        if p.dim() != 2 or p.shape != z.shape:
+            raise ValueError(f"infonce: p {tuple(p.shape)} and z {tuple(z.shape)} must be equal 2-D shapes")
+        nq, dim = p.shape
+        q_hat, q_inv = rownorm(p, precision, eps)
+        k_hat, _ = rownorm(z.detach(), precision, eps)
+        k_all, pos_offset = all_gather_keys(k_hat, group)
+        n_keys = k_all.shape[0]
+        prec = L.dtype_code(precision)
+        ws_bytes = L.lib().msf_infonce_workspace_bytes(nq, n_keys, dim, prec)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=p.device)
+        loss_sum = torch.empty((), dtype=torch.float32, device=p.device)
+        L.check(L.lib().msf_infonce_fwd(L.ptr(q_hat), L.ptr(k_all), nq, n_keys, dim, pos_offset, tau, prec, L.ptr(loss_sum), 0,
+                                        L.ptr(ws), ws_bytes, L.stream_ptr()), "msf_infonce_fwd")
+        L.launch_count += 3
+        ctx.save_for_backward(q_hat, k_all, q_inv, ws)
+        ctx.meta = (nq, n_keys, dim, pos_offset, tau, prec, ws_bytes, p.dtype)
+        return loss_sum / nq  # per-rank mean, like the reference's per-rank .mean() under DDP
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        nq, n_keys, dim, pos_offset, tau, prec, ws_bytes, p_dtype = ctx.meta
+        q_hat, k_all, q_inv, ws = ctx.saved_tensors
+        g = _contig(grad_out.to(torch.float32))
+        grad_q = torch.empty((nq, dim), dtype=p_dtype, device=q_hat.device)
+        L.check(L.lib().msf_infonce_bwd(L.ptr(q_hat), L.ptr(k_all), L.ptr(q_inv), nq, n_keys, dim, pos_offset, tau, prec, L.ptr(g),
+                                        1.0 / nq, L.ptr(ws), ws_bytes, L.ptr(grad_q), L.dtype_code(p_dtype), L.stream_ptr()),
+                "msf_infonce_bwd")
+        L.launch_count += 1
+        return grad_q, None, None, None, None, None
+
+
+def infonce_loss(p: torch.Tensor, z: torch.Tensor, tau: float = 0.07, precision: Optional[torch.dtype] = None,
+                 eps: float = COS_EPS, group=None) -> torch.Tensor:
+    """mean_i [logsumexp_j(p_hat_i . z_hat_j / tau) - p_hat_i . z_hat_pos(i) / tau] with keys all-gathered over
+    ``group`` (rank-major) and detached.  Positive of local row i on rank r is global row r*rows+i."""
+    if precision is None:
+        precision = infonce_precision_for(p.shape[1], p.dtype)
+    return _InfoNCE.apply(p, z, float(tau), precision, float(eps), group)
+
+
+# ------------------------------------------------------------------------------------------
+# A2: crop + bilinear resample            (integer case: src/models/hooknet.py:29-32)
+# ------------------------------------------------------------------------------------------
+class _CropResample(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, boxes, oh: int, ow: int):
+        feat = _contig(feat)
+        boxes = _contig(boxes.to(torch.float32))
+        L.require_cuda(feat, boxes)
+        B, Cc, H, W = feat.shape
+        if boxes.dim() != 3 or boxes.shape[0] != B or boxes.shape[2] != 4:
+            raise ValueError(f"crop_resample: boxes must be (B,K,4); got {tuple(boxes.shape)}")
+        K = boxes.shape[1]
+        out = torch.empty((B, K, Cc, oh, ow), dtype=feat.dtype, device=feat.device)
+        L.check(L.lib().msf_crop_resample_fwd(L.ptr(feat), B, Cc, H, W, L.ptr(boxes), K, oh, ow, L.dtype_code(feat.dtype), L.ptr(out),
+                                              L.stream_ptr()), "msf_crop_resample_fwd")
+        L.launch_count += 1
+        ctx.save_for_backward(boxes)
+        ctx.meta = (B, Cc, H, W, K, oh, ow, feat.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        B, Cc, H, W, K, oh, ow, dt = ctx.meta
+        (boxes,) = ctx.saved_tensors
+        go = _contig(grad_out.to(dt))
+        gfeat = torch.zeros((B, Cc, H, W), dtype=torch.float32, device=go.device)
+        L.check(L.lib().msf_crop_resample_bwd(L.ptr(go), B, Cc, H, W, L.ptr(boxes), K, oh, ow, L.dtype_code(dt), L.ptr(gfeat),
+                                              L.stream_ptr()), "msf_crop_resample_bwd")
+        L.launch_count += 1
+        return gfeat.to(dt), None, None, None
+
+
+def crop_resample(feat: torch.Tensor, boxes: torch.Tensor, out_hw: Tuple[int, int]) -> torch.Tensor:
+    """feat (B,C,H,W), boxes (B,K,4) [y0,x0,y1,x1) -> (B,K,C,oh,ow)."""
+    return _CropResample.apply(feat, boxes, int(out_hw[0]), int(out_hw[1]))
+
+
+def footprint_boxes(B: int, scale: int, H: int, W: int, device) -> torch.Tensor:
+    """Footprints of the scale x scale high-magnification tiles on a low-magnification (H,W) map, in the raster
+    order of ``blockshaped`` (src/utils/data/bcss.py:203-216): tile t -> rows [H/scale*(t//scale), +H/scale)."""
+    th, tw = H / scale, W / scale
+    t = torch.arange(scale * scale, device=device)
+    y0 = (t // scale).to(torch.float32) * th
+    x0 = (t % scale).to(torch.float32) * tw
+    box = torch.stack((y0, x0, y0 + th, x0 + tw), dim=1)
+    return box.unsqueeze(0).expand(B, -1, -1).contiguous()
+
+
+# ------------------------------------------------------------------------------------------
+# E1: multi-tensor EMA (extension)
+# ------------------------------------------------------------------------------------------
+class EmaUpdater:
+    """``teacher <- m * teacher + (1 - m) * student`` over a fixed parameter list, one launch per step.
+    The device-side tensor table is built once here."""
+
+    def __init__(self, teacher: Sequence[torch.Tensor], student: Sequence[torch.Tensor]):
+        teacher, student = list(teacher), list(student)
+        if len(teacher) != len(student) or not teacher:
+            raise ValueError("EmaUpdater: need equally long, non-empty tensor lists")
+        L.require_cuda(*teacher, *student)
+        self.tdt, self.sdt = teacher[0].dtype, student[0].dtype
+        n = len(teacher)
+        numels = (C.c_int64 * n)()
+        for i, (t, s) in enumerate(zip(teacher, student)):
+            if t.shape != s.shape or t.dtype != self.tdt or s.dtype != self.sdt:
+                raise ValueError(f"EmaUpdater: tensor {i} shape/dtype mismatch")
+            if not (t.is_contiguous() and s.is_contiguous()):
+                raise ValueError(f"EmaUpdater: tensor {i} must be contiguous")
+            numels[i] = t.numel()
+        prefix = (C.c_int32 * (n + 1))()
+        L.check(L.lib().msf_ema_plan(numels, n, prefix), "msf_ema_plan")
+        self.n, self.total_chunks = n, int(prefix[n])
+        table = torch.empty((n, 3), dtype=torch.int64)
+        for i, (t, s) in enumerate(zip(teacher, student)):
+            table[i, 0], table[i, 1], table[i, 2] = t.data_ptr(), s.data_ptr(), t.numel()
+        dev = teacher[0].device
+        self._table = table.to(dev)
+        self._prefix = torch.tensor(list(prefix), dtype=torch.int32, device=dev)
+        self._keep = (teacher, student)  # the table holds raw pointers: keep the tensors alive
+        self.numel = int(sum(numels))
+
+    def step(self, momentum: float) -> None:
+        L.check(L.lib().msf_ema_multi(L.ptr(self._table), L.ptr(self._prefix), self.n, self.total_chunks, L.dtype_code(self.tdt),
+                                      L.dtype_code(self.sdt), float(momentum), L.stream_ptr()), "msf_ema_multi")
+        L.launch_count += 1

@@ -172,6 +172,15 @@ def main():
     x = O.closed_form_tensor((2, 128, 32, 32), 5.0, 1.0)
     crop = x[:, :, 16 - 4: 16 + 4, 16 - 4: 16 + 4]
     np.savez_compressed(os.path.join(args.out, "hooknet_crop.npz"), x_salt=np.float64(5.0), crop=crop.numpy())
+    # state-dict key/shape contract of the full reference module (real ResNet-18 encoders,
+    # pretrained=False wrapper because the hard-coded pretrained=True cannot download offline)
+    import json
+    from src.models import resnet as ref_resnet
+    full = MSFWSI(lambda **kw: ref_resnet.resnet18(**{**kw, "pretrained": False}), 4, 2048, 512, 0.5, False)
+    contract = {k: list(v.shape) for k, v in full.state_dict().items()}
+    with open(os.path.join(args.out, "state_dict_contract.json"), "w") as fh:
+        json.dump({"n_params": sum(p.numel() for p in full.parameters()), "n_param_tensors": len(list(full.parameters())),
+                   "state_dict": contract}, fh, indent=0)
     print("wrote", sorted(os.listdir(args.out)))
     print("loss fp64", loss.item(), "loss fp32", gold["loss_fp32"])
 

@@ -1,0 +1,69 @@
+"""Drop-in contract of msfwsi_b200.MSFWSI against the reference's state-dict (fixture generated from the
+unmodified reference module by oracle/make_golden.py) and the optimizer prefix filter of ssl_train.py:281-307."""
+import json
+import os
+import warnings
+
+import pytest
+import torch
+
+import msfwsi_b200 as M
+
+
+@pytest.fixture(scope="module")
+def model():
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return M.MSFWSI(M.resnet18, 4, 2048, 512, 0.5, False)
+
+
+def test_state_dict_contract_matches_reference(model, golden_dir):
+    ref = json.load(open(os.path.join(golden_dir, "state_dict_contract.json")))
+    mine = {k: list(v.shape) for k, v in model.state_dict().items()}
+    assert mine == ref["state_dict"]
+    assert sum(p.numel() for p in model.parameters()) == ref["n_params"] == 123551584
+    assert len(list(model.parameters())) == ref["n_param_tensors"] == 264
+
+
+def test_optimizer_prefix_filter_covers_every_parameter(model):
+    # tools/ssl_train.py:281-307 builds three Adam groups by name prefix and drops anything else
+    names = [n for n, _ in model.named_parameters()]
+    assert all(n.startswith(("context_", "target_", "inter_")) for n in names)
+
+
+def test_constructor_semantics(model):
+    assert model.K == 16 and model.n_keep == 8
+    assert [int(d) for d in model.ms_inter_dim] == [576, 1152, 2304, 4608]
+    assert isinstance(model.context_encoder.fc, torch.nn.Identity)
+    m2 = M.MSFWSI(lambda **kw: M.resnet18(**{**kw, "pretrained": False}), 2, mask_ratio=0.25)
+    assert m2.K == 4 and m2.n_keep == 3
+
+
+def test_survives_sync_batchnorm_conversion(model):
+    import copy
+    conv = torch.nn.SyncBatchNorm.convert_sync_batchnorm(copy.deepcopy(model))
+    n_sync = sum(isinstance(m, torch.nn.SyncBatchNorm) for m in conv.modules())
+    assert n_sync == 88  # 48 in the heads + 40 in the encoders
+    assert set(conv.state_dict()) == set(model.state_dict())
+
+
+def test_encoder_feature_contract():
+    enc = M.resnet18(return_features=True, zero_init_residual=True)
+    enc.fc = torch.nn.Identity()
+    enc.eval()
+    with torch.no_grad():
+        feats = enc(torch.randn(2, 3, 64, 64))
+    assert [tuple(f.shape) for f in feats] == [(2, 64), (2, 128), (2, 256), (2, 512)]
+    assert all((f >= 0).all() for f in feats)  # pooled post-ReLU maps
+
+
+def test_forward_requires_cuda_library_path(model):
+    x = (torch.randn(2, 3, 64, 64), torch.randn(32, 3, 64, 64))
+    rev = [torch.arange(16).repeat(2, 1), torch.arange(16).repeat(2, 1)]
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model(x, x, rev)  # the hot path has no CPU fallback
+
+
+def test_bad_loss_mode():
+    with pytest.raises(ValueError):
+        M.ssl_loss((), mode="nope")
