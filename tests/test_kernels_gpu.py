@@ -127,10 +127,11 @@ def test_cosine_loss_and_grad_vs_oracle(dtype, tol, rows, dim):
     z = base.to(dtype)
     pd = p.to(DEV).requires_grad_(True)
     loss = ops.cosine_loss([pd], [z.to(DEV)], [-0.35])
-    (loss * 3.0).backward()  # non-unit upstream gradient (GradScaler, ssl_train.py:472)
+    up = 3.0 * rows  # non-unit upstream gradient (GradScaler, ssl_train.py:472); keeps fp16 grads out of the subnormals
+    (loss * up).backward()
     ref = -0.35 * O.cosine_rows(p.double(), z.double()).mean()  # same (rounded) inputs, fp64 arithmetic
     assert abs(loss.item() - ref.item()) <= tol * abs(ref.item())
-    gref = 3.0 * O.cosine_loss_grad(p.double(), z.double(), -0.35)
+    gref = up * O.cosine_loss_grad(p.double(), z.double(), -0.35)
     assert _cos(pd.grad, gref) >= 0.9999
     if dtype == torch.float32:
         assert torch.allclose(pd.grad.cpu().double(), gref, rtol=1e-4, atol=1e-9)
@@ -306,3 +307,47 @@ def test_ema_unaligned_views():
     ops.EmaUpdater(teacher, student).step(0.9)
     for t, r in zip(teacher, ref):
         assert torch.equal(t, r)
+
+
+# ------------------------------------------------------------------ InfoNCE bf16 tcgen05 path
+@pytest.mark.parametrize("nq,n,dim,off", [(128, 128, 64, 0), (128, 128, 128, 0), (128, 128, 256, 0), (256, 1024, 128, 512),
+                                           (100, 257, 64, 31), (1000, 3000, 256, 2000), (4096, 4096, 128, 0), (4096, 4096, 256, 0),
+                                           (2048, 16384, 64, 8192), (5, 5, 128, 0)])
+def test_infonce_bf16_tensor_core_vs_oracle(nq, n, dim, off):
+    tau = 0.07
+    q, k = _nce_inputs(nq, n, dim, 31, torch.bfloat16)
+    if off:
+        k[off:off + nq] = k[:nq].clone()
+    q_hat, q_inv = ops.rownorm(q.to(DEV), torch.bfloat16)
+    k_hat, _ = ops.rownorm(k.to(DEV), torch.bfloat16)
+    prec = L.MSF_BF16
+    ws_bytes = L.lib().msf_infonce_workspace_bytes(nq, n, dim, prec)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=DEV)
+    loss_sum = torch.empty((), dtype=torch.float32, device=DEV)
+    lse = torch.empty(nq, dtype=torch.float32, device=DEV)
+    L.check(L.lib().msf_infonce_fwd(q_hat.data_ptr(), k_hat.data_ptr(), nq, n, dim, off, tau, prec, loss_sum.data_ptr(),
+                                    lse.data_ptr(), ws.data_ptr(), ws_bytes, L.stream_ptr()), "fwd")
+    torch.cuda.synchronize()
+    ref_loss, _, ref_lse = O.infonce_loss(q.double(), k.double(), tau, pos_offset=off)
+    assert abs(loss_sum.item() / nq - ref_loss.item()) <= 2e-3 * abs(ref_loss.item()), (loss_sum.item() / nq, ref_loss.item())
+    assert torch.allclose(lse.cpu().double(), ref_lse, rtol=2e-3, atol=2e-2)
+    g = torch.full((), 1.0, device=DEV)
+    grad = torch.empty((nq, dim), dtype=torch.float32, device=DEV)
+    L.check(L.lib().msf_infonce_bwd(q_hat.data_ptr(), k_hat.data_ptr(), q_inv.data_ptr(), nq, n, dim, off, tau, prec, g.data_ptr(),
+                                    1.0 / nq, ws.data_ptr(), ws_bytes, grad.data_ptr(), L.MSF_F32, L.stream_ptr()), "bwd")
+    gref = O.infonce_grad(q.double(), k.double(), tau, off)
+    assert _cos(grad, gref) >= 0.9999, _cos(grad, gref)
+
+
+def test_infonce_bf16_autograd_entry_and_determinism():
+    nq, dim, tau = 1024, 128, 0.07
+    q, k = _nce_inputs(nq, nq, dim, 41, torch.bfloat16)
+    qd = q.to(DEV).requires_grad_(True)
+    l1 = ops.infonce_loss(qd, k.to(DEV), tau=tau)
+    l1.backward()
+    l2 = ops.infonce_loss(qd.detach(), k.to(DEV), tau=tau)
+    assert l1.item() == l2.item()
+    ref, _, _ = O.infonce_loss(q.double(), k.double(), tau)
+    assert abs(l1.item() - ref.item()) <= 2e-3 * abs(ref.item())
+    assert qd.grad.dtype == torch.bfloat16
+    assert _cos(qd.grad, O.infonce_grad(q.double(), k.double(), tau)) >= 0.9999
