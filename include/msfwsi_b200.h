@@ -135,6 +135,10 @@ int msf_rownorm(const void* x, int64_t rows, int dim, int in_dtype, float eps, v
                 float* inv_norm, void* stream);
 
 size_t msf_infonce_workspace_bytes(int64_t nq, int64_t n_keys, int dim, int precision);
+/* Workspace layout for inspection / tests: info[0]=splits, [1]=nq_pad, [2]=byte offset of the fp32 row-sum
+ * partials [splits][nq_pad], [3]=byte offset of the fp32 O partials [splits][nq_pad][dim], [4]=offset of the
+ * positive cosines [nq], [5]=offset of the total row sums [nq], [6]=query rows per CTA, [7]=keys per tile. */
+int msf_infonce_plan_info(int64_t nq, int64_t n_keys, int dim, int precision, int64_t* info /*host, 8*/);
 /* loss_sum_out: device fp32 scalar that receives sum_i row_loss_i (NOT divided; the caller
  * divides by the global row count).  row_lse (nq) may be NULL. */
 int msf_infonce_fwd(const void* q_hat, const void* k_hat, int64_t nq, int64_t n_keys, int dim,
@@ -173,8 +177,11 @@ typedef struct {
   int64_t numel;
 } msf_ema_entry;
 int msf_ema_plan(const int64_t* numels /*host*/, int n_tensors, int32_t* chunk_prefix /*host, n+1*/);
+/* `one_minus_momentum` is passed separately so the caller controls its rounding (torch evaluates 1-m in
+ * double before narrowing); the kernel computes fma(one_minus_momentum, student, rn(momentum*teacher)). */
 int msf_ema_multi(const msf_ema_entry* entries /*device*/, const int32_t* chunk_prefix /*device*/, int n_tensors,
-                  int total_chunks, int teacher_dtype, int student_dtype, float momentum, void* stream);
+                  int total_chunks, int teacher_dtype, int student_dtype, float momentum, float one_minus_momentum,
+                  void* stream);
 
 #ifdef __cplusplus
 }

@@ -114,13 +114,13 @@ extern "C" int msf_ema_plan(const int64_t* numels, int n_tensors, int32_t* chunk
 }
 
 extern "C" int msf_ema_multi(const msf_ema_entry* entries, const int32_t* chunk_prefix, int n_tensors, int total_chunks,
-                             int teacher_dtype, int student_dtype, float momentum, void* stream) {
+                             int teacher_dtype, int student_dtype, float momentum, float one_minus_momentum, void* stream) {
   MSF_REQUIRE(n_tensors >= 0 && total_chunks >= 0, MSF_ERR_INVALID, "negative sizes");
   if (n_tensors == 0 || total_chunks == 0) return MSF_OK;
   MSF_REQUIRE(entries && chunk_prefix, MSF_ERR_INVALID, "NULL table");
   MSF_REQUIRE(dtype_ok(teacher_dtype) && dtype_ok(student_dtype), MSF_ERR_INVALID, "bad dtype");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const float m = momentum, om = 1.0f - momentum;
+  const float m = momentum, om = one_minus_momentum;
 #define MSF_EMA_CASE(T, S)                                                                                   \
   if (teacher_dtype == T && student_dtype == S) {                                                            \
     ema_kernel<T, S><<<total_chunks, kThreads, 0, st>>>(entries, chunk_prefix, n_tensors, m, om);            \

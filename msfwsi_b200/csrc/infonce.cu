@@ -345,6 +345,14 @@ extern "C" size_t msf_infonce_workspace_bytes(int64_t nq, int64_t n_keys, int di
   return make_nce_plan(nq, n_keys, dim, precision).total;
 }
 
+extern "C" int msf_infonce_plan_info(int64_t nq, int64_t n_keys, int dim, int precision, int64_t* info) {
+  MSF_REQUIRE(info && nq > 0 && n_keys > 0 && dim > 0, MSF_ERR_INVALID, "bad arguments");
+  const NcePlan p = make_nce_plan(nq, n_keys, dim, precision);
+  info[0] = p.splits; info[1] = p.nq_pad; info[2] = static_cast<int64_t>(p.off_rowsum); info[3] = static_cast<int64_t>(p.off_o);
+  info[4] = static_cast<int64_t>(p.off_pos); info[5] = static_cast<int64_t>(p.off_sum); info[6] = p.tile_m; info[7] = p.tile_n;
+  return MSF_OK;
+}
+
 extern "C" int msf_infonce_fwd(const void* q_hat, const void* k_hat, int64_t nq, int64_t n_keys, int dim,
                                int64_t pos_offset, float tau, int precision, float* loss_sum_out, float* row_lse,
                                void* workspace, size_t workspace_bytes, void* stream) {

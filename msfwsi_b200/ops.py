@@ -315,5 +315,5 @@ class EmaUpdater:
 
     def step(self, momentum: float) -> None:
         L.check(L.lib().msf_ema_multi(L.ptr(self._table), L.ptr(self._prefix), self.n, self.total_chunks, L.dtype_code(self.tdt),
-                                      L.dtype_code(self.sdt), float(momentum), L.stream_ptr()), "msf_ema_multi")
+                                      L.dtype_code(self.sdt), float(momentum), float(1.0 - float(momentum)), L.stream_ptr()), "msf_ema_multi")
         L.launch_count += 1

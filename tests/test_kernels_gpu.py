@@ -20,6 +20,11 @@ def _cos(a, b):
     return float((a @ b) / (a.norm() * b.norm() + 1e-300))
 
 
+def _relerr(a, b):
+    a, b = a.double().flatten().cpu(), b.double().flatten().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-300))
+
+
 def _rand(shape, seed, dtype=torch.float32, scale=1.0):
     g = torch.Generator().manual_seed(seed)
     return (torch.randn(*shape, generator=g) * scale).to(dtype)
@@ -134,7 +139,7 @@ def test_cosine_loss_and_grad_vs_oracle(dtype, tol, rows, dim):
     gref = up * O.cosine_loss_grad(p.double(), z.double(), -0.35)
     assert _cos(pd.grad, gref) >= 0.9999
     if dtype == torch.float32:
-        assert torch.allclose(pd.grad.cpu().double(), gref, rtol=1e-4, atol=1e-9)
+        assert _relerr(pd.grad, gref) <= 1e-5
 
 
 def test_cosine_loss_many_pairs_zero_rows_and_determinism():
@@ -182,7 +187,7 @@ def test_rownorm(in_dtype, out_dtype, rows, dim):
 
 def _nce_inputs(nq, n, dim, seed, dtype=torch.float32):
     k = _rand((n, dim), seed)
-    q = k[:nq] + 0.5 * _rand((nq, dim), seed + 1)  # positives correlated: loss in a realistic 1-6 nat range
+    q = 0.3 * k[:nq] + _rand((nq, dim), seed + 1)  # weakly correlated positives: loss in a realistic 1-6 nat range
     return q.to(dtype), k.to(dtype)
 
 
@@ -204,7 +209,8 @@ def test_infonce_fp32_vs_oracle(nq, n, dim, off):
     L.check(L.lib().msf_infonce_fwd(q_hat.data_ptr(), k_hat.data_ptr(), nq, n, dim, off, tau, prec, loss_sum.data_ptr(),
                                     lse.data_ptr(), ws.data_ptr(), ws_bytes, L.stream_ptr()), "fwd")
     ref_loss, ref_rows, ref_lse = O.infonce_loss(q.double(), k.double(), tau, pos_offset=off)
-    assert abs(loss_sum.item() / nq - ref_loss.item()) <= 1e-5 * abs(ref_loss.item())
+    # logits are O(1/tau) = 14: fp32 rounding of lse - pos is ~1e-6 absolute, so tiny losses (N = 8) get a floor
+    assert abs(loss_sum.item() / nq - ref_loss.item()) <= 1e-5 * max(abs(ref_loss.item()), 0.5)
     assert torch.allclose(lse.cpu().double(), ref_lse, rtol=1e-5, atol=1e-5)
     g = torch.full((), 2.0, device=DEV)
     grad = torch.empty_like(q_hat)
@@ -212,7 +218,7 @@ def test_infonce_fp32_vs_oracle(nq, n, dim, off):
                                     1.0 / nq, ws.data_ptr(), ws_bytes, grad.data_ptr(), L.MSF_F32, L.stream_ptr()), "bwd")
     gref = 2.0 * O.infonce_grad(q.double(), k.double(), tau, off)
     assert _cos(grad, gref) >= 0.9999
-    assert torch.allclose(grad.cpu().double(), gref, rtol=2e-3, atol=1e-7 * float(gref.abs().max()) + 1e-12)
+    assert _relerr(grad, gref) <= 1e-4
 
 
 def test_infonce_autograd_entry_fp32_and_cosine_anchor():

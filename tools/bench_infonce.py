@@ -41,7 +41,7 @@ def main():
         for n in args.n:
             g = torch.Generator(device=dev).manual_seed(3407)
             k = torch.randn(n, d, device=dev, generator=g)
-            q = (k + 0.5 * torch.randn(n, d, device=dev, generator=g)).to(torch.bfloat16)
+            q = (0.3 * k + torch.randn(n, d, device=dev, generator=g)).to(torch.bfloat16)
             k = k.to(torch.bfloat16)
             q_hat, q_inv = ops.rownorm(q, torch.bfloat16)
             k_hat, _ = ops.rownorm(k, torch.bfloat16)
