@@ -1,0 +1,352 @@
+"""bench.py -- SSL pre-training tiles/s of the MSF-WSI hot path on N B200s (+ roofline of the fused InfoNCE kernel).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's arm (one rank per GPU under torchrun for N>1)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle port) on host cores
+
+A "step" is one full pre-training step of BASELINE.json configs[1] (BCSS-shaped, per-GPU batch 256, bf16 autocast,
+synthetic 1024^2-tile-shaped inputs: 2 context + 32 target 224^2 views and 2 jigsaw index rows per tile):
+ResNet-18 encoders on PyTorch/cuDNN (not a CUDA target of this repo) -> hot path (gather/concat kernel, heads,
+fused loss kernel) -> backward -> Adam.  `value` times K steps with inputs resident in HBM; `e2e` times the same
+step fed from pinned host memory with the loss read back every step.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ssl_pretrain_tiles_per_sec"
+UNIT = "tiles/s"
+FUSER_WEIGHTS = (0.1, 0.4, 0.7, 1.0)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch in tiles (configs[1]: 256)")
+    ap.add_argument("--img", type=int, default=224)
+    ap.add_argument("--loss", default="infonce", choices=["infonce", "cosine"],
+                    help="infonce = north_star objective (extension); cosine = reference-exact SimSiam loss")
+    ap.add_argument("--tau", type=float, default=0.07)
+    ap.add_argument("--cpu-sample", type=int, default=4, help="tiles per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-microbench", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(args):
+    return (f"BCSS fold-0 SSL pretraining bf16, batch {args.batch}/GPU, synthetic L0_1024_s512-shaped tiles "
+            f"(2x(3,{args.img},{args.img}) context + 2x(16,3,{args.img},{args.img}) target views), loss={args.loss}")
+
+
+# ------------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port on host cores
+# ------------------------------------------------------------------------------------------------------------
+def run_cpu_port(sample_tiles, steps, warmup, loss, tau, img):
+    from oracle.cpu_step import CpuReferenceStep  # the one place bench.py executes oracle/
+    port = CpuReferenceStep(sample_tiles, img=img, loss=loss, tau=tau)
+    for _ in range(warmup):
+        port.step()
+    times = [port.step() for _ in range(steps)]
+    total = sum(times)
+    return {"value": sample_tiles * steps / total, "unit": UNIT, "cores": port.threads, "kind": "port",
+            "sample": f"{steps} step(s) of {sample_tiles} tiles ({34 * sample_tiles} encoder images of {img}^2) after {warmup} warm-up, "
+                      f"fp32, torch CPU, full step incl. backward + Adam",
+            "ms_per_step": 1e3 * total / steps}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # other ranks exit 0 without work
+    steps, warmup = max(1, args.steps), max(0, min(args.warmup, 1))  # bounded: each CPU step costs seconds
+    steps = min(steps, 3)
+    cb = run_cpu_port(args.cpu_sample, steps, warmup, args.loss, args.tau, args.img)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(args), "cpu_sample_tiles": args.cpu_sample},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi while the timed region runs)
+# ------------------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.f.read().splitlines():
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------------------------
+def ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import msfwsi_b200 as M
+    from msfwsi_b200 import _lib, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback in the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.benchmark = True
+    torch.manual_seed(3407 + rank)
+
+    class LossStep(torch.nn.Module):  # forward() returns the loss so DDP hooks see the whole hot path
+        def __init__(self, model):
+            super().__init__()
+            self.model = model
+
+        def forward(self, x1, x2, rev):
+            return self.model.forward_loss(x1, x2, rev, FUSER_WEIGHTS, mode=args.loss, tau=args.tau)
+
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = M.MSFWSI(M.resnet18, 4, 2048, 512, 0.5, False)  # random init: no network for ImageNet weights
+    if world > 1:
+        model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)  # tools/ssl_train.py:160
+    model = model.to(dev).to(memory_format=torch.channels_last).train()
+    step_mod = LossStep(model)
+    if world > 1:
+        step_mod = torch.nn.parallel.DistributedDataParallel(step_mod, device_ids=[local])  # ssl_train.py:170
+    lr = 1e-3 * (args.batch * world) ** 0.5 / 32 ** 0.5  # ssl_train.py:155
+    groups = [{"params": [p for n, p in model.named_parameters() if n.startswith(pre)]} for pre in ("context_", "target_", "inter_")]
+    opt = torch.optim.Adam(groups, lr=lr, fused=True)
+
+    B, K, img = args.batch, 16, args.img
+    g = torch.Generator().manual_seed(3407 + rank)
+    host = {"c1": torch.randn(B, 3, img, img, generator=g).pin_memory(), "c2": torch.randn(B, 3, img, img, generator=g).pin_memory(),
+            "t1": torch.randn(B * K, 3, img, img, generator=g).pin_memory(), "t2": torch.randn(B * K, 3, img, img, generator=g).pin_memory(),
+            "r1": torch.stack([torch.randperm(K, generator=g).argsort() for _ in range(B)]).pin_memory(),
+            "r2": torch.stack([torch.randperm(K, generator=g).argsort() for _ in range(B)]).pin_memory()}
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host.values())
+
+    def to_dev():
+        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        for k in ("c1", "c2", "t1", "t2"):
+            d[k] = d[k].contiguous(memory_format=torch.channels_last)
+        return d
+
+    def step(d):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = step_mod((d["c1"], d["t1"]), (d["c2"], d["t2"]), [d["r1"], d["r2"]])
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    resident = to_dev()
+    for _ in range(max(3, args.warmup)):
+        step(resident)
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM --------------------------------------------------------
+    clocks = Clocks(local) if rank == 0 else None
+    ops.PROFILE = []
+    launches0 = _lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(resident)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = _lib.launch_count - launches0
+    prof, ops.PROFILE = ops.PROFILE, None
+    clk = clocks.stop() if clocks else None
+    last_loss = float(loss.item())
+    value = B * world * args.steps / (ms / 1e3)
+
+    # ---- timed region 2: end to end from pinned host memory, loss read back every step -------------------
+    del resident
+    d = to_dev()
+    step(d).item()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        d = to_dev()
+        step(d).item()  # device -> host read of the step's result
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e = B * world * args.steps / (ms_e2e / 1e3)
+
+    # ---- roofline of the dominant kernel of this repo inside the timed steps ----------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    roofline = None
+    if prof:
+        tc = [(a.elapsed_time(b), fl) for a, b, fl, tcpath in prof if tcpath]
+        if tc:
+            t_ms, fl = sum(t for t, _ in tc), sum(f for _, f in tc)
+            peak = peaks.get("bf16_tflops_sustained", 1400.0)
+            roofline = {"kernel": "infonce_tc_kernel (+finalize) inside the step: target branch, dims 64/128/256, N=16*batch",
+                        "bound": "tensor", "achieved": fl / t_ms / 1e9, "peak": peak,
+                        "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback", "unit": "TFLOP/s",
+                        "frac": fl / t_ms / 1e9 / peak, "traffic": None, "launches": len(tc), "avg_us": 1e3 * t_ms / len(tc),
+                        "flops_per_launch": fl / len(tc)}
+    micro = None
+    if rank == 0 and not args.no_microbench:
+        micro = infonce_microbench(torch, ops, _lib, dev, peaks)
+    if roofline is None and micro:
+        roofline = micro["roofline"]
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb = run_cpu_port(args.cpu_sample, 2, 1, args.loss, args.tau, args.img)
+        cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic",
+                "config": {"workload": workload_name(args), "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                           "encoder": "resnet18 random-init (PyTorch/cuDNN, channels_last)", "optimizer": "Adam fused, 3 groups",
+                           "l2_policy": "per-step inputs (5.2 GB) and activations exceed the 126 MB L2"},
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline, "loss": last_loss,
+                "encoder_images_per_sec": value * 34}
+        if micro:
+            line["roofline_microbench"] = micro["rows"]
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def infonce_microbench(torch, ops, _lib, dev, peaks):
+    """c5 rows measured in the same process: the fused InfoNCE forward (main tcgen05 kernel + finalize) and the
+    whole fwd+bwd chain (row-normalise x2, forward, backward) with CUDA events, L2 flushed between iterations."""
+    L = _lib
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    peak = peaks.get("bf16_tflops", 1590.0)
+    rows = []
+    for n, d in ((16384, 128), (65536, 128), (65536, 256)):
+        g = torch.Generator(device=dev).manual_seed(3407)
+        k = torch.randn(n, d, device=dev, generator=g)
+        q = (0.3 * k + torch.randn(n, d, device=dev, generator=g)).to(torch.bfloat16)
+        k = k.to(torch.bfloat16)
+        qh, qi = ops.rownorm(q, torch.bfloat16)
+        kh, _ = ops.rownorm(k, torch.bfloat16)
+        wsb = L.lib().msf_infonce_workspace_bytes(n, n, d, L.MSF_BF16)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        loss, gout, gq = torch.empty((), device=dev), torch.ones((), device=dev), torch.empty_like(q)
+        st = L.stream_ptr()
+
+        def fwd():
+            L.check(L.lib().msf_infonce_fwd(qh.data_ptr(), kh.data_ptr(), n, n, d, 0, 0.07, L.MSF_BF16, loss.data_ptr(), 0, ws.data_ptr(), wsb, st), "fwd")
+
+        def chain():
+            a, ai = ops.rownorm(q, torch.bfloat16)
+            b, _ = ops.rownorm(k, torch.bfloat16)
+            L.check(L.lib().msf_infonce_fwd(a.data_ptr(), b.data_ptr(), n, n, d, 0, 0.07, L.MSF_BF16, loss.data_ptr(), 0, ws.data_ptr(), wsb, st), "fwd")
+            L.check(L.lib().msf_infonce_bwd(a.data_ptr(), b.data_ptr(), ai.data_ptr(), n, n, d, 0, 0.07, L.MSF_BF16, gout.data_ptr(), 1.0 / n,
+                                            ws.data_ptr(), wsb, gq.data_ptr(), L.MSF_BF16, st), "bwd")
+
+        out = {"N": n, "D": d, "flops": 4.0 * n * n * d}
+        for name, fn in (("fwd", fwd), ("fwd_bwd", chain)):
+            for _ in range(3):
+                fn()
+            ts = []
+            for _ in range(7):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            out[f"ms_{name}"] = statistics.median(ts)
+            out[f"tflops_{name}"] = out["flops"] / out[f"ms_{name}"] / 1e9
+            out[f"frac_{name}"] = out[f"tflops_{name}"] / peak
+        rows.append(out)
+    best = max(rows, key=lambda r: r["frac_fwd_bwd"])
+    roof = {"kernel": f"infonce_tc_kernel N={best['N']} D={best['D']} (fwd+bwd chain)", "bound": "tensor", "achieved": best["tflops_fwd_bwd"],
+            "peak": peak, "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback", "unit": "TFLOP/s",
+            "frac": best["frac_fwd_bwd"], "traffic": None}
+    return {"rows": rows, "roofline": roof}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()
