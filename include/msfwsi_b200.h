@@ -127,7 +127,9 @@ int msf_cosine_loss_bwd(const msf_cos_pair* pairs /*host*/, int n_pairs, int dty
  * Step 4  msf_infonce_bwd: grad_q (dtype of q) from the saved workspace.
  *
  * precision: MSF_F32  -> fp32 SIMT kernel (q_hat/k_hat fp32), for <=1e-5 parity.
- *            MSF_BF16 -> TMA + tcgen05/TMEM kernel (q_hat/k_hat bf16), dim in {64,128,256}.
+ *            MSF_BF16 -> TMA + tcgen05/TMEM kernels (q_hat/k_hat bf16): flash-style single pass for dim in
+ *                        {64,128,256}; two tcgen05 GEMM passes with P materialised in bf16 for larger multiples
+ *                        of 64 (512 and the fuser widths 576..4608), where TMEM cannot hold O and S together.
  * tau must satisfy 2*log2(e)/tau <= 120 (tau >= 0.0241): the softmax uses the fixed bound
  * max_j s_ij <= 1/tau that L2-normalised operands guarantee, so no running max is kept.
  * ---------------------------------------------------------------------------------------- */
@@ -149,6 +151,16 @@ int msf_infonce_fwd(const void* q_hat, const void* k_hat, int64_t nq, int64_t n_
 int msf_infonce_bwd(const void* q_hat, const void* k_hat, const float* q_inv_norm, int64_t nq, int64_t n_keys,
                     int dim, int64_t pos_offset, float tau, int precision, const float* grad_out, float scale,
                     const void* workspace, size_t workspace_bytes, void* grad_q, int grad_dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * G1  bf16 tcgen05 GEMM  C[M,N] = alpha * A[M,K] * op(B) (+ bias[N]), fp32 accumulate in TMEM.
+ * The Linear layers of the heads (src/models/backbone.py:14,17,20,27,30): y = x W^T is b_is_kn = 0 with
+ * B = W [N=out, K=in]; the input gradient dX = dY W is b_is_kn = 1 with B = W [K=out, N=in].
+ * A [M,K] row-major (lda), B [N,K] (b_is_kn=0) or [K,N] (b_is_kn=1) row-major (ldb), both bf16;
+ * C row-major (ldc), MSF_F32 or MSF_BF16.  lda/ldb multiples of 8, bases 16-byte aligned.
+ * ---------------------------------------------------------------------------------------- */
+int msf_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t M, int64_t N,
+                  int64_t K, int b_is_kn, int out_dtype, float alpha, const float* bias, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * A2  feature-map crop to each tile's footprint + bilinear resample.

@@ -302,7 +302,8 @@ int check_nce(const void* qh, const void* kh, int64_t nq, int64_t n_keys, int di
   MSF_REQUIRE(tau > 0.f && 2.f * kLog2e / tau <= 120.f, MSF_ERR_UNSUPPORTED,
               "tau=%g outside the supported range (tau >= 0.0241): fixed-bound softmax would underflow fp32", tau);
   if (precision == MSF_BF16)
-    MSF_REQUIRE(tc_dim_ok(dim), MSF_ERR_UNSUPPORTED, "tcgen05 path covers dim in {64,128,256}; got %d (use MSF_F32)", dim);
+    MSF_REQUIRE(tc_dim_ok(dim) || twopass_dim_ok(dim), MSF_ERR_UNSUPPORTED,
+                "tcgen05 paths cover dim in {64,128,256} (flash) and multiples of 64 above 256 (two-pass); got %d (use MSF_F32)", dim);
   else
     MSF_REQUIRE(dim % 4 == 0, MSF_ERR_INVALID, "dim must be a multiple of 4");
   return MSF_OK;
@@ -369,8 +370,15 @@ extern "C" int msf_infonce_fwd(const void* q_hat, const void* k_hat, int64_t nq,
   float* sum_tot = reinterpret_cast<float*>(ws + plan.off_sum);
   float* partials = reinterpret_cast<float*>(ws + plan.off_part);
   const float a = kLog2e / tau;
-  if (precision == MSF_BF16) {
+  if (plan.mode == 0) {
     if (int rc = launch_infonce_tc(q_hat, k_hat, nq, n_keys, dim, tau, plan, rowsum, o_part, st)) return rc;
+  } else if (plan.mode == 2) {
+    // pass 1: P = exp2(a * Q K^T - a) in bf16 (+ row-sum partials per 256-key tile column); pass 2: O = P K
+    void* P = ws + plan.off_p;
+    if (int rc = launch_gemm_tc(q_hat, dim, k_hat, dim, P, plan.ld_p, nq, n_keys, dim, 0, 2 /*EPI_EXP*/, a, nullptr, rowsum,
+                                plan.nq_pad, st)) return rc;
+    if (int rc = launch_gemm_tc(P, plan.ld_p, k_hat, dim, o_part, dim, nq, dim, n_keys, 1, 0 /*EPI_F32*/, 1.f, nullptr, nullptr, 0, st))
+      return rc;
   } else {
     dim3 grid(static_cast<unsigned>(plan.q_tiles), static_cast<unsigned>(plan.splits));
     infonce_simt_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(q_hat), static_cast<const float*>(k_hat), nq,
@@ -384,10 +392,10 @@ extern "C" int msf_infonce_fwd(const void* q_hat, const void* k_hat, int64_t nq,
   const char* qh = static_cast<const char*>(q_hat);
   const char* kh = static_cast<const char*>(k_hat);
   if (precision == MSF_BF16)
-    nce_fwd_final_kernel<MSF_BF16><<<blocks, 256, 0, st>>>(qh, kh, nq, dim, pos_offset, 1.f / tau, plan.splits, plan.nq_pad,
+    nce_fwd_final_kernel<MSF_BF16><<<blocks, 256, 0, st>>>(qh, kh, nq, dim, pos_offset, 1.f / tau, plan.rs_splits, plan.nq_pad,
                                                            rowsum, pos, sum_tot, row_lse, partials, lanes);
   else
-    nce_fwd_final_kernel<MSF_F32><<<blocks, 256, 0, st>>>(qh, kh, nq, dim, pos_offset, 1.f / tau, plan.splits, plan.nq_pad,
+    nce_fwd_final_kernel<MSF_F32><<<blocks, 256, 0, st>>>(qh, kh, nq, dim, pos_offset, 1.f / tau, plan.rs_splits, plan.nq_pad,
                                                           rowsum, pos, sum_tot, row_lse, partials, lanes);
   MSF_LAUNCH_OK("nce_fwd_final_kernel");
   final_sum_kernel<<<1, 256, 0, st>>>(partials, blocks, loss_sum_out);

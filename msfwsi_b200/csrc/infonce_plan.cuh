@@ -9,7 +9,9 @@ struct NcePlan {
   int tile_n;            // keys per inner tile
   int64_t q_tiles;       // CTAs along the query rows
   int64_t k_tiles;       // key tiles in total
-  int splits;            // key-range splits (partials are summed deterministically afterwards)
+  int mode;              // 0 flash tcgen05, 1 fp32 SIMT, 2 two-pass tcgen05 GEMMs (P materialised in bf16)
+  int splits;            // key-range splits of the main loop = number of O partials
+  int rs_splits;         // number of row-sum partials (two-pass: one per 256-key GEMM tile column)
   int64_t tiles_per_split;
   int64_t nq_pad;        // q_tiles * tile_m
   // workspace offsets in bytes
@@ -19,16 +21,20 @@ struct NcePlan {
   size_t off_sum;        // [nq] fp32 total row sum
   size_t off_part;       // [part_cap] fp32 loss partials (one per finalize CTA)
   size_t part_cap;
+  size_t off_p;          // two-pass only: P [nq][ld_p] bf16
+  int64_t ld_p;
   size_t total;
 };
 
 inline bool tc_dim_ok(int dim) { return dim == 64 || dim == 128 || dim == 256; }
+inline bool twopass_dim_ok(int dim) { return dim % 64 == 0 && dim > 256; }  // 512 and the fuser widths 576..4608
 
 inline NcePlan make_nce_plan(int64_t nq, int64_t n_keys, int dim, int precision) {
   NcePlan p{};
   const bool tc = precision == MSF_BF16;
+  p.mode = !tc ? 1 : (tc_dim_ok(dim) ? 0 : 2);
   p.tile_m = tc ? 128 : 64;
-  p.tile_n = tc ? 128 : 64;
+  p.tile_n = p.mode == 2 ? 256 : (tc ? 128 : 64);
   p.q_tiles = (nq + p.tile_m - 1) / p.tile_m;
   p.k_tiles = (n_keys + p.tile_n - 1) / p.tile_n;
   // choose the split count that minimises (waves x per-CTA tiles), the per-CTA prologue/epilogue
@@ -46,13 +52,15 @@ inline NcePlan make_nce_plan(int64_t nq, int64_t n_keys, int dim, int precision)
       best = s;
     }
   }
+  if (p.mode == 2) best = 1;  // the GEMMs own their tiling; O is written once
   p.splits = best;
+  p.rs_splits = p.mode == 2 ? static_cast<int>(p.k_tiles) : best;
   p.tiles_per_split = (p.k_tiles + best - 1) / best;
   p.nq_pad = p.q_tiles * p.tile_m;
   auto align = [](size_t v) { return (v + 255) & ~static_cast<size_t>(255); };
   size_t off = 0;
   p.off_rowsum = off;
-  off = align(off + static_cast<size_t>(p.splits) * p.nq_pad * sizeof(float));
+  off = align(off + static_cast<size_t>(p.rs_splits) * p.nq_pad * sizeof(float));
   p.off_o = off;
   off = align(off + static_cast<size_t>(p.splits) * p.nq_pad * dim * sizeof(float));
   p.off_pos = off;
@@ -62,6 +70,9 @@ inline NcePlan make_nce_plan(int64_t nq, int64_t n_keys, int dim, int precision)
   p.off_part = off;
   p.part_cap = static_cast<size_t>(nq / 8 + 2);
   off = align(off + p.part_cap * sizeof(float));
+  p.off_p = off;
+  p.ld_p = (n_keys + 7) & ~static_cast<int64_t>(7);
+  if (p.mode == 2) off = align(off + static_cast<size_t>(nq) * p.ld_p * 2);
   p.total = off;
   return p;
 }
@@ -69,5 +80,9 @@ inline NcePlan make_nce_plan(int64_t nq, int64_t n_keys, int dim, int precision)
 // implemented in infonce_tc.cu: TMA + tcgen05/TMEM main loop (bf16 operands, dim in {64,128,256})
 int launch_infonce_tc(const void* q_hat, const void* k_hat, int64_t nq, int64_t n_keys, int dim, float tau,
                       const NcePlan& plan, float* rowsum, float* o_part, cudaStream_t st);
+
+// implemented in gemm_tc.cu
+int launch_gemm_tc(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                   int b_mn_major, int epi, float alpha, const float* bias, float* rowsum_part, int64_t m_pad, cudaStream_t st);
 
 }  // namespace msf

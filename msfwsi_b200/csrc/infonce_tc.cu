@@ -13,15 +13,14 @@
 // Warp roles (384 threads): w0 TMA producer, w1 MMA issuer, w2 TMEM allocator, w3 idle, w4-7 softmax WG0,
 // w8-11 softmax WG1.  TMEM map (512 columns): O [0,D), S0/P0 [256,384), S1/P1 [384,512).
 // Algorithmic work: 4*Nq*N*D FLOP per launch (2 GEMMs); bytes 2*(Nq+N)*D read + 4*splits*Nq*(D+1) written.
-#include <cuda.h>
-#include <cudaTypedefs.h>
-
 #include "infonce_plan.cuh"
+#include "tc_common.cuh"
 
 namespace msf {
 namespace {
 
-constexpr int BM = 128, BN = 128;
+using namespace tc;
+constexpr int BN = 128;
 constexpr int kThreads = 384;
 constexpr uint32_t kSlabBytes = 128 * 128;  // 128 rows x 64 bf16 (one 128-byte swizzle span per row)
 constexpr uint32_t kTmemCols = 512, kColS0 = 256, kColS1 = 384;
@@ -34,108 +33,6 @@ struct Cfg {
   static constexpr uint32_t kBarBytes = 1024;
   static constexpr uint32_t kSmem = 1024 /*alignment slack*/ + kTileBytes * (1 + kStages) + kBarBytes;
 };
-
-// ---- PTX wrappers ------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a pipeline bug traps (reported as a CUDA error) instead of hanging the GPU box.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) __trap();
-  }
-}
-
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {  // arrives on `bar` when all prior MMAs of this thread retire
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc]
-__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem desc]
-__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {  // 32 lanes x 32 consecutive columns
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
-      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
-      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-// UMMA shared-memory descriptor, SWIZZLE_128B, version 1 (sm_100).  Byte offsets are encoded >> 4.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo_bytes >> 4) << 16) |
-         (static_cast<uint64_t>(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-// kind::f16 instruction descriptor: fp32 accumulate, bf16 x bf16, M=128
-__host__ __device__ constexpr uint32_t umma_idesc(int n, bool b_mn_major) {
-  return (1u << 4) /*D=f32*/ | (1u << 7) /*A=bf16*/ | (1u << 10) /*B=bf16*/ | (b_mn_major ? (1u << 16) : 0u) |
-         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
-}
 
 template <int D>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -241,36 +138,60 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     const int row = ((warp & 3) << 5) + lane;   // TMEM lane == query row inside the tile
     const uint32_t lane_base = tmem + (static_cast<uint32_t>((warp & 3) << 5) << 16);
     const uint32_t s_addr = lane_base + (wg ? kColS1 : kColS0);
-    float rs = 0.f;
-    const float neg_a = -a;
+    float2 rs2 = make_float2(0.f, 0.f);
+    const float2 a2 = make_float2(a, a), na2 = make_float2(-a, -a);
+    // one 32-column chunk of S -> 16 packed bf16x2 of P; packed fp32x2 FMA/ADD halve the issue slots per logit
+    auto chunk = [&](const uint32_t* v, uint32_t* u, int col0, int valid, bool mask) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const float2 y = __ffma2_rn(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), a2, na2);
+        float2 e = make_float2(ex2_approx(y.x), ex2_approx(y.y));
+        if (mask) {  // zero-filled (out-of-range) keys of the last tile contribute nothing
+          if (col0 + i >= valid) e.x = 0.f;
+          if (col0 + i + 1 >= valid) e.y = 0.f;
+        }
+        rs2 = __fadd2_rn(rs2, e);
+        __nv_bfloat162 h = __floats2bfloat162_rn(e.x, e.y);  // key 2j in the low half, 2j+1 in the high half
+        u[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+      }
+    };
     for (int t = wg; t < T; t += 2) {
       mbar_wait(s_full + wg, (t >> 1) & 1);
       tc_fence_after();
       const int64_t key0 = (kt0 + t) * BN;
       const int valid = (n_keys - key0) < BN ? static_cast<int>(n_keys - key0) : BN;
-#pragma unroll
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32], u[16];
-        tmem_ld32(s_addr + c * 32, v);
+      uint32_t v0[32], v1[32], u[16];
+      tmem_ld32(s_addr, v0);
+      if (valid == BN) {  // hot path: no per-element masking; the next chunk's TMEM load overlaps the math
         tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float e0 = ex2_approx(fmaf(__uint_as_float(v[i]), a, neg_a));
-          float e1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), a, neg_a));
-          if (valid < BN) {  // zero-filled (out-of-range) keys of the last tile contribute nothing
-            if (c * 32 + i >= valid) e0 = 0.f;
-            if (c * 32 + i + 1 >= valid) e1 = 0.f;
-          }
-          rs += e0 + e1;
-          __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1);  // key 2j in the low half, 2j+1 in the high half
-          u[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+        tmem_ld32(s_addr + 32, v1);
+        chunk(v0, u, 0, BN, false);
+        tmem_st16(s_addr, u);  // P overlays the S columns already consumed
+        tmem_ld_wait();
+        tmem_ld32(s_addr + 64, v0);
+        chunk(v1, u, 32, BN, false);
+        tmem_st16(s_addr + 16, u);
+        tmem_ld_wait();
+        tmem_ld32(s_addr + 96, v1);
+        chunk(v0, u, 64, BN, false);
+        tmem_st16(s_addr + 32, u);
+        tmem_ld_wait();
+        chunk(v1, u, 96, BN, false);
+        tmem_st16(s_addr + 48, u);
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          if (c > 0) tmem_ld32(s_addr + c * 32, v0);
+          tmem_ld_wait();
+          chunk(v0, u, c * 32, valid, true);
+          tmem_st16(s_addr + c * 16, u);
         }
-        tmem_st16(s_addr + c * 16, u);  // P overlays the S columns already consumed
       }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(p_full + wg);
     }
+    const float rs = rs2.x + rs2.y;
     // ---- epilogue: row sums (WG1 -> smem -> WG0 -> global), then O from TMEM to the split's partial ----
     if (wg == 1) rs_xchg[row] = rs;
     asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -303,31 +224,6 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
 }
 
 // ---- host side ---------------------------------------------------------------------------
-PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
-  static PFN_cuTensorMapEncodeTiled_v12000 fn = [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
-      p = nullptr;
-    return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
-  }();
-  return fn;
-}
-
-int make_map(CUtensorMap* map, const void* base, int64_t rows, int dim) {
-  auto fn = encode_fn();
-  MSF_REQUIRE(fn, MSF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(dim), static_cast<cuuint64_t>(rows)};
-  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(dim) * 2};
-  const cuuint32_t box[2] = {64, 128};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  MSF_REQUIRE(r == CUDA_SUCCESS, MSF_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
-  return MSF_OK;
-}
-
 template <int D>
 int launch(const CUtensorMap& tq, const CUtensorMap& tk, int64_t n_keys, const NcePlan& plan, float a, float* rowsum,
            float* o_part, cudaStream_t st) {
@@ -346,8 +242,8 @@ int launch_infonce_tc(const void* q_hat, const void* k_hat, int64_t nq, int64_t 
   MSF_REQUIRE(tc_dim_ok(dim), MSF_ERR_UNSUPPORTED, "tcgen05 path covers dim in {64,128,256}; got %d", dim);
   MSF_REQUIRE(n_keys < (1ll << 31) && nq < (1ll << 31), MSF_ERR_UNSUPPORTED, "row counts must fit 31 bits");
   CUtensorMap tq, tk;
-  if (int rc = make_map(&tq, q_hat, nq, dim)) return rc;
-  if (int rc = make_map(&tk, k_hat, n_keys, dim)) return rc;
+  if (int rc = make_map_bf16(&tq, q_hat, nq, dim, dim, 64, 128)) return rc;
+  if (int rc = make_map_bf16(&tk, k_hat, n_keys, dim, dim, 64, 128)) return rc;
   const float a = 1.4426950408889634f / tau;
   switch (dim) {
     case 64: return launch<64>(tq, tk, n_keys, plan, a, rowsum, o_part, st);

@@ -174,8 +174,10 @@ def rownorm(x: torch.Tensor, out_dtype: torch.dtype, eps: float = COS_EPS):
 
 
 def infonce_precision_for(dim: int, dtype: torch.dtype) -> torch.dtype:
-    """bf16 tcgen05 path where it exists (16-bit inputs, dim in {64,128,256}); fp32 SIMT otherwise."""
-    return torch.bfloat16 if (dtype in (torch.bfloat16, torch.float16) and dim in (64, 128, 256)) else torch.float32
+    """bf16 tcgen05 paths for 16-bit inputs: flash kernel for dim in {64,128,256}, two-pass GEMMs for larger multiples
+    of 64 (512 and the fuser widths); fp32 SIMT otherwise (fp32 inputs keep <=1e-5 parity)."""
+    tc = dim in (64, 128, 256) or (dim > 256 and dim % 64 == 0)
+    return torch.bfloat16 if (dtype in (torch.bfloat16, torch.float16) and tc) else torch.float32
 
 
 def all_gather_keys(k_hat: torch.Tensor, group=None) -> Tuple[torch.Tensor, int]:
@@ -210,7 +212,7 @@ class _InfoNCE(torch.autograd.Function):
                                         L.ptr(ws), ws_bytes, L.stream_ptr()), "msf_infonce_fwd")
         if PROFILE is not None:
             ev1.record()
-            PROFILE.append((ev0, ev1, 4.0 * nq * n_keys * dim, precision == torch.bfloat16))
+            PROFILE.append((ev0, ev1, 4.0 * nq * n_keys * dim, precision == torch.bfloat16 and dim in (64, 128, 256)))
         L.launch_count += 3
         ctx.save_for_backward(q_hat, k_all, q_inv, ws)
         ctx.meta = (nq, n_keys, dim, pos_offset, tau, prec, ws_bytes, p.dtype)

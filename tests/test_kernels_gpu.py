@@ -357,3 +357,53 @@ def test_infonce_bf16_autograd_entry_and_determinism():
     assert abs(l1.item() - ref.item()) <= 2e-3 * abs(ref.item())
     assert qd.grad.dtype == torch.bfloat16
     assert _cos(qd.grad, O.infonce_grad(q.double(), k.double(), tau)) >= 0.9999
+
+
+# ------------------------------------------------------------------ G1 tcgen05 GEMM + two-pass InfoNCE
+def _gemm(A, B, b_is_kn, out_dtype, alpha=1.0, bias=None):
+    M, K = A.shape
+    N = B.shape[1] if b_is_kn else B.shape[0]
+    Cm = torch.empty((M, N), dtype=out_dtype, device=DEV)
+    L.check(L.lib().msf_gemm_bf16(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), Cm.data_ptr(), Cm.stride(0), M, N, K, int(b_is_kn),
+                                  L.dtype_code(out_dtype), alpha, L.ptr(bias), L.stream_ptr()), "msf_gemm_bf16")
+    return Cm
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 512), (4096, 512, 512), (300, 200, 136), (1, 8, 8), (256, 4608, 4608),
+                                    (1000, 1152, 288), (129, 257, 72)])
+@pytest.mark.parametrize("b_is_kn", [False, True])
+def test_gemm_bf16_vs_torch(M, N, K, b_is_kn):
+    A = _rand((M, K), 1, torch.bfloat16).to(DEV)
+    if b_is_kn and N % 8:
+        N = (N + 7) // 8 * 8  # [K,N] row-major needs a 16-byte aligned row stride
+    B = (_rand((K, N), 2, torch.bfloat16) if b_is_kn else _rand((N, K), 2, torch.bfloat16)).to(DEV)
+    bias = _rand((N,), 3).to(DEV)
+    ref = A.double() @ (B.double() if b_is_kn else B.double().t())
+    out = _gemm(A, B, b_is_kn, torch.float32)
+    assert _relerr(out, ref) <= 2e-5, _relerr(out, ref)  # fp32 accumulate of exact bf16 products
+    out2 = _gemm(A, B, b_is_kn, torch.bfloat16, alpha=0.5, bias=bias)
+    assert _relerr(out2, 0.5 * ref + bias.double()) <= 4e-3
+
+
+@pytest.mark.parametrize("nq,n,dim,off", [(128, 256, 512, 0), (256, 256, 576, 0), (100, 300, 512, 100), (1024, 4096, 512, 2048),
+                                           (64, 64, 1152, 0), (256, 256, 4608, 0)])
+def test_infonce_bf16_two_pass_wide_dims(nq, n, dim, off):
+    tau = 0.07
+    q, k = _nce_inputs(nq, n, dim, 51, torch.bfloat16)
+    if off:
+        k[off:off + nq] = k[:nq].clone()
+    q_hat, q_inv = ops.rownorm(q.to(DEV), torch.bfloat16)
+    k_hat, _ = ops.rownorm(k.to(DEV), torch.bfloat16)
+    prec = L.MSF_BF16
+    ws_bytes = L.lib().msf_infonce_workspace_bytes(nq, n, dim, prec)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=DEV)
+    loss_sum = torch.empty((), dtype=torch.float32, device=DEV)
+    L.check(L.lib().msf_infonce_fwd(q_hat.data_ptr(), k_hat.data_ptr(), nq, n, dim, off, tau, prec, loss_sum.data_ptr(), 0, ws.data_ptr(),
+                                    ws_bytes, L.stream_ptr()), "fwd")
+    ref_loss, _, _ = O.infonce_loss(q.double(), k.double(), tau, pos_offset=off)
+    assert abs(loss_sum.item() / nq - ref_loss.item()) <= 2e-3 * max(abs(ref_loss.item()), 0.5), (loss_sum.item() / nq, ref_loss.item())
+    g = torch.full((), 1.0, device=DEV)
+    grad = torch.empty((nq, dim), dtype=torch.float32, device=DEV)
+    L.check(L.lib().msf_infonce_bwd(q_hat.data_ptr(), k_hat.data_ptr(), q_inv.data_ptr(), nq, n, dim, off, tau, prec, g.data_ptr(),
+                                    1.0 / nq, ws.data_ptr(), ws_bytes, grad.data_ptr(), L.MSF_F32, L.stream_ptr()), "bwd")
+    assert _cos(grad, O.infonce_grad(q.double(), k.double(), tau, off)) >= 0.9999
