@@ -1,0 +1,62 @@
+"""2-GPU NCCL parity of the sharded InfoNCE path (keys all-gathered over NVLink, queries local) against the CPU
+oracle on the concatenated batch.  Skipped on boxes with fewer than 2 GPUs (run with `gpurun --gpus 2`)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from msfwsi_b200 import ops
+        from oracle import msf_oracle as O
+        res = {}
+        for dim, rows, dtype, tol in ((128, 1024, torch.bfloat16, 2e-3), (512, 256, torch.bfloat16, 2e-3), (64, 200, torch.float32, 1e-5)):
+            g = torch.Generator().manual_seed(7)
+            k_all = torch.randn(world * rows, dim, generator=g)
+            p_all = (0.3 * k_all + torch.randn(world * rows, dim, generator=g)).to(dtype)
+            k_all = k_all.to(dtype)
+            p = p_all[rank * rows:(rank + 1) * rows].cuda().requires_grad_(True)
+            z = k_all[rank * rows:(rank + 1) * rows].cuda()
+            loss = ops.infonce_loss(p, z, tau=0.07)
+            loss.backward()
+            t = loss.detach().clone()
+            dist.all_reduce(t)
+            ref, _, _ = O.infonce_loss(p_all.double(), k_all.double(), 0.07)
+            gref = O.infonce_grad(p_all.double(), k_all.double(), 0.07)[rank * rows:(rank + 1) * rows]
+            got = p.grad.double().cpu() / world  # DDP averages gradients over ranks
+            cos = float((got.flatten() @ gref.flatten()) / (got.norm() * gref.norm()))
+            assert abs(t.item() / world - ref.item()) <= tol * abs(ref.item()), (dim, t.item() / world, ref.item())
+            assert cos >= 0.9999, (dim, cos)
+            res[dim] = (t.item() / world, ref.item(), cos)
+        q.put((rank, "ok", res))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, "fail: " + traceback.format_exc()[-800:], None))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.timeout(300)
+def test_sharded_infonce_nccl_matches_single_process_oracle():
+    world, port = 2, 29600 + (os.getpid() % 300)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(30)
+    assert all(r[1] == "ok" for r in res), res
