@@ -38,6 +38,22 @@ __device__ __forceinline__ void row_dots(const char* p, const char* z, uint32_t 
   constexpr int VEC = Elem<DT>::VEC;
   dot = pp = zz = 0.f;
   uint32_t c = valid ? lane : cpr;  // invalid rows load nothing but still take part in the shuffles
+  for (; c + 3 * lanes < cpr; c += 4 * lanes) {  // four chunks of each operand in flight
+    uint4 pa[4], za[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      pa[u] = ldg_stream(p + static_cast<size_t>(c + u * lanes) * 16);
+      za[u] = ldg_stream(z + static_cast<size_t>(c + u * lanes) * 16);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float fa[VEC], fb[VEC];
+      Elem<DT>::unpack(pa[u], fa);
+      Elem<DT>::unpack(za[u], fb);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) { dot = fmaf(fa[i], fb[i], dot); pp = fmaf(fa[i], fa[i], pp); zz = fmaf(fb[i], fb[i], zz); }
+    }
+  }
   for (; c + lanes < cpr; c += 2 * lanes) {  // two chunks of each operand in flight
     const uint4 a0 = ldg_stream(p + static_cast<size_t>(c) * 16), b0 = ldg_stream(z + static_cast<size_t>(c) * 16);
     const uint4 a1 = ldg_stream(p + static_cast<size_t>(c + lanes) * 16), b1 = ldg_stream(z + static_cast<size_t>(c + lanes) * 16);
@@ -137,7 +153,25 @@ __global__ void __launch_bounds__(kThreads) cos_bwd_kernel(const __grid_constant
     const char* p = g.p + row * row_bytes;
     const char* z = g.z + row * row_bytes;
     char* o = g.grad_p + row * row_bytes;
-    for (uint32_t c = lane; c < g.cpr; c += lanes) {
+    uint32_t c = lane;
+    for (; c + 3 * lanes < g.cpr; c += 4 * lanes) {  // 8 x 128-bit loads in flight per thread
+      uint4 pv[4], zv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        pv[u] = ldg_stream(p + static_cast<size_t>(c + u * lanes) * 16);
+        zv[u] = ldg_stream(z + static_cast<size_t>(c + u * lanes) * 16);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float fp[VEC], fz[VEC];
+        Elem<DT>::unpack(pv[u], fp);
+        Elem<DT>::unpack(zv[u], fz);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) fp[i] = a * fz[i] - b * fp[i];
+        stg_stream(o + static_cast<size_t>(c + u * lanes) * 16, Elem<DT>::pack(fp));
+      }
+    }
+    for (; c < g.cpr; c += lanes) {
       const uint4 pv = ldg_stream(p + static_cast<size_t>(c) * 16), zv = ldg_stream(z + static_cast<size_t>(c) * 16);
       float fp[VEC], fz[VEC];
       Elem<DT>::unpack(pv, fp);
@@ -173,7 +207,9 @@ int build(Params& P, const msf_cos_pair* pairs, int n_pairs, int dtype, bool nee
     g.grad_p = static_cast<char*>(q.grad_p);
     g.rows = q.rows;
     g.cpr = q.dim / vec;
-    g.lanes = g.cpr >= 32 ? 32 : (g.cpr >= 16 ? 16 : 8);
+    // ~4 chunks of each operand per lane: few shuffle rounds per row, 8 x 128-bit loads in flight per thread
+    g.lanes = 1;
+    while (g.lanes < 32 && g.lanes * 4 < g.cpr) g.lanes <<= 1;
     const uint32_t groups = kThreads / g.lanes;
     const size_t row_bytes = static_cast<size_t>(g.cpr) * 16 * 2;
     uint32_t rpb = static_cast<uint32_t>((96 * 1024 + row_bytes - 1) / row_bytes);  // ~96 KB of reads per CTA

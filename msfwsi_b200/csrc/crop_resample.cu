@@ -85,6 +85,98 @@ __global__ void __launch_bounds__(256) crop_fwd_kernel(const void* __restrict__ 
   }
 }
 
+// ---- fast path: warp-cooperative rows, 128-bit stores ---------------------------------------------------
+// CTA = one box (b,k) x a group of channels; a lane group of ow/VEC lanes owns one output row at a time.
+//   1. the group loads the source span of the row from the two source rows with CONSECUTIVE lanes on consecutive
+//      pixels (coalesced sectors, L1-resident for the `zoom` output rows that share them) and interpolates
+//      vertically;
+//   2. every source pixel is parked in the warp's shared row as float2 {v[s], v[s+1]-v[s]} (the neighbour comes
+//      from a shuffle);
+//   3. each lane forms its VEC outputs with ONE 64-bit shared load + one FMA each (out = v + wx*dv; wx == 0 returns
+//      v exactly, so an integer box of the output size is a bit-exact copy) and stores 16 bytes.
+// x taps live in registers (a lane always owns the same output columns); y taps in shared memory.
+constexpr int kFastThreads = 256;
+
+template <int DT>
+__global__ void __launch_bounds__(kFastThreads) crop_fwd_fast_kernel(const void* __restrict__ feat, const float* __restrict__ boxes,
+                                                                     void* __restrict__ out, Geo g, int ch_per_cta, int park_stride) {
+  constexpr int VEC = Elem<DT>::VEC;
+  extern __shared__ __align__(16) float sm[];
+  const int tpr = g.ow / VEC;            // lanes per output row (power of two <= 32)
+  const int rows_per_warp = 32 / tpr;
+  int* y_i0 = reinterpret_cast<int*>(sm);
+  int* y_i1 = y_i0 + g.oh;
+  float* y_w = reinterpret_cast<float*>(y_i1 + g.oh);
+  float2* parks = reinterpret_cast<float2*>(sm + ((3 * g.oh + 3) & ~3));  // [warps * rows_per_warp][park_stride]
+  const int groups_c = (g.C + ch_per_cta - 1) / ch_per_cta;
+  const int64_t bk = blockIdx.x / groups_c;
+  const int c_begin = static_cast<int>(blockIdx.x % groups_c) * ch_per_cta;
+  const int c_end = min(c_begin + ch_per_cta, g.C);
+  const int64_t b = bk / g.K;
+  const float4 bx = __ldg(reinterpret_cast<const float4*>(boxes) + bk);  // y0,x0,y1,x1
+  for (int o = threadIdx.x; o < g.oh; o += kFastThreads) axis_taps(bx.x, bx.z - bx.x, o, g.oh, g.H, y_i0[o], y_i1[o], y_w[o]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = lane / tpr, lig = lane % tpr;
+  int xs, xl0, xl1;
+  float wtmp;
+  axis_taps(bx.y, bx.w - bx.y, 0, g.ow, g.W, xs, xl0, wtmp);            // first source column of the box
+  axis_taps(bx.y, bx.w - bx.y, g.ow - 1, g.ow, g.W, xl0, xl1, wtmp);    // last one
+  const int fw = xl1 - xs + 1;                                           // <= park_stride
+  int xi0[VEC];
+  float xw[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    int a0, a1;
+    axis_taps(bx.y, bx.w - bx.y, lig * VEC + v, g.ow, g.W, a0, a1, xw[v]);
+    if (a1 == a0) xw[v] = 0.f;  // clamped second tap
+    xi0[v] = a0 - xs;
+  }
+  __syncthreads();
+  float2* park = parks + (warp * rows_per_warp + grp) * park_stride;
+  const int rows_per_iter = (kFastThreads / 32) * rows_per_warp;
+  const int total_rows = (c_end - c_begin) * g.oh;
+  const int iters = (total_rows + rows_per_iter - 1) / rows_per_iter;
+  const int64_t plane_sz = static_cast<int64_t>(g.H) * g.W;
+  for (int itn = 0; itn < iters; ++itn) {
+    const int r = itn * rows_per_iter + warp * rows_per_warp + grp;
+    const bool valid = r < total_rows;
+    const int cl = valid ? r / g.oh : 0, oy = valid ? r - cl * g.oh : 0;
+    const int c = c_begin + cl;
+    const float wy = y_w[oy], om = 1.f - wy;
+    const int64_t r0 = (b * g.C + c) * plane_sz + static_cast<int64_t>(y_i0[oy]) * g.W + xs;
+    const int64_t r1 = (b * g.C + c) * plane_sz + static_cast<int64_t>(y_i1[oy]) * g.W + xs;
+    for (int j0 = 0; j0 < fw; j0 += tpr) {  // group-uniform trip count
+      const int j = j0 + lig;
+      float vj = 0.f;
+      if (valid && j < fw) {
+        const float t = ld1<DT>(feat, r0 + j);
+        vj = wy == 0.f ? t : fmaf(ld1<DT>(feat, r1 + j), wy, t * om);
+      }
+      float vn = __shfl_down_sync(0xffffffffu, vj, 1, tpr);     // v[j+1] from the next lane of the group (warp-uniform loop)
+      if (lig == tpr - 1) {                                      // ... or the first pixel of the next batch
+        vn = vj;
+        if (valid && j + 1 < fw) {
+          const float t = ld1<DT>(feat, r0 + j + 1);
+          vn = wy == 0.f ? t : fmaf(ld1<DT>(feat, r1 + j + 1), wy, t * om);
+        }
+      }
+      if (valid && j < fw) park[j] = make_float2(vj, j + 1 < fw ? vn - vj : 0.f);
+    }
+    __syncwarp();
+    if (valid) {
+      float res[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const float2 p2 = park[xi0[v]];
+        res[v] = fmaf(xw[v], p2.y, p2.x);
+      }
+      const int64_t o = (((bk * g.C + c) * g.oh + oy) * static_cast<int64_t>(g.ow)) + lig * VEC;
+      stg_stream(static_cast<char*>(out) + o * (16 / VEC), Elem<DT>::pack(res));
+    }
+    __syncwarp();
+  }
+}
+
 template <int DT>
 __global__ void __launch_bounds__(256) crop_bwd_kernel(const void* __restrict__ gout, const float* __restrict__ boxes,
                                                        float* __restrict__ gfeat, Geo g, int64_t total) {
@@ -140,7 +232,21 @@ extern "C" int msf_crop_resample_fwd(const void* feat, int64_t B, int C, int H, 
   const int vec = 16 / static_cast<int>(dtype_size(dtype));
   const bool vec_ok = (ow % vec == 0) && aligned16(out);
   const int64_t rows = B * K * static_cast<int64_t>(C) * oh;
-  if (vec_ok) {
+  const int tpr = vec_ok ? ow / vec : 0;
+  const int park_stride = (W + 2 + 1) & ~1;
+  const size_t fast_smem = static_cast<size_t>((3 * oh + 3) & ~3) * 4 +
+                           static_cast<size_t>(kFastThreads / 32) * (tpr > 0 && tpr <= 32 ? 32 / tpr : 1) * park_stride * 8;
+  const bool fast_ok = vec_ok && tpr >= 1 && tpr <= 32 && (tpr & (tpr - 1)) == 0 && fast_smem <= 48 * 1024 && B * K < (1ll << 24);
+  if (fast_ok) {
+    // enough CTAs for several waves of 148 SMs x 8 CTAs while keeping >= 256 output rows per CTA
+    int ch_per_cta = C;
+    while (ch_per_cta > 1 && (static_cast<int64_t>(ch_per_cta / 2) * oh >= 256) &&
+           B * K * ((C + ch_per_cta - 1) / ch_per_cta) < static_cast<int64_t>(kNumSMs) * 64)
+      ch_per_cta = (ch_per_cta + 1) / 2;
+    const int64_t ctas = B * K * ((C + ch_per_cta - 1) / ch_per_cta);
+    MSF_DISPATCH_DTYPE(dtype, (crop_fwd_fast_kernel<DT><<<static_cast<unsigned>(ctas), kFastThreads, fast_smem, st>>>(
+                                  feat, boxes, out, g, ch_per_cta, park_stride)));
+  } else if (vec_ok) {
     const int64_t total = rows * (ow / vec);
     MSF_DISPATCH_DTYPE(dtype, (crop_fwd_kernel<DT, Elem<DT>::VEC><<<grid_for(total), 256, 0, st>>>(feat, boxes, out, g, total)));
   } else {

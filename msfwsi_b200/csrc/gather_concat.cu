@@ -14,16 +14,17 @@ struct Segment {
   const char* src;     // base of the source rows
   const char* src2;    // optional second source added to the first (backward only)
   char* dst;
+  char* dst2;          // forward gather only: second destination (fuser rows) for source rows < n_keep
   const int64_t* idx;  // optional (B,K) permutation
   int64_t rows;        // rows in this segment
   uint32_t block_prefix;  // first CTA of this segment
   uint32_t cpr;        // 16-byte chunks per row
   int32_t shift;       // log2(cpr) if cpr is a power of two, else -1
-  uint32_t src_stride, src2_stride, dst_stride;  // row strides in chunks
+  uint32_t src_stride, src2_stride, dst_stride, dst2_stride;  // row strides in chunks
   int32_t mode;        // 0 plain copy; 1 gather src row via idx; 2 scatter dst row via idx (+src2 if dstrow%K<n_keep)
 };
 
-constexpr int kMaxSeg = 3 * MSF_GATHER_MAX_ITEMS;
+constexpr int kMaxSeg = 2 * MSF_GATHER_MAX_ITEMS;
 struct Params {
   Segment seg[kMaxSeg];
   int n_seg;
@@ -40,48 +41,59 @@ __global__ void __launch_bounds__(kThreads) row_copy_kernel(const __grid_constan
 #pragma unroll 1
   while (s + 1 < P.n_seg && blockIdx.x >= P.seg[s + 1].block_prefix) ++s;
   const Segment& g = P.seg[s];
-  const int64_t seg_chunks = g.rows * static_cast<int64_t>(g.cpr);
-  const int64_t chunk0 = static_cast<int64_t>(blockIdx.x - g.block_prefix) * kChunksPerBlock + threadIdx.x;
+  // 32-bit index arithmetic inside a segment (the host rejects segments with >= 2^31 chunks)
+  const uint32_t seg_chunks = static_cast<uint32_t>(g.rows) * g.cpr;
+  const uint32_t chunk0 = (blockIdx.x - g.block_prefix) * kChunksPerBlock + threadIdx.x;
+  const uint32_t K = static_cast<uint32_t>(P.K);
+  const bool k_pow2 = (K & (K - 1)) == 0;
 #pragma unroll 1
   for (int it = 0; it < kIter; ++it) {
     uint4 v[kIlp], v2[kIlp];
     char* dst[kIlp];
+    char* dstb[kIlp];
     bool has2[kIlp];
 #pragma unroll
     for (int u = 0; u < kIlp; ++u) {
-      const int64_t local = chunk0 + static_cast<int64_t>(it * kIlp + u) * kThreads;
+      const uint32_t local = chunk0 + static_cast<uint32_t>(it * kIlp + u) * kThreads;
       dst[u] = nullptr;
+      dstb[u] = nullptr;
       has2[u] = false;
       if (local >= seg_chunks) continue;
-      int64_t row;
-      uint32_t c;
+      uint32_t row, c;
       if (g.shift >= 0) {
         row = local >> g.shift;
-        c = static_cast<uint32_t>(local) & (g.cpr - 1);
+        c = local & (g.cpr - 1);
       } else {
         row = local / g.cpr;
-        c = static_cast<uint32_t>(local - row * g.cpr);
+        c = local - row * g.cpr;
       }
-      int64_t srow = row, drow = row;
+      uint32_t srow = row, drow = row;
       if (g.mode != 0) {
-        const int64_t b = row / P.K;
-        int64_t r = g.idx[row];
-        if (r < -P.K || r >= P.K) {  // the reference raises IndexError (advanced indexing on CPU)
+        const uint32_t bk = k_pow2 ? (row & ~(K - 1)) : (row / K) * K;  // first row of this sample
+        long long r = g.idx[row];
+        if (r < -static_cast<long long>(K) || r >= static_cast<long long>(K)) {  // the reference raises IndexError
           if (status) atomicOr(status, 1);
           r = 0;
         }
-        if (r < 0) r += P.K;
+        if (r < 0) r += K;
+        const uint32_t ru = static_cast<uint32_t>(r);
         if (g.mode == 1) {
-          srow = b * P.K + r;
+          srow = bk + ru;
+          if (g.dst2 && ru < static_cast<uint32_t>(P.n_keep)) {  // the same 16 bytes also feed ms[b, (1+r)*d + c]
+            const uint32_t b = k_pow2 ? (row >> (31 - __clz(K))) : row / K;
+            dstb[u] = g.dst2 + (static_cast<size_t>(b) * g.dst2_stride + ru * g.cpr + c) * 16;
+          }
         } else {
-          drow = b * P.K + r;
-          has2[u] = g.src2 != nullptr && r < P.n_keep;
-          if (has2[u])  // g_ms[b, (1+r)*d + c]  -- src2 points at g_ms + d (first target slot)
-            v2[u] = ldg_stream(g.src2 + (b * g.src2_stride + r * g.cpr + c) * 16);
+          drow = bk + ru;
+          has2[u] = g.src2 != nullptr && ru < static_cast<uint32_t>(P.n_keep);
+          if (has2[u]) {  // g_ms[b, (1+r)*d + c]  -- src2 points at g_ms + d (first target slot)
+            const uint32_t b = k_pow2 ? (row >> (31 - __clz(K))) : row / K;
+            v2[u] = ldg_stream(g.src2 + (static_cast<size_t>(b) * g.src2_stride + ru * g.cpr + c) * 16);
+          }
         }
       }
-      dst[u] = g.dst + (drow * g.dst_stride + c) * 16;
-      if (g.src) v[u] = ldg_stream(g.src + (srow * g.src_stride + c) * 16);
+      dst[u] = g.dst + (static_cast<size_t>(drow) * g.dst_stride + c) * 16;
+      if (g.src) v[u] = ldg_stream(g.src + (static_cast<size_t>(srow) * g.src_stride + c) * 16);
       else v[u] = make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
@@ -96,17 +108,21 @@ __global__ void __launch_bounds__(kThreads) row_copy_kernel(const __grid_constan
         v[u] = Elem<DT>::pack(a);
       }
       stg_stream(dst[u], v[u]);
+      if (dstb[u]) stg_stream(dstb[u], v[u]);
     }
   }
 }
 
 int push(Params& P, const void* src, const void* src2, void* dst, const int64_t* idx, int64_t rows, uint32_t cpr,
-         uint32_t ss, uint32_t s2s, uint32_t ds, int mode) {
+         uint32_t ss, uint32_t s2s, uint32_t ds, int mode, void* dst2 = nullptr, uint32_t d2s = 0) {
   if (rows == 0 || cpr == 0) return 0;
+  if (rows * static_cast<int64_t>(cpr) >= (1ll << 31)) return -1;
   Segment& g = P.seg[P.n_seg++];
   g.src = static_cast<const char*>(src);
   g.src2 = static_cast<const char*>(src2);
   g.dst = static_cast<char*>(dst);
+  g.dst2 = static_cast<char*>(dst2);
+  g.dst2_stride = d2s;
   g.idx = idx;
   g.rows = rows;
   g.block_prefix = P.total_blocks;
@@ -158,12 +174,13 @@ extern "C" int msf_gather_concat_fwd(const msf_gather_item* items, int n_items, 
     const uint32_t cpr = it.d / vec;
     const uint32_t ms_stride = (n_keep + 1) * cpr;
     // sorted[b*K+j] = tgt_f[b*K + rev[b,j]]
-    push(P, it.tgt_f, nullptr, it.tgt_sorted, it.rev, B * K, cpr, cpr, 0, cpr, 1);
+    // sorted[b*K+j] = tgt_f[b*K + rev[b,j]]; the same load also fills ms[b, (1+s)*d ...] when the source row
+    // s = rev[b,j] is one of the first n_keep shuffled vectors, so every target row is read exactly once
+    int bad = push(P, it.tgt_f, nullptr, it.tgt_sorted, it.rev, B * K, cpr, cpr, 0, cpr, 1,
+                   static_cast<char*>(it.ms_f) + static_cast<size_t>(cpr) * 16, ms_stride);
     // ms[b, 0:d] = ctx_f[b]
-    push(P, it.ctx_f, nullptr, it.ms_f, nullptr, B, cpr, cpr, 0, ms_stride, 0);
-    // ms[b, d:(1+n_keep)d] = tgt_f[b*K : b*K+n_keep] (contiguous in the shuffled order)
-    push(P, it.tgt_f, nullptr, static_cast<char*>(it.ms_f) + static_cast<size_t>(cpr) * 16, nullptr, B, n_keep * cpr,
-         K * cpr, 0, ms_stride, 0);
+    bad |= push(P, it.ctx_f, nullptr, it.ms_f, nullptr, B, cpr, cpr, 0, ms_stride, 0);
+    MSF_REQUIRE(!bad, MSF_ERR_UNSUPPORTED, "item %d: more than 2^31 16-byte chunks in one tensor", i);
   }
   P.K = K;
   P.n_keep = n_keep;
@@ -186,9 +203,10 @@ extern "C" int msf_gather_concat_bwd(const msf_gather_grad_item* items, int n_it
     const uint32_t ms_stride = (n_keep + 1) * cpr;
     const char* ms_tgt = it.g_ms ? static_cast<const char*>(it.g_ms) + static_cast<size_t>(cpr) * 16 : nullptr;
     // g_tgt_f[b*K + rev[b,j]] = g_sorted[b*K+j] (+ g_ms[b, (1+rev)*d ...] when rev < n_keep)
-    push(P, it.g_sorted, ms_tgt, it.g_tgt_f, it.rev, B * K, cpr, cpr, ms_stride, cpr, 2);
+    int bad = push(P, it.g_sorted, ms_tgt, it.g_tgt_f, it.rev, B * K, cpr, cpr, ms_stride, cpr, 2);
     // g_ctx_f[b] = g_ms[b, 0:d]
-    push(P, it.g_ms, nullptr, it.g_ctx_f, nullptr, B, cpr, ms_stride, 0, cpr, 0);
+    bad |= push(P, it.g_ms, nullptr, it.g_ctx_f, nullptr, B, cpr, ms_stride, 0, cpr, 0);
+    MSF_REQUIRE(!bad, MSF_ERR_UNSUPPORTED, "item %d: more than 2^31 16-byte chunks in one tensor", i);
   }
   P.K = K;
   P.n_keep = n_keep;

@@ -288,7 +288,11 @@ __global__ void __launch_bounds__(256) nce_bwd_kernel(const char* __restrict__ q
   }
 }
 
-inline uint32_t lanes_for(uint32_t cpr) { return cpr >= 32 ? 32 : (cpr >= 16 ? 16 : 8); }
+inline uint32_t lanes_for(uint32_t cpr) {  // ~4 chunks per lane: few shuffle rounds per row, several loads in flight
+  uint32_t lanes = 1;
+  while (lanes < 32 && lanes * 4 < cpr) lanes <<= 1;
+  return lanes;
+}
 
 int check_nce(const void* qh, const void* kh, int64_t nq, int64_t n_keys, int dim, int64_t pos_offset, float tau,
               int precision) {
