@@ -13,6 +13,8 @@
 // Warp roles (384 threads): w0 TMA producer, w1 MMA issuer, w2 TMEM allocator, w3 idle, w4-7 softmax WG0,
 // w8-11 softmax WG1.  TMEM map (512 columns): O [0,D), S0/P0 [256,384), S1/P1 [384,512).
 // Algorithmic work: 4*Nq*N*D FLOP per launch (2 GEMMs); bytes 2*(Nq+N)*D read + 4*splits*Nq*(D+1) written.
+#include <stdlib.h>
+
 #include "infonce_plan.cuh"
 #include "tc_common.cuh"
 
@@ -38,7 +40,7 @@ template <int D>
 __global__ void __launch_bounds__(kThreads, 1)
 infonce_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k, int64_t n_keys,
                   int64_t k_tiles, int64_t tiles_per_split, int64_t nq_pad, float a, float* __restrict__ rowsum,
-                  float* __restrict__ o_part) {
+                  float* __restrict__ o_part, int issue_policy) {
   using C = Cfg<D>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -100,9 +102,8 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
       constexpr uint32_t idesc1 = umma_idesc(BN, false);  // S = Q K^T : N = 128 keys, B K-major
       constexpr uint32_t idesc2 = umma_idesc(D, true);    // O += P K  : N = D, B MN-major (same smem tile)
       const uint32_t q_addr = smem_u32(sQ);
-      auto gemm1 = [&](int t) {
+      auto gemm1 = [&](int t) {  // operands are known to be ready
         const int stage = t % C::kStages;
-        mbar_wait(k_full + stage, (t / C::kStages) & 1);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(sK + stage * C::kTileBytes);
         const uint32_t d_tmem = tmem + ((t & 1) ? kColS1 : kColS0);
@@ -115,7 +116,6 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
       };
       auto gemm2 = [&](int t) {
         const int stage = t % C::kStages;
-        mbar_wait(p_full + (t & 1), (t >> 1) & 1);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(sK + stage * C::kTileBytes);
         const uint32_t p_tmem = tmem + ((t & 1) ? kColS1 : kColS0);
@@ -125,10 +125,47 @@ infonce_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         tc_commit(k_empty + stage);
       };
       mbar_wait(q_full, 0);
-      gemm1(0);
-      for (int t = 0; t < T; ++t) {
-        if (t + 1 < T) gemm1(t + 1);  // keep the tensor pipe busy while tile t is in the softmax
-        gemm2(t);
+      // Out-of-order issue over two queues: GEMM1(a) needs K tile a in smem and its S buffer free (GEMM2(a-2)
+      // issued, i.e. a <= b+1); GEMM2(b) needs P(b) from the softmax.  GEMM1 goes first whenever it can, so the
+      // softmax warpgroups always have a tile and a late TMA load is hidden behind the other queue.
+      int a_next = 0, b_next = 0;
+      if (issue_policy == 0) {
+        // in-order issue: GEMM1(t+1) is queued before GEMM2(t) so the tensor pipe works while tile t is in the softmax
+        mbar_wait(k_full, 0);
+        gemm1(0);
+        for (int t = 0; t < T; ++t) {
+          if (t + 1 < T) {
+            mbar_wait(k_full + ((t + 1) % C::kStages), ((t + 1) / C::kStages) & 1);
+            gemm1(t + 1);
+          }
+          mbar_wait(p_full + (t & 1), (t >> 1) & 1);
+          gemm2(t);
+        }
+      } else {
+        long long t_progress = clock64();
+        while (b_next < T) {
+          const bool g1_idx = a_next < T && a_next <= b_next + 1;  // GEMM1 allowed by the S-buffer rule
+          const bool g2_idx = b_next < a_next;                      // GEMM2 has an S tile in flight
+          uint64_t* kbar = k_full + (a_next % C::kStages);
+          const uint32_t kpar = (a_next / C::kStages) & 1;
+          uint64_t* pbar = p_full + (b_next & 1);
+          const uint32_t ppar = (b_next >> 1) & 1;
+          if (g1_idx && !g2_idx) {
+            mbar_wait(kbar, kpar);  // only one candidate: sleep on its barrier (fast hardware wake-up)
+            gemm1(a_next++);
+          } else if (g2_idx && !g1_idx) {
+            mbar_wait(pbar, ppar);
+            gemm2(b_next++);
+          } else if (mbar_test_wait(kbar, kpar)) {  // both possible: GEMM1 first so the softmax always has a tile
+            gemm1(a_next++);
+          } else if (mbar_test_wait(pbar, ppar)) {
+            gemm2(b_next++);
+          } else {
+            if (clock64() - t_progress > 4000000000ll) __trap();  // watchdog: a pipeline bug is a CUDA error, not a hung box
+            continue;
+          }
+          t_progress = clock64();
+        }
       }
       tc_commit(o_full);
     }
@@ -229,8 +266,12 @@ int launch(const CUtensorMap& tq, const CUtensorMap& tk, int64_t n_keys, const N
            float* o_part, cudaStream_t st) {
   MSF_CUDA_OK(cudaFuncSetAttribute(infonce_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<D>::kSmem));
   dim3 grid(static_cast<unsigned>(plan.q_tiles), static_cast<unsigned>(plan.splits));
+  // D = 256 has only two 64 KB key stages: out-of-order issue hides the TMA latency there; with >= 4 stages the
+  // in-order schedule is already load-latency free and keeps the issuing warp asleep between tiles
+  static const int forced = getenv("MSF_TC_ISSUE_POLICY") ? atoi(getenv("MSF_TC_ISSUE_POLICY")) : -1;
+  const int policy = forced >= 0 ? forced : (Cfg<D>::kStages <= 2 ? 1 : 0);
   infonce_tc_kernel<D><<<grid, kThreads, Cfg<D>::kSmem, st>>>(tq, tk, n_keys, plan.k_tiles, plan.tiles_per_split, plan.nq_pad, a,
-                                                              rowsum, o_part);
+                                                              rowsum, o_part, policy);
   MSF_LAUNCH_OK("infonce_tc_kernel");
   return MSF_OK;
 }
