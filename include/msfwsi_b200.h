@@ -156,11 +156,12 @@ int msf_infonce_bwd(const void* q_hat, const void* k_hat, const float* q_inv_nor
  * G1  bf16 tcgen05 GEMM  C[M,N] = alpha * A[M,K] * op(B) (+ bias[N]), fp32 accumulate in TMEM.
  * The Linear layers of the heads (src/models/backbone.py:14,17,20,27,30): y = x W^T is b_is_kn = 0 with
  * B = W [N=out, K=in]; the input gradient dX = dY W is b_is_kn = 1 with B = W [K=out, N=in].
- * A [M,K] row-major (lda), B [N,K] (b_is_kn=0) or [K,N] (b_is_kn=1) row-major (ldb), both bf16;
- * C row-major (ldc), MSF_F32 or MSF_BF16.  lda/ldb multiples of 8, bases 16-byte aligned.
+ * the weight gradient dW = dY^T X is a_is_km = 1 (A = dY stored [K=rows, M=out]) with b_is_kn = 1 (B = X [K=rows, N=in]).
+ * A [M,K] (a_is_km=0) or [K,M] (a_is_km=1) row-major (lda), B [N,K] (b_is_kn=0) or [K,N] (b_is_kn=1) row-major (ldb),
+ * both bf16; C row-major (ldc), MSF_F32 or MSF_BF16.  lda/ldb multiples of 8, bases 16-byte aligned.
  * ---------------------------------------------------------------------------------------- */
 int msf_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t M, int64_t N,
-                  int64_t K, int b_is_kn, int out_dtype, float alpha, const float* bias, void* stream);
+                  int64_t K, int a_is_km, int b_is_kn, int out_dtype, float alpha, const float* bias, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * A2  feature-map crop to each tile's footprint + bilinear resample.

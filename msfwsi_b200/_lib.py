@@ -64,7 +64,7 @@ _SIGS = {
     "msf_infonce_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.c_float,
                                   C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]),
     "msf_gemm_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
-                                C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+                                C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
     "msf_crop_resample_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.c_void_p, C.c_void_p]),
     "msf_crop_resample_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,

@@ -31,6 +31,7 @@ struct GemmArgs {
   float* rowsum_part;   // EPI_EXP: [n_tiles][m_pad]
   int64_t m_pad;
   int b_mn_major;       // 0: B is [N,K] row-major (C = A B^T); 1: B is [K,N] row-major (C = A B)
+  int a_mn_major;       // 0: A is [M,K] row-major; 1: A is stored transposed, [K,M] row-major (C = A^T-stored x B)
 };
 
 template <int EPI>
@@ -77,7 +78,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           mbar_expect_tx(full + s, kStageBytes);
           uint8_t* sa = smem + s * kStageBytes;
           uint8_t* sb = sa + kABytes;
-          tma_load_2d(sa, &tm_a, kb * GBK, m0, full + s);
+          if (!g.a_mn_major) {
+            tma_load_2d(sa, &tm_a, kb * GBK, m0, full + s);  // one 64(k) x 128(m) box: rows = m, 128 B of k per row
+          } else {
+            for (int j = 0; j < BM / 64; ++j)                // two 64(m) x 64(k) boxes: rows = k, 128 B of m per row
+              tma_load_2d(sa + j * (GBK * 128), &tm_a, m0 + j * 64, kb * GBK, full + s);
+          }
           if (!g.b_mn_major) {
             tma_load_2d(sb, &tm_b, kb * GBK, n0, full + s);  // one 64 x 256 box: rows = n, 128 B of k per row
           } else {
@@ -89,7 +95,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc(GBN, g.b_mn_major != 0);
+      const uint32_t idesc = umma_idesc(GBN, g.b_mn_major != 0, g.a_mn_major != 0);
       uint32_t kb_total = 0, it = 0;
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const uint32_t buf = it & 1;
@@ -103,7 +109,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           const uint32_t a_addr = smem_u32(smem + s * kStageBytes), b_addr = a_addr + kABytes;
 #pragma unroll
           for (int k = 0; k < GBK / 16; ++k) {
-            const uint64_t ad = umma_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t ad = g.a_mn_major ? umma_desc(a_addr + k * 2048, GBK * 128, 1024) : umma_desc(a_addr + k * 32, 16, 1024);
             const uint64_t bd = g.b_mn_major ? umma_desc(b_addr + k * 2048, GBK * 128, 1024) : umma_desc(b_addr + k * 32, 16, 1024);
             mma_ss(d_tmem, ad, bd, idesc, (kb > 0 || k > 0));
           }
@@ -211,18 +217,23 @@ int launch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, 
 
 // Internal entry used by the InfoNCE two-pass path and by msf_gemm_bf16.
 int launch_gemm_tc(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
-                   int b_mn_major, int epi, float alpha, const float* bias, float* rowsum_part, int64_t m_pad, cudaStream_t st) {
+                   int b_mn_major, int epi, float alpha, const float* bias, float* rowsum_part, int64_t m_pad, cudaStream_t st,
+                   int a_mn_major) {
   MSF_REQUIRE(M > 0 && N > 0 && K > 0, MSF_ERR_INVALID, "empty GEMM %lld x %lld x %lld", (long long)M, (long long)N, (long long)K);
   MSF_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), MSF_ERR_UNSUPPORTED, "GEMM extents must fit 31 bits");
   MSF_REQUIRE(A && B && C, MSF_ERR_INVALID, "NULL operand");
   CUtensorMap ta, tb;
-  if (int rc = make_map_bf16(&ta, A, M, K, lda, GBK, BM)) return rc;
+  if (a_mn_major) {
+    if (int rc = make_map_bf16(&ta, A, K, M, lda, 64, GBK)) return rc;
+  } else {
+    if (int rc = make_map_bf16(&ta, A, M, K, lda, GBK, BM)) return rc;
+  }
   if (b_mn_major) {
     if (int rc = make_map_bf16(&tb, B, K, N, ldb, 64, GBK)) return rc;
   } else {
     if (int rc = make_map_bf16(&tb, B, N, K, ldb, GBK, GBN)) return rc;
   }
-  GemmArgs g{M, N, K, ldc, C, bias, alpha, rowsum_part, m_pad, b_mn_major};
+  GemmArgs g{M, N, K, ldc, C, bias, alpha, rowsum_part, m_pad, b_mn_major, a_mn_major};
   switch (epi) {
     case EPI_F32: return launch_epi<EPI_F32>(ta, tb, g, st);
     case EPI_BF16: return launch_epi<EPI_BF16>(ta, tb, g, st);
@@ -236,8 +247,8 @@ int launch_gemm_tc(const void* A, int64_t lda, const void* B, int64_t ldb, void*
 using namespace msf;
 
 extern "C" int msf_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t M, int64_t N,
-                             int64_t K, int b_is_kn, int out_dtype, float alpha, const float* bias, void* stream) {
+                             int64_t K, int a_is_km, int b_is_kn, int out_dtype, float alpha, const float* bias, void* stream) {
   MSF_REQUIRE(out_dtype == MSF_F32 || out_dtype == MSF_BF16, MSF_ERR_INVALID, "out_dtype must be MSF_F32 or MSF_BF16");
   return launch_gemm_tc(A, lda, B, ldb, C, ldc, M, N, K, b_is_kn, out_dtype == MSF_F32 ? 0 : 1, alpha, bias, nullptr, 0,
-                        static_cast<cudaStream_t>(stream));
+                        static_cast<cudaStream_t>(stream), a_is_km);
 }

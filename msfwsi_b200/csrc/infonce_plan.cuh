@@ -83,6 +83,7 @@ int launch_infonce_tc(const void* q_hat, const void* k_hat, int64_t nq, int64_t 
 
 // implemented in gemm_tc.cu
 int launch_gemm_tc(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
-                   int b_mn_major, int epi, float alpha, const float* bias, float* rowsum_part, int64_t m_pad, cudaStream_t st);
+                   int b_mn_major, int epi, float alpha, const float* bias, float* rowsum_part, int64_t m_pad, cudaStream_t st,
+                   int a_mn_major = 0);
 
 }  // namespace msf

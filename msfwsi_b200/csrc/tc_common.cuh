@@ -119,8 +119,8 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
          (static_cast<uint64_t>(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 // kind::f16 instruction descriptor: fp32 accumulate, bf16 x bf16, M=128
-__host__ __device__ constexpr uint32_t umma_idesc(int n, bool b_mn_major) {
-  return (1u << 4) /*D=f32*/ | (1u << 7) /*A=bf16*/ | (1u << 10) /*B=bf16*/ | (b_mn_major ? (1u << 16) : 0u) |
+__host__ __device__ constexpr uint32_t umma_idesc(int n, bool b_mn_major, bool a_mn_major = false) {
+  return (1u << 4) /*D=f32*/ | (1u << 7) /*A=bf16*/ | (1u << 10) /*B=bf16*/ | (a_mn_major ? (1u << 15) : 0u) | (b_mn_major ? (1u << 16) : 0u) |
          (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
 }
 

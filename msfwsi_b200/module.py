@@ -6,8 +6,9 @@ parameter / buffer names (so ``convert_sync_batchnorm``, DDP, the ``context_/tar
 filter of the optimizer at ssl_train.py:281-307 and checkpoints keep working).  What changes is the
 hot path after the encoder calls: the inverse-jigsaw gather + fuser concat run as one CUDA launch
 (``ops.gather_concat``) and the loss block as one fused launch (``ops.cosine_loss``) or the
-flash-style InfoNCE kernel (``ops.infonce_loss``).  Linear / BatchNorm1d of the heads stay on
-cuBLAS / ATen in this round (SURVEY 8f rank 1 is the next widening step).
+flash-style InfoNCE kernel (``ops.infonce_loss``).  Under bf16 autocast the head Linears (forward, dX, dW) run
+on this repo's persistent tcgen05 GEMM (``TCLinear`` -> ``ops.linear_tc``); BatchNorm1d stays on ATen this round
+(fusing its statistics into the GEMM epilogue is SURVEY 8f rank 1, the next widening step).
 """
 from __future__ import annotations
 
@@ -22,11 +23,28 @@ PYRAMID_WIDTHS = (64, 128, 256, 512)  # pooled layer1..4 widths of the ResNet-18
 DEFAULT_FUSER_WEIGHTS = (0.1, 0.4, 0.7, 1.0)  # --fuser_weights default, tools/ssl_train.py:623-625
 
 
+class TCLinear(nn.Linear):
+    """nn.Linear whose bf16-autocast CUDA forward/backward run on this repo's tcgen05 GEMM (ops.linear_tc).
+    Same parameters and state-dict keys as nn.Linear; outside bf16 autocast it is exactly nn.Linear (cuBLAS)."""
+    use_tc = True
+
+    def forward(self, x):
+        if (TCLinear.use_tc and x.is_cuda and x.dim() == 2 and torch.is_autocast_enabled()
+                and torch.get_autocast_dtype("cuda") == torch.bfloat16 and self.in_features % 8 == 0 and self.out_features % 8 == 0):
+            # bf16 copy of the master weight, refreshed when the optimizer has written the parameter (both views of a
+            # step share it, like autocast's per-forward cast cache)
+            key = (self.weight._version, self.weight.data_ptr())
+            if getattr(self, "_wb_key", None) != key:
+                self._wb, self._wb_key = self.weight.detach().to(torch.bfloat16), key
+            return ops.linear_tc(x, self.weight, self.bias, self._wb)
+        return super().forward(x)
+
+
 def make_projector(in_dim: int, out_dim: int) -> nn.Sequential:
     """3-layer projector, indices 0..7 as in backbone.py:12-22 (last BN has no affine)."""
     layers = []
     for width_out, affine, act in ((in_dim, True, True), (in_dim, True, True), (out_dim, False, False)):
-        layers.append(nn.Linear(in_dim, width_out, bias=False))
+        layers.append(TCLinear(in_dim, width_out, bias=False))
         layers.append(nn.BatchNorm1d(width_out, affine=affine))
         if act:
             layers.append(nn.ReLU(inplace=True))
@@ -35,8 +53,8 @@ def make_projector(in_dim: int, out_dim: int) -> nn.Sequential:
 
 def make_predictor(in_dim: int, hidden_dim: int) -> nn.Sequential:
     """2-layer bottleneck predictor, indices 0..3 as in backbone.py:25-31."""
-    return nn.Sequential(nn.Linear(in_dim, hidden_dim, bias=False), nn.BatchNorm1d(hidden_dim), nn.ReLU(inplace=True),
-                         nn.Linear(hidden_dim, in_dim))
+    return nn.Sequential(TCLinear(in_dim, hidden_dim, bias=False), nn.BatchNorm1d(hidden_dim), nn.ReLU(inplace=True),
+                         TCLinear(hidden_dim, in_dim))
 
 
 def ssl_loss(outputs, fuser_weights: Sequence[float] = DEFAULT_FUSER_WEIGHTS, mode: str = "cosine", tau: float = 0.07,

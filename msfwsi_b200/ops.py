@@ -241,6 +241,62 @@ def infonce_loss(p: torch.Tensor, z: torch.Tensor, tau: float = 0.07, precision:
 
 
 # ------------------------------------------------------------------------------------------
+# G1: Linear layers of the heads on the tcgen05 GEMM      (src/models/backbone.py:14,17,20,27,30)
+# ------------------------------------------------------------------------------------------
+def gemm_bf16(A, B, M, N, K, a_is_km=False, b_is_kn=False, out_dtype=torch.bfloat16, alpha=1.0, bias=None):
+    """C[M,N] = alpha * op(A) op(B) (+ bias) on the persistent tcgen05 kernel; A/B bf16 row-major 2-D tensors."""
+    C_ = torch.empty((M, N), dtype=out_dtype, device=A.device)
+    L.check(L.lib().msf_gemm_bf16(L.ptr(A), A.stride(0), L.ptr(B), B.stride(0), L.ptr(C_), C_.stride(0), M, N, K, int(a_is_km), int(b_is_kn),
+                                  L.dtype_code(out_dtype), float(alpha), L.ptr(bias), L.stream_ptr()), "msf_gemm_bf16")
+    L.launch_count += 1
+    return C_
+
+
+class _LinearTC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, wb):
+        L.require_cuda(x, weight)
+        xb = _contig(x.to(torch.bfloat16))
+        if wb is None:
+            wb = _contig(weight.to(torch.bfloat16))  # fp32 master weights -> bf16 operand (what autocast does for F.linear)
+        rows, fin = xb.shape
+        fout = wb.shape[0]
+        bf = None if bias is None else _contig(bias.to(torch.float32))
+        y = gemm_bf16(xb, wb, rows, fout, fin, bias=bf)
+        ctx.save_for_backward(xb, wb)
+        ctx.meta = (weight.dtype, None if bias is None else bias.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        xb, wb = ctx.saved_tensors
+        wdt, bdt = ctx.meta
+        gyb = _contig(gy.to(torch.bfloat16))
+        rows, fin = xb.shape
+        fout = wb.shape[0]
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = gemm_bf16(gyb, wb, rows, fin, fout, b_is_kn=True)                                   # dX = dY W
+        if ctx.needs_input_grad[1]:
+            gw = gemm_bf16(gyb, xb, fout, fin, rows, a_is_km=True, b_is_kn=True, out_dtype=torch.float32).to(wdt)  # dW = dY^T X
+        if bdt is not None and ctx.needs_input_grad[2]:
+            gb = gyb.sum(dim=0, dtype=torch.float32).to(bdt)
+        return gx, gw, gb, None
+
+
+def linear_tc(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+              weight_bf16: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = x W^T (+ b) in bf16 with fp32 accumulation on the tcgen05 GEMM (forward, dX and dW all on it).
+    x (rows, in), W (out, in); in and out must be multiples of 8.  ``weight_bf16`` is an optional cached bf16 copy
+    of ``weight`` (autocast caches the same cast per forward pass)."""
+    if x.dim() != 2 or weight.dim() != 2 or x.shape[1] != weight.shape[1]:
+        raise ValueError(f"linear_tc: x {tuple(x.shape)} vs weight {tuple(weight.shape)}")
+    if x.shape[1] % 8 or weight.shape[0] % 8:
+        raise ValueError("linear_tc: in/out features must be multiples of 8")
+    return _LinearTC.apply(x, weight, bias, weight_bf16)
+
+
+# ------------------------------------------------------------------------------------------
 # A2: crop + bilinear resample            (integer case: src/models/hooknet.py:29-32)
 # ------------------------------------------------------------------------------------------
 class _CropResample(torch.autograd.Function):

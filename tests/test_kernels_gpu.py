@@ -360,13 +360,22 @@ def test_infonce_bf16_autograd_entry_and_determinism():
 
 
 # ------------------------------------------------------------------ G1 tcgen05 GEMM + two-pass InfoNCE
-def _gemm(A, B, b_is_kn, out_dtype, alpha=1.0, bias=None):
-    M, K = A.shape
+def _gemm(A, B, b_is_kn, out_dtype, alpha=1.0, bias=None, a_is_km=False):
+    (K, M) = A.shape if a_is_km else A.shape[::-1]
     N = B.shape[1] if b_is_kn else B.shape[0]
     Cm = torch.empty((M, N), dtype=out_dtype, device=DEV)
-    L.check(L.lib().msf_gemm_bf16(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), Cm.data_ptr(), Cm.stride(0), M, N, K, int(b_is_kn),
-                                  L.dtype_code(out_dtype), alpha, L.ptr(bias), L.stream_ptr()), "msf_gemm_bf16")
+    L.check(L.lib().msf_gemm_bf16(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), Cm.data_ptr(), Cm.stride(0), M, N, K, int(a_is_km),
+                                  int(b_is_kn), L.dtype_code(out_dtype), alpha, L.ptr(bias), L.stream_ptr()), "msf_gemm_bf16")
     return Cm
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (512, 512, 4096), (4608, 4608, 256), (136, 72, 1000), (64, 16, 48)])
+def test_gemm_bf16_weight_gradient_layout(M, N, K):
+    """dW[out,in] = dY^T X with dY stored [rows,out] (A transposed in memory) and X [rows,in]."""
+    dY = _rand((K, M), 5, torch.bfloat16).to(DEV)
+    X = _rand((K, N), 6, torch.bfloat16).to(DEV)
+    out = _gemm(dY, X, True, torch.float32, a_is_km=True)
+    assert _relerr(out, dY.double().t() @ X.double()) <= 2e-5
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 512), (4096, 512, 512), (300, 200, 136), (1, 8, 8), (256, 4608, 4608),

@@ -175,3 +175,29 @@ def test_full_forward_with_resnet_encoders_smoke():
     loss.backward()
     assert torch.isfinite(loss) and -6.7 <= loss.item() <= 6.7
     assert all(p.grad is not None for p in m.parameters())
+
+
+@pytest.mark.parametrize("rows,fin,fout,bias", [(256, 64, 64, False), (4096, 512, 128, False), (4096, 128, 512, True), (48, 4608, 1152, False),
+                                                 (3, 576, 144, True), (1000, 16, 64, True)])
+def test_tc_linear_matches_cublas_autocast(rows, fin, fout, bias):
+    """Head Linear on the tcgen05 GEMM vs F.linear under the same bf16 autocast (what the reference runs)."""
+    torch.manual_seed(0)
+    lin = M.TCLinear(fin, fout, bias=bias).to(DEV)
+    x = torch.randn(rows, fin, device=DEV).to(torch.bfloat16)
+    w = torch.randn(rows, fout, device=DEV)
+    outs = []
+    for use_tc in (True, False):
+        M.TCLinear.use_tc = use_tc
+        lin.zero_grad(set_to_none=True)
+        xi = x.clone().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = lin(xi)
+        (y.float() * w).sum().backward()
+        outs.append((y.detach().float(), xi.grad.float(), lin.weight.grad.clone(), None if not bias else lin.bias.grad.clone()))
+    M.TCLinear.use_tc = True
+    (y1, gx1, gw1, gb1), (y0, gx0, gw0, gb0) = outs
+    assert y1.dtype == y0.dtype
+    assert (y1 - y0).norm() / y0.norm() <= 4e-3
+    assert _cos(gx1, gx0) >= 0.9999 and _cos(gw1, gw0) >= 0.9999
+    if bias:
+        assert _cos(gb1, gb0) >= 0.9999
