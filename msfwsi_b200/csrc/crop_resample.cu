@@ -85,93 +85,144 @@ __global__ void __launch_bounds__(256) crop_fwd_kernel(const void* __restrict__ 
   }
 }
 
-// ---- fast path: warp-cooperative rows, 128-bit stores ---------------------------------------------------
-// CTA = one box (b,k) x a group of channels; a lane group of ow/VEC lanes owns one output row at a time.
-//   1. the group loads the source span of the row from the two source rows with CONSECUTIVE lanes on consecutive
-//      pixels (coalesced sectors, L1-resident for the `zoom` output rows that share them) and interpolates
-//      vertically;
-//   2. every source pixel is parked in the warp's shared row as float2 {v[s], v[s+1]-v[s]} (the neighbour comes
-//      from a shuffle);
-//   3. each lane forms its VEC outputs with ONE 64-bit shared load + one FMA each (out = v + wx*dv; wx == 0 returns
-//      v exactly, so an integer box of the output size is a bit-exact copy) and stores 16 bytes.
-// x taps live in registers (a lane always owns the same output columns); y taps in shared memory.
-constexpr int kFastThreads = 256;
+// ---- fast path: one warp per (box, channel) plane, horizontal pass once per source row -----------------------
+// CTA = one box (b,k) x 8 consecutive channels (one per warp).  A warp walks down its output plane:
+//   horizontal  every source row is interpolated along x ONCE (lane owns ox = lane + 32k; neighbouring lanes read
+//               the same or adjacent source pixels, so a warp load is 1-2 sectors) into a 4-row rolling buffer in
+//               shared memory -- its cost is shared by the `zoom` output rows that reuse the row;
+//   vertical    two output rows per iteration: each lane reads 2 x (two 128-bit shared loads) of the two source
+//               rows, blends with (1-wy, wy), and stores 16 bytes (VEC outputs).
+// Weights equal to zero short-circuit, so an integer box of the output size is a bit-exact copy.
+constexpr int kFastThreads = 256, kMaxOxPerLane = 8;
 
 template <int DT>
 __global__ void __launch_bounds__(kFastThreads) crop_fwd_fast_kernel(const void* __restrict__ feat, const float* __restrict__ boxes,
-                                                                     void* __restrict__ out, Geo g, int ch_per_cta, int park_stride) {
+                                                                     void* __restrict__ out, Geo g, int kRoll) {
   constexpr int VEC = Elem<DT>::VEC;
   extern __shared__ __align__(16) float sm[];
-  const int tpr = g.ow / VEC;            // lanes per output row (power of two <= 32)
-  const int rows_per_warp = 32 / tpr;
   int* y_i0 = reinterpret_cast<int*>(sm);
   int* y_i1 = y_i0 + g.oh;
   float* y_w = reinterpret_cast<float*>(y_i1 + g.oh);
-  float2* parks = reinterpret_cast<float2*>(sm + ((3 * g.oh + 3) & ~3));  // [warps * rows_per_warp][park_stride]
-  const int groups_c = (g.C + ch_per_cta - 1) / ch_per_cta;
+  float* roll = sm + ((3 * g.oh + 3) & ~3);  // [8 warps][kRoll][ow]
+  const int groups_c = (g.C + 7) / 8;
   const int64_t bk = blockIdx.x / groups_c;
-  const int c_begin = static_cast<int>(blockIdx.x % groups_c) * ch_per_cta;
-  const int c_end = min(c_begin + ch_per_cta, g.C);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = static_cast<int>(blockIdx.x % groups_c) * 8 + warp;
   const int64_t b = bk / g.K;
   const float4 bx = __ldg(reinterpret_cast<const float4*>(boxes) + bk);  // y0,x0,y1,x1
   for (int o = threadIdx.x; o < g.oh; o += kFastThreads) axis_taps(bx.x, bx.z - bx.x, o, g.oh, g.H, y_i0[o], y_i1[o], y_w[o]);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int grp = lane / tpr, lig = lane % tpr;
-  int xs, xl0, xl1;
-  float wtmp;
-  axis_taps(bx.y, bx.w - bx.y, 0, g.ow, g.W, xs, xl0, wtmp);            // first source column of the box
-  axis_taps(bx.y, bx.w - bx.y, g.ow - 1, g.ow, g.W, xl0, xl1, wtmp);    // last one
-  const int fw = xl1 - xs + 1;                                           // <= park_stride
-  int xi0[VEC];
-  float xw[VEC];
+  // x taps of the output columns this lane interpolates in the horizontal pass
+  const int nk = g.ow >> 5;  // ow is a multiple of 32 on this path
+  int xa[kMaxOxPerLane], xb[kMaxOxPerLane];
+  float xw[kMaxOxPerLane];
 #pragma unroll
-  for (int v = 0; v < VEC; ++v) {
-    int a0, a1;
-    axis_taps(bx.y, bx.w - bx.y, lig * VEC + v, g.ow, g.W, a0, a1, xw[v]);
-    if (a1 == a0) xw[v] = 0.f;  // clamped second tap
-    xi0[v] = a0 - xs;
+  for (int k = 0; k < kMaxOxPerLane; ++k) {
+    xa[k] = xb[k] = 0;
+    xw[k] = 0.f;
+    if (k < nk) axis_taps(bx.y, bx.w - bx.y, lane + 32 * k, g.ow, g.W, xa[k], xb[k], xw[k]);
   }
   __syncthreads();
-  float2* park = parks + (warp * rows_per_warp + grp) * park_stride;
-  const int rows_per_iter = (kFastThreads / 32) * rows_per_warp;
-  const int total_rows = (c_end - c_begin) * g.oh;
-  const int iters = (total_rows + rows_per_iter - 1) / rows_per_iter;
-  const int64_t plane_sz = static_cast<int64_t>(g.H) * g.W;
-  for (int itn = 0; itn < iters; ++itn) {
-    const int r = itn * rows_per_iter + warp * rows_per_warp + grp;
-    const bool valid = r < total_rows;
-    const int cl = valid ? r / g.oh : 0, oy = valid ? r - cl * g.oh : 0;
-    const int c = c_begin + cl;
-    const float wy = y_w[oy], om = 1.f - wy;
-    const int64_t r0 = (b * g.C + c) * plane_sz + static_cast<int64_t>(y_i0[oy]) * g.W + xs;
-    const int64_t r1 = (b * g.C + c) * plane_sz + static_cast<int64_t>(y_i1[oy]) * g.W + xs;
-    for (int j0 = 0; j0 < fw; j0 += tpr) {  // group-uniform trip count
-      const int j = j0 + lig;
-      float vj = 0.f;
-      if (valid && j < fw) {
-        const float t = ld1<DT>(feat, r0 + j);
-        vj = wy == 0.f ? t : fmaf(ld1<DT>(feat, r1 + j), wy, t * om);
+  const int owv = g.ow / VEC;                 // lanes per output row (power of two <= 32)
+  const int rows_per_iter = 32 / owv;
+  // the source rows one iteration touches must fit the rolling buffer (always true unless the box is strongly
+  // down-sampled); otherwise this CTA takes the direct four-tap path
+  int fits = 1;
+  for (int o = threadIdx.x * rows_per_iter; o < g.oh; o += kFastThreads * rows_per_iter)
+    if (y_i1[min(o + rows_per_iter, g.oh) - 1] - y_i0[o] + 1 > kRoll) fits = 0;
+  fits = __syncthreads_and(fits);
+  if (c >= g.C) return;
+  const int64_t plane = (b * g.C + c) * static_cast<int64_t>(g.H) * g.W;
+  const int64_t oplane = (bk * g.C + c) * static_cast<int64_t>(g.oh) * g.ow;
+  // integer box of exactly the output size (the reference's case, hooknet.py:29-32): plain strided copy with the
+  // widest loads the source alignment allows; every lane moves one 16-byte output chunk per step
+  const bool is_copy = bx.x == floorf(bx.x) && bx.y == floorf(bx.y) && bx.z - bx.x == static_cast<float>(g.oh) &&
+                       bx.w - bx.y == static_cast<float>(g.ow) && bx.x >= 0.f && bx.y >= 0.f &&
+                       bx.z <= static_cast<float>(g.H) && bx.w <= static_cast<float>(g.W);
+  if (is_copy) {
+    constexpr int ES = 16 / VEC;  // element size in bytes
+    const char* src = static_cast<const char*>(feat) + (plane + static_cast<int64_t>(bx.x) * g.W + static_cast<int64_t>(bx.y)) * ES;
+    char* dst = static_cast<char*>(out) + oplane * ES;
+    const int64_t src_pitch = static_cast<int64_t>(g.W) * ES;
+    const int unit = static_cast<int>((reinterpret_cast<uintptr_t>(src) | static_cast<uintptr_t>(src_pitch) | 16u) &
+                                      (~(reinterpret_cast<uintptr_t>(src) | static_cast<uintptr_t>(src_pitch) | 16u) + 1));  // lowest set bit
+    const int chunks = g.oh * owv;
+    for (int e = lane; e < chunks; e += 32) {
+      const int oy = e / owv, xc = e - oy * owv;
+      const char* sp = src + oy * src_pitch + xc * 16;
+      uint4 v;
+      if (unit >= 16) {
+        v = ldg_stream(sp);
+      } else if (unit == 8) {
+        const uint2 a = __ldg(reinterpret_cast<const uint2*>(sp)), b2 = __ldg(reinterpret_cast<const uint2*>(sp + 8));
+        v = make_uint4(a.x, a.y, b2.x, b2.y);
+      } else if (unit == 4) {
+        v = make_uint4(__ldg(reinterpret_cast<const uint32_t*>(sp)), __ldg(reinterpret_cast<const uint32_t*>(sp + 4)),
+                       __ldg(reinterpret_cast<const uint32_t*>(sp + 8)), __ldg(reinterpret_cast<const uint32_t*>(sp + 12)));
+      } else {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          w[i] = static_cast<uint32_t>(__ldg(reinterpret_cast<const uint16_t*>(sp + 4 * i))) |
+                 (static_cast<uint32_t>(__ldg(reinterpret_cast<const uint16_t*>(sp + 4 * i + 2))) << 16);
+        v = make_uint4(w[0], w[1], w[2], w[3]);
       }
-      float vn = __shfl_down_sync(0xffffffffu, vj, 1, tpr);     // v[j+1] from the next lane of the group (warp-uniform loop)
-      if (lig == tpr - 1) {                                      // ... or the first pixel of the next batch
-        vn = vj;
-        if (valid && j + 1 < fw) {
-          const float t = ld1<DT>(feat, r0 + j + 1);
-          vn = wy == 0.f ? t : fmaf(ld1<DT>(feat, r1 + j + 1), wy, t * om);
-        }
-      }
-      if (valid && j < fw) park[j] = make_float2(vj, j + 1 < fw ? vn - vj : 0.f);
+      stg_stream(dst + static_cast<int64_t>(e) * 16, v);
     }
+    return;
+  }
+  if (!fits) {
+    for (int e = lane; e < g.oh * g.ow; e += 32) {
+      const int oy = e / g.ow, ox = e - oy * g.ow;
+      int x0, x1;
+      float wx;
+      axis_taps(bx.y, bx.w - bx.y, ox, g.ow, g.W, x0, x1, wx);
+      const int64_t r0 = plane + static_cast<int64_t>(y_i0[oy]) * g.W, r1 = plane + static_cast<int64_t>(y_i1[oy]) * g.W;
+      const float top = lerp_exact(ld1<DT>(feat, r0 + x0), wx == 0.f ? 0.f : ld1<DT>(feat, r0 + x1), wx);
+      float bot = 0.f;
+      if (y_w[oy] != 0.f) bot = lerp_exact(ld1<DT>(feat, r1 + x0), wx == 0.f ? 0.f : ld1<DT>(feat, r1 + x1), wx);
+      st1<DT>(out, oplane + e, lerp_exact(top, bot, y_w[oy]));
+    }
+    return;
+  }
+  float* myroll = roll + warp * kRoll * g.ow;
+  const int r_in = lane / owv, xv = lane - r_in * owv;
+  int y_have = y_i0[0] - 1;                   // highest source row already in the rolling buffer
+  for (int oy0 = 0; oy0 < g.oh; oy0 += rows_per_iter) {
+    const int oy_last = min(oy0 + rows_per_iter, g.oh) - 1;
+    const int y_need = y_i1[oy_last];
+    int y_from = max(y_have + 1, y_i0[oy0]);  // rows below the window are never read again
+    for (int y = y_from; y <= y_need; ++y) {
+      const int64_t row = plane + static_cast<int64_t>(y) * g.W;
+      float* dst = myroll + (y & (kRoll - 1)) * g.ow + lane;
+#pragma unroll
+      for (int k = 0; k < kMaxOxPerLane; ++k)
+        if (k < nk) {
+          const float a = ld1<DT>(feat, row + xa[k]);
+          dst[32 * k] = xw[k] == 0.f ? a : fmaf(ld1<DT>(feat, row + xb[k]), xw[k], a * (1.f - xw[k]));
+        }
+    }
+    y_have = max(y_have, y_need);
     __syncwarp();
-    if (valid) {
+    const int oy = oy0 + r_in;
+    if (oy < g.oh) {
+      const float wy = y_w[oy], om = 1.f - wy;
+      const float* top = myroll + (y_i0[oy] & (kRoll - 1)) * g.ow + xv * VEC;
+      const float* bot = myroll + (y_i1[oy] & (kRoll - 1)) * g.ow + xv * VEC;
       float res[VEC];
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        const float2 p2 = park[xi0[v]];
-        res[v] = fmaf(xw[v], p2.y, p2.x);
+      for (int v = 0; v < VEC; v += 4) {
+        const float4 t4 = *reinterpret_cast<const float4*>(top + v);
+        res[v] = t4.x; res[v + 1] = t4.y; res[v + 2] = t4.z; res[v + 3] = t4.w;
       }
-      const int64_t o = (((bk * g.C + c) * g.oh + oy) * static_cast<int64_t>(g.ow)) + lig * VEC;
-      stg_stream(static_cast<char*>(out) + o * (16 / VEC), Elem<DT>::pack(res));
+      if (wy != 0.f) {
+#pragma unroll
+        for (int v = 0; v < VEC; v += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bot + v);
+          res[v] = fmaf(b4.x, wy, res[v] * om); res[v + 1] = fmaf(b4.y, wy, res[v + 1] * om);
+          res[v + 2] = fmaf(b4.z, wy, res[v + 2] * om); res[v + 3] = fmaf(b4.w, wy, res[v + 3] * om);
+        }
+      }
+      stg_stream(static_cast<char*>(out) + (oplane + static_cast<int64_t>(oy) * g.ow + xv * VEC) * (16 / VEC), Elem<DT>::pack(res));
     }
     __syncwarp();
   }
@@ -232,20 +283,16 @@ extern "C" int msf_crop_resample_fwd(const void* feat, int64_t B, int C, int H, 
   const int vec = 16 / static_cast<int>(dtype_size(dtype));
   const bool vec_ok = (ow % vec == 0) && aligned16(out);
   const int64_t rows = B * K * static_cast<int64_t>(C) * oh;
-  const int tpr = vec_ok ? ow / vec : 0;
-  const int park_stride = (W + 2 + 1) & ~1;
-  const size_t fast_smem = static_cast<size_t>((3 * oh + 3) & ~3) * 4 +
-                           static_cast<size_t>(kFastThreads / 32) * (tpr > 0 && tpr <= 32 ? 32 / tpr : 1) * park_stride * 8;
-  const bool fast_ok = vec_ok && tpr >= 1 && tpr <= 32 && (tpr & (tpr - 1)) == 0 && fast_smem <= 48 * 1024 && B * K < (1ll << 24);
+  // fast path: output rows of 32..256 pixels (multiple of 32); rolling buffer of kRoll source rows per warp
+  const int owv = vec_ok ? ow / vec : 0;
+  int kroll = 4;
+  while (kroll < 32 && kroll * 2 * ow <= 1024) kroll *= 2;
+  const size_t fast_smem = (static_cast<size_t>((3 * oh + 3) & ~3) + static_cast<size_t>(8) * kroll * ow) * 4;
+  const bool fast_ok = vec_ok && ow % 32 == 0 && ow <= 32 * kMaxOxPerLane && owv <= 32 && (owv & (owv - 1)) == 0 &&
+                       fast_smem <= 48 * 1024 && B * K < (1ll << 24);
   if (fast_ok) {
-    // enough CTAs for several waves of 148 SMs x 8 CTAs while keeping >= 256 output rows per CTA
-    int ch_per_cta = C;
-    while (ch_per_cta > 1 && (static_cast<int64_t>(ch_per_cta / 2) * oh >= 256) &&
-           B * K * ((C + ch_per_cta - 1) / ch_per_cta) < static_cast<int64_t>(kNumSMs) * 64)
-      ch_per_cta = (ch_per_cta + 1) / 2;
-    const int64_t ctas = B * K * ((C + ch_per_cta - 1) / ch_per_cta);
-    MSF_DISPATCH_DTYPE(dtype, (crop_fwd_fast_kernel<DT><<<static_cast<unsigned>(ctas), kFastThreads, fast_smem, st>>>(
-                                  feat, boxes, out, g, ch_per_cta, park_stride)));
+    const int64_t ctas = B * K * ((C + 7) / 8);
+    MSF_DISPATCH_DTYPE(dtype, (crop_fwd_fast_kernel<DT><<<static_cast<unsigned>(ctas), kFastThreads, fast_smem, st>>>(feat, boxes, out, g, kroll)));
   } else if (vec_ok) {
     const int64_t total = rows * (ow / vec);
     MSF_DISPATCH_DTYPE(dtype, (crop_fwd_kernel<DT, Elem<DT>::VEC><<<grid_for(total), 256, 0, st>>>(feat, boxes, out, g, total)));

@@ -416,3 +416,19 @@ def test_infonce_bf16_two_pass_wide_dims(nq, n, dim, off):
     L.check(L.lib().msf_infonce_bwd(q_hat.data_ptr(), k_hat.data_ptr(), q_inv.data_ptr(), nq, n, dim, off, tau, prec, g.data_ptr(),
                                     1.0 / nq, ws.data_ptr(), ws_bytes, grad.data_ptr(), L.MSF_F32, L.stream_ptr()), "bwd")
     assert _cos(grad, O.infonce_grad(q.double(), k.double(), tau, off)) >= 0.9999
+
+
+@pytest.mark.parametrize("H,W,oh,ow,scale", [(128, 128, 128, 128, 4), (128, 128, 32, 32, 4), (64, 96, 64, 32, 2), (256, 256, 32, 64, 1),
+                                              (40, 40, 32, 256, 2)])
+def test_crop_resample_fast_path_shapes(H, W, oh, ow, scale):
+    """Shapes that take the warp-per-plane fast path (ow multiple of 32), incl. strong down-sampling (fallback inside)."""
+    B, Cc = 2, 11  # channel count not a multiple of 8: idle warps in the last channel group
+    x = _rand((B, Cc, H, W), 13).to(torch.bfloat16)
+    boxes = ops.footprint_boxes(B, scale, H, W, "cpu")
+    out = ops.crop_resample(x.to(DEV), boxes.to(DEV), (oh, ow)).cpu()
+    for t, (y0, x0, y1, x1) in enumerate(O.blockshaped_coords(H, W, H // scale, W // scale).tolist()):
+        it = torch.nn.functional.interpolate(x[:, :, y0:y1, x0:x1].float(), size=(oh, ow), mode="bilinear", align_corners=False)
+        assert torch.allclose(out[:, t].float(), it, rtol=1e-2, atol=1e-2), (t, (out[:, t].float() - it).abs().max())
+    if (H // scale, W // scale) == (oh, ow):  # integer copy stays bit-exact
+        for t, (y0, x0, y1, x1) in enumerate(O.blockshaped_coords(H, W, oh, ow).tolist()):
+            assert torch.equal(out[:, t], x[:, :, y0:y1, x0:x1])

@@ -120,7 +120,9 @@ def main():
             outp = torch.empty((Bc, 16, Cc, oh, ow), dtype=dt, device=dev)
             cr = lambda: L.check(L.lib().msf_crop_resample_fwd(feat.data_ptr(), Bc, Cc, H, W, boxes.data_ptr(), 16, oh, ow, L.dtype_code(dt),
                                                                outp.data_ptr(), L.stream_ptr()), "crop")
-            rec(f"A2 crop_resample fwd {dt} {tag}", nbytes, timeit(cr), f"feat {tuple(feat.shape)} -> {oh}x{ow}")
+            wr = Bc * 16 * Cc * oh * ow * e
+            rec(f"A2 crop_resample fwd {dt} {tag}", nbytes, timeit(cr),
+                f"feat {tuple(feat.shape)} -> {oh}x{ow}; {100 * wr // nbytes}% of the bytes are writes (write-only probe on this GPU: ~3.96 TB/s, tools/probe_write_bw.py)")
             del feat, outp
     if args.out:
         json.dump({"peak_GBps": peak, "rows": rows}, open(args.out, "w"), indent=1)
