@@ -79,7 +79,16 @@ def reference_arm(args):
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -166,7 +175,10 @@ def ours(args):
     model = model.to(dev).to(memory_format=torch.channels_last).train()
     step_mod = LossStep(model)
     if world > 1:
-        step_mod = torch.nn.parallel.DistributedDataParallel(step_mod, device_ids=[local])  # ssl_train.py:170
+        # ssl_train.py:170; SyncBN keeps the buffers identical on every rank, so the per-forward buffer broadcast is
+        # redundant; large buckets suit NVSwitch (latency-, not link-bound)
+        step_mod = torch.nn.parallel.DistributedDataParallel(step_mod, device_ids=[local], broadcast_buffers=False,
+                                                             gradient_as_bucket_view=True, bucket_cap_mb=128)
     lr = 1e-3 * (args.batch * world) ** 0.5 / 32 ** 0.5  # ssl_train.py:155
     groups = [{"params": [p for n, p in model.named_parameters() if n.startswith(pre)]} for pre in ("context_", "target_", "inter_")]
     opt = torch.optim.Adam(groups, lr=lr, fused=True)
@@ -282,7 +294,7 @@ def ours(args):
                 "encoder_images_per_sec": value * 34}
         if micro:
             line["roofline_microbench"] = micro["rows"]
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -342,6 +354,11 @@ def infonce_microbench(torch, ops, _lib, dev, peaks):
 
 def main():
     args = parse()
+    # Only the JSON line may reach stdout: libraries (NCCL prints its version banner there) get stderr instead.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         reference_arm(args)
     else:
