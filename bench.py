@@ -262,15 +262,25 @@ def ours(args):
         pass
     roofline = None
     if prof:
-        tc = [(a.elapsed_time(b), fl) for a, b, fl, tcpath in prof if tcpath]
-        if tc:
-            t_ms, fl = sum(t for t, _ in tc), sum(f for _, f in tc)
+        flash = [(a.elapsed_time(b), fl, d) for a, b, fl, kind, d in prof if kind == "flash"]
+        if flash:
+            t_ms, fl = sum(t for t, _, _ in flash), sum(f for _, f, _ in flash)
             peak = peaks.get("bf16_tflops_sustained", 1400.0)
-            roofline = {"kernel": "infonce_tc_kernel (+finalize) inside the step: target branch, dims 64/128/256, N=16*batch",
+            per_dim = {}
+            for t, f, d in flash:
+                e = per_dim.setdefault(str(d), [0.0, 0.0, 0])
+                e[0] += t; e[1] += f; e[2] += 1
+            roofline = {"kernel": "infonce_tc_kernel<D> (flash tcgen05 main kernel) inside the timed steps: N = 16*batch*gpus keys, "
+                                  "Nq = 16*batch (target branch) or batch rows, D in {64,128,256}",
                         "bound": "tensor", "achieved": fl / t_ms / 1e9, "peak": peak,
                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback", "unit": "TFLOP/s",
-                        "frac": fl / t_ms / 1e9 / peak, "traffic": None, "launches": len(tc), "avg_us": 1e3 * t_ms / len(tc),
-                        "flops_per_launch": fl / len(tc)}
+                        "frac": fl / t_ms / 1e9 / peak, "traffic": None, "launches": len(flash), "avg_us": 1e3 * t_ms / len(flash),
+                        "flops_per_launch": fl / len(flash),
+                        "per_dim": {d: {"launches": v[2], "avg_us": 1e3 * v[0] / v[2], "tflops": v[1] / v[0] / 1e9} for d, v in per_dim.items()},
+                        "timing": "cudaEventRecord by the library immediately before/after the main kernel on its stream"}
+            other = [(a.elapsed_time(b), fl) for a, b, fl, kind, d in prof if kind != "flash"]
+            if other:
+                roofline["two_pass_gemm_paths"] = {"launches": len(other), "tflops": sum(f for _, f in other) / sum(t for t, _ in other) / 1e9}
     micro = None
     if rank == 0 and not args.no_microbench:
         micro = infonce_microbench(torch, ops, _lib, dev, peaks)

@@ -146,6 +146,12 @@ int msf_infonce_plan_info(int64_t nq, int64_t n_keys, int dim, int precision, in
 int msf_infonce_fwd(const void* q_hat, const void* k_hat, int64_t nq, int64_t n_keys, int dim,
                     int64_t pos_offset, float tau, int precision, float* loss_sum_out, float* row_lse,
                     void* workspace, size_t workspace_bytes, void* stream);
+/* Same as msf_infonce_fwd, additionally recording two caller-owned cudaEvent_t (passed as void*, may be NULL) on
+ * `stream` immediately before and after the MAIN kernel (flash tcgen05 kernel, or the two GEMM passes, or the SIMT
+ * kernel) -- used by bench.py to time the dominant kernel alone, without the small finalize launches. */
+int msf_infonce_fwd_timed(const void* q_hat, const void* k_hat, int64_t nq, int64_t n_keys, int dim, int64_t pos_offset,
+                          float tau, int precision, float* loss_sum_out, float* row_lse, void* workspace,
+                          size_t workspace_bytes, void* stream, void* ev_main_start, void* ev_main_stop);
 /* grad_q = *grad_out * scale * J_normalize(q)^T [ (O_i / rowsum_i - k_hat_pos(i)) / tau ],
  * scale = 1 / n_rows_global supplied by the caller. */
 int msf_infonce_bwd(const void* q_hat, const void* k_hat, const float* q_inv_norm, int64_t nq, int64_t n_keys,

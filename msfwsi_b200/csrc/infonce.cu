@@ -361,6 +361,14 @@ extern "C" int msf_infonce_plan_info(int64_t nq, int64_t n_keys, int dim, int pr
 extern "C" int msf_infonce_fwd(const void* q_hat, const void* k_hat, int64_t nq, int64_t n_keys, int dim,
                                int64_t pos_offset, float tau, int precision, float* loss_sum_out, float* row_lse,
                                void* workspace, size_t workspace_bytes, void* stream) {
+  return msf_infonce_fwd_timed(q_hat, k_hat, nq, n_keys, dim, pos_offset, tau, precision, loss_sum_out, row_lse, workspace,
+                               workspace_bytes, stream, nullptr, nullptr);
+}
+
+extern "C" int msf_infonce_fwd_timed(const void* q_hat, const void* k_hat, int64_t nq, int64_t n_keys, int dim,
+                                     int64_t pos_offset, float tau, int precision, float* loss_sum_out, float* row_lse,
+                                     void* workspace, size_t workspace_bytes, void* stream, void* ev_main_start,
+                                     void* ev_main_stop) {
   if (int rc = check_nce(q_hat, k_hat, nq, n_keys, dim, pos_offset, tau, precision)) return rc;
   MSF_REQUIRE(loss_sum_out, MSF_ERR_INVALID, "loss_sum_out is NULL");
   const NcePlan plan = make_nce_plan(nq, n_keys, dim, precision);
@@ -374,6 +382,7 @@ extern "C" int msf_infonce_fwd(const void* q_hat, const void* k_hat, int64_t nq,
   float* sum_tot = reinterpret_cast<float*>(ws + plan.off_sum);
   float* partials = reinterpret_cast<float*>(ws + plan.off_part);
   const float a = kLog2e / tau;
+  if (ev_main_start) MSF_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(ev_main_start), st));
   if (plan.mode == 0) {
     if (int rc = launch_infonce_tc(q_hat, k_hat, nq, n_keys, dim, tau, plan, rowsum, o_part, st)) return rc;
   } else if (plan.mode == 2) {
@@ -389,6 +398,7 @@ extern "C" int msf_infonce_fwd(const void* q_hat, const void* k_hat, int64_t nq,
                                               n_keys, dim, a, a, plan.tiles_per_split, plan.nq_pad, rowsum, o_part);
     MSF_LAUNCH_OK("infonce_simt_kernel");
   }
+  if (ev_main_stop) MSF_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(ev_main_stop), st));
   const uint32_t cpr = dim / (precision == MSF_BF16 ? 8 : 4);
   const uint32_t lanes = lanes_for(cpr), groups = 256 / lanes;
   const unsigned blocks = static_cast<unsigned>((nq + groups - 1) / groups);
