@@ -202,6 +202,51 @@ int msf_ema_multi(const msf_ema_entry* entries /*device*/, const int32_t* chunk_
                   int total_chunks, int teacher_dtype, int student_dtype, float momentum, float one_minus_momentum,
                   void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * N1  channels-last train-mode BatchNorm2d of the encoders with the element-wise work around it fused in
+ * (caller side of the hot path: src/models/resnet.py:59-82 BasicBlock `bn -> relu`, `bn -> (+identity) -> relu`,
+ * and the stem `bn1 -> relu -> maxpool` of src/models/resnet.py:244-247; statistics follow
+ * torch.nn.BatchNorm2d / SyncBatchNorm, tools/ssl_train.py:160).  The convolutions stay on cuDNN.
+ * The activation is a [rows = N*H*W][C] matrix, C contiguous (NHWC), C a multiple of 8 (16-bit) or 4 (fp32).
+ *
+ * forward : msf_bn2d_stats -> (all-reduce `sums` over ranks for SyncBN) -> msf_bn2d_finalize -> msf_bn2d_apply[_pool]
+ * backward: msf_bn2d[_pool]_bwd_reduce -> (all-reduce) -> msf_bn2d[_pool]_bwd_elemt
+ *   sums (forward)  : 2C+1 doubles {sum x, sum x^2 per channel, element count} -- sum-reducible over ranks
+ *   sums (backward) : 2C doubles {sum dy', sum dy' * xhat}; grad_beta = sums[0:C], grad_gamma = sums[C:2C] (local part)
+ *   dy' = dy * (y > 0) when relu != 0; y is recomputed from x, or read from `y_mask` (the saved output) when the
+ *   forward added a residual.  gamma / beta may be NULL (1 / 0).
+ * ---------------------------------------------------------------------------------------- */
+size_t msf_bn2d_workspace_bytes(int64_t rows, int C);
+int msf_bn2d_stats(const void* x, int64_t rows, int C, int dtype, double* sums_out /*2C+1*/, void* workspace,
+                   size_t workspace_bytes, void* stream);
+/* mean / invstd (fp32, C each) from sums; running_mean / running_var (both or neither) get the momentum update with
+ * the unbiased variance, like torch.nn.BatchNorm2d. */
+int msf_bn2d_finalize(const double* sums /*2C+1*/, int C, float eps, float momentum, float* mean, float* invstd,
+                      float* running_mean, float* running_var, void* stream);
+/* y = act(gamma * (x - mean) * invstd + beta (+ res)); res may be NULL; relu != 0 applies max(., 0). */
+int msf_bn2d_apply(const void* x, const void* res, void* y, int64_t rows, int C, int dtype, const float* mean,
+                   const float* invstd, const float* gamma, const float* beta, int relu, void* stream);
+int msf_bn2d_bwd_reduce(const void* x, const void* dy, const void* y_mask, int64_t rows, int C, int dtype,
+                        const float* mean, const float* invstd, const float* gamma, const float* beta, int relu,
+                        double* sums_out /*2C*/, void* workspace, size_t workspace_bytes, void* stream);
+/* dx = gamma*invstd * (dy' - sums[c]/count - xhat * sums[C+c]/count); dres (may be NULL) = dy'.
+ * `count` is a DEVICE double (element 2C of the forward sums). */
+int msf_bn2d_bwd_elemt(const void* x, const void* dy, const void* y_mask, void* dx, void* dres, int64_t rows, int C,
+                       int dtype, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                       int relu, const double* sums /*2C*/, const double* count, void* stream);
+/* Stem: y (N,PH,PW,C) = maxpool3x3/stride2/pad1(relu(bn(x))), x (N,H,W,C), PH = (H-1)/2+1, PW = (W-1)/2+1;
+ * tap (N,PH,PW,C) uint8 = arg-max tap dr*3+dc of each output (first maximum in scan order over the values as
+ * rounded to `dtype`, ATen's max_pool2d rule), 255 where the output is 0 (no gradient). */
+int msf_bn2d_apply_pool(const void* x, void* y, uint8_t* tap, int64_t N, int H, int W, int C, int dtype,
+                        const float* mean, const float* invstd, const float* gamma, const float* beta, void* stream);
+int msf_bn2d_pool_bwd_reduce(const void* x, const void* dpool, const uint8_t* tap, int64_t N, int H, int W, int C,
+                             int dtype, const float* mean, const float* invstd, double* sums_out /*2C*/,
+                             void* workspace, size_t workspace_bytes /* msf_bn2d_workspace_bytes(N*PH*PW, C) */,
+                             void* stream);
+int msf_bn2d_pool_bwd_elemt(const void* x, const void* dpool, const uint8_t* tap, void* dx, int64_t N, int H, int W,
+                            int C, int dtype, const float* mean, const float* invstd, const float* gamma,
+                            const double* sums /*2C*/, const double* count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,783 @@
+// Channels-last (NHWC) train-mode BatchNorm2d for the encoders that feed the hot path, with the element-wise work
+// around it fused in: ReLU, the residual add of a BasicBlock, and the stem's 3x3/2 max-pool.  (Caller-side helper:
+// the convolutions stay on cuDNN.  ATen's channels-last batch-norm / max-pool / add / relu kernels reach 0.5-1 TB/s on
+// the 64..512-channel ResNet-18 activations and together cost 2.7x the convolutions at batch 4096; every kernel here
+// is a streaming pass bounded by HBM bandwidth.)
+//
+// The activation is viewed as a [rows = N*H*W][C] matrix with C contiguous.
+//   bn_stats          partial per-channel sum / sum of squares per CTA (fp32 in registers, fixed-order shared reduce)
+//   bn_combine        partials -> fp64 sums[2C] (+ the element count at sums[2C], so a cross-rank all-reduce of the
+//                     whole vector yields global statistics even with unequal per-rank batches)
+//   bn_finalize       sums -> mean, invstd, running-stat update
+//   bn_apply          y = act(x * sc + sh (+ res)),  sc = gamma*invstd, sh = beta - mean*sc
+//   bn_bwd_reduce     partial sum(dy'), sum(dy' * xhat), dy' = dy * (y > 0); y is recomputed from x (no mask stored)
+//                     or, with a residual, read from the saved output
+//   bn_bwd_elemt      dx = sc * (dy' - mean(dy') - xhat * mean(dy' * xhat));  dres = dy'
+//   bn_apply_pool     stem: y = maxpool3x3/2/pad1(relu(bn(x))) + one byte per output with the arg-max tap (255 = dead)
+//   bn_pool_bwd_*     the two backward passes through pool + relu + bn from the pooled gradient and the tap bytes
+// Bytes per element: forward 2 reads + 1 write, backward 4 reads + 1 write (+1 read / +1 write with a residual).
+// 64-bit indexing throughout (the stem activation of a 4096-image batch has 3.3e9 elements).
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace msf {
+namespace {
+
+constexpr int kThreads = 256;
+
+// thread layout inside a CTA of the reduce kernels: `ct` consecutive threads cover `ct` 16-byte chunks of a row
+// (a "column group"), kThreads/ct row lanes walk the rows.  CTA b handles the row groups b, b+G, b+2G, ... (G = grid
+// size = SMs x resident CTAs, so there is exactly one wave and all CTAs sweep memory together).
+constexpr int kMaxRowBlocks = kNumSMs * 8;
+struct Layout {
+  int cvec;     // 16-byte chunks per row
+  int ct;       // chunks per column group handled by one CTA (power of two <= 32)
+  int cgroups;  // column groups
+  int rlanes;   // row lanes per CTA
+};
+inline Layout make_layout(int C, int vec) {
+  Layout l;
+  l.cvec = C / vec;
+  l.ct = 1;
+  while (l.ct < 32 && l.ct * 2 <= l.cvec && l.cvec % (l.ct * 2) == 0) l.ct *= 2;
+  l.cgroups = l.cvec / l.ct;
+  l.rlanes = kThreads / l.ct;
+  return l;
+}
+// number of row blocks (grid.x) for a reduce kernel: one wave of resident CTAs, never more than the rows need
+template <typename Kern>
+inline int reduce_grid(Kern kern, size_t smem, const Layout& l, int64_t rows, int rows_per_iter) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem) != cudaSuccess || occ < 1) occ = 1;
+  int64_t g = static_cast<int64_t>(kNumSMs) * occ / l.cgroups;
+  const int64_t need = (rows + rows_per_iter - 1) / rows_per_iter;
+  if (g > need) g = need;
+  if (g > kMaxRowBlocks) g = kMaxRowBlocks;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+template <int DT>
+__device__ __forceinline__ float round_store(float v) {  // the value a store in dtype DT followed by a load returns
+  if (DT == MSF_BF16) return __bfloat162float(__float2bfloat16_rn(v));
+  if (DT == MSF_F16) return __half2float(__float2half_rn(v));
+  return v;
+}
+
+// fixed-order reduction of the per-thread accumulators over the row lanes of a CTA -> partial[blk][2][C]
+template <int V>
+__device__ __forceinline__ void cta_reduce_store(const float* s, const float* q, int ct, int cvec, int cl, int rl,
+                                                 float* __restrict__ partial) {
+  extern __shared__ float sm[];
+  const int rlanes = kThreads / ct;
+  float* mine = sm + (static_cast<size_t>(rl) * ct + cl) * (2 * V);
+#pragma unroll
+  for (int i = 0; i < V; ++i) { mine[i] = s[i]; mine[V + i] = q[i]; }
+  __syncthreads();
+  for (int e = threadIdx.x; e < ct * 2 * V; e += kThreads) {
+    const int c2 = e / (2 * V), k = e % (2 * V);
+    float t = 0.f;
+    for (int j = 0; j < rlanes; ++j) t += sm[(static_cast<size_t>(j) * ct + c2) * (2 * V) + k];
+    const int C = cvec * V;
+    const int ch = (blockIdx.y * ct + c2) * V + (k % V);
+    partial[(static_cast<size_t>(blockIdx.x) * 2 + (k / V)) * C + ch] = t;
+  }
+}
+
+constexpr int kStatsRows = 8;  // rows in flight per thread
+template <int DT>
+__global__ void __launch_bounds__(kThreads) bn_stats_kernel(const char* __restrict__ x, int64_t rows, int cvec, int ct,
+                                                            float* __restrict__ partial) {
+  constexpr int V = Elem<DT>::VEC;
+  constexpr int U = kStatsRows;
+  const int cl = threadIdx.x % ct, rl = threadIdx.x / ct, rlanes = kThreads / ct;
+  const int chunk = blockIdx.y * ct + cl;
+  float s[V], q[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) s[i] = q[i] = 0.f;
+  const int64_t step = static_cast<int64_t>(gridDim.x) * U * rlanes;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * U * rlanes + rl; r < rows; r += step) {
+    uint4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t rr = r + u * rlanes;
+      v[u] = make_uint4(0, 0, 0, 0);
+      if (rr < rows) v[u] = ldg_stream(x + (rr * cvec + chunk) * 16);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float f[V];
+      Elem<DT>::unpack(v[u], f);
+#pragma unroll
+      for (int i = 0; i < V; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+    }
+  }
+  cta_reduce_store<V>(s, q, ct, cvec, cl, rl, partial);
+}
+
+// partial [nblk][2][C] -> sums[2][C] (fp64); sums[2C] = count when count >= 0.  32 consecutive (which, channel) entries
+// per CTA, 8 block lanes each summing every 8th row block, combined in fixed order.
+__global__ void __launch_bounds__(256) bn_combine_kernel(const float* __restrict__ partial, int nblk, int C, double* __restrict__ sums,
+                                                         double count) {
+  __shared__ double sh[8][32];
+  const int lane = threadIdx.x & 31, sub = threadIdx.x >> 5;
+  const int e = blockIdx.x * 32 + lane;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && count >= 0.0) sums[2 * C] = count;
+  double t = 0.0;
+  if (e < 2 * C)
+    for (int b = sub; b < nblk; b += 8) t += static_cast<double>(partial[static_cast<size_t>(b) * 2 * C + e]);
+  sh[sub][lane] = t;
+  __syncthreads();
+  if (sub == 0 && e < 2 * C) {
+    double a = sh[0][lane];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) a += sh[j][lane];
+    sums[e] = a;
+  }
+}
+
+// sums[2C+1] (possibly all-reduced over ranks) -> mean, invstd, running stats (momentum update, unbiased variance)
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, int C, float eps, float momentum, float* __restrict__ mean,
+                                   float* __restrict__ invstd, float* __restrict__ running_mean, float* __restrict__ running_var) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= C) return;
+  const double count = sums[2 * C];
+  const double m = sums[ch] / count;
+  double var = sums[C + ch] / count - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[ch] = static_cast<float>(m);
+  invstd[ch] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  if (running_mean) {
+    const double unbiased = count > 1.0 ? var * (count / (count - 1.0)) : var;
+    running_mean[ch] = static_cast<float>((1.0 - momentum) * running_mean[ch] + momentum * m);
+    running_var[ch] = static_cast<float>((1.0 - momentum) * running_var[ch] + momentum * unbiased);
+  }
+}
+
+// per-channel constants of one 16-byte chunk
+template <int V>
+struct ChanConst {
+  float sc[V], sh[V];
+  __device__ __forceinline__ void load(int ch0, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      sc[i] = __ldg(invstd + ch0 + i) * (gamma ? __ldg(gamma + ch0 + i) : 1.f);
+      sh[i] = fmaf(-__ldg(mean + ch0 + i), sc[i], beta ? __ldg(beta + ch0 + i) : 0.f);  // explicit: fwd and bwd kernels must agree bit for bit
+    }
+  }
+};
+
+template <int DT, bool RES>
+__global__ void __launch_bounds__(kThreads) bn_apply_kernel(const char* __restrict__ x, const char* __restrict__ res,
+                                                            char* __restrict__ y, int64_t chunks, int cvec,
+                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta, int relu) {
+  constexpr int V = Elem<DT>::VEC;
+  constexpr int U = RES ? 2 : 4;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
+  const bool fixed = (kThreads % cvec) == 0;  // then a thread always sees the same channel chunk: constants in registers
+  ChanConst<V> k;
+  if (fixed) k.load((threadIdx.x % cvec) * V, mean, invstd, gamma, beta);
+  for (int64_t e = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; e < chunks; e += U * stride) {
+    uint4 v[U], w[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (e + u * stride < chunks) {
+        v[u] = ldg_stream(x + (e + u * stride) * 16);
+        if (RES) w[u] = ldg_stream(res + (e + u * stride) * 16);
+      }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t idx = e + u * stride;
+      if (idx >= chunks) break;
+      if (!fixed) k.load(static_cast<int>(idx % cvec) * V, mean, invstd, gamma, beta);
+      float f[V], g[V];
+      Elem<DT>::unpack(v[u], f);
+      if (RES) Elem<DT>::unpack(w[u], g);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        float o = fmaf(f[i], k.sc[i], k.sh[i]);
+        if (RES) o += g[i];
+        if (relu) o = fmaxf(o, 0.f);
+        f[i] = o;
+      }
+      stg_stream(y + idx * 16, Elem<DT>::pack(f));
+    }
+  }
+}
+
+// MASK: 0 none, 1 relu mask recomputed from x, 2 relu mask from the saved output y
+constexpr int kReduceRows = 4;  // rows in flight per thread (x 2 or 3 tensors)
+template <int DT, int MASK>
+__global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const char* __restrict__ x, const char* __restrict__ dy,
+                                                                 const char* __restrict__ ymask, int64_t rows, int cvec, int ct,
+                                                                 const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                 float* __restrict__ partial) {
+  constexpr int V = Elem<DT>::VEC;
+  constexpr int U = kReduceRows;
+  const int cl = threadIdx.x % ct, rl = threadIdx.x / ct, rlanes = kThreads / ct;
+  const int chunk = blockIdx.y * ct + cl;
+  float mu[V], is[V], s[V], q[V];
+  ChanConst<V> k;
+  if (MASK == 1) k.load(chunk * V, mean, invstd, gamma, beta);
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    mu[i] = mean[chunk * V + i];
+    is[i] = invstd[chunk * V + i];
+    s[i] = q[i] = 0.f;
+  }
+  const int64_t step = static_cast<int64_t>(gridDim.x) * U * rlanes;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * U * rlanes + rl; r < rows; r += step) {
+    uint4 a[U], b[U], m[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t rr = r + u * rlanes;
+      a[u] = b[u] = m[u] = make_uint4(0, 0, 0, 0);  // dy = 0 contributes nothing
+      if (rr < rows) {
+        a[u] = ldg_stream(x + (rr * cvec + chunk) * 16);
+        b[u] = ldg_stream(dy + (rr * cvec + chunk) * 16);
+        if (MASK == 2) m[u] = ldg_stream(ymask + (rr * cvec + chunk) * 16);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float fx[V], fd[V], fm[V];
+      Elem<DT>::unpack(a[u], fx);
+      Elem<DT>::unpack(b[u], fd);
+      if (MASK == 2) Elem<DT>::unpack(m[u], fm);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        float d = fd[i];
+        if (MASK == 1 && fmaf(fx[i], k.sc[i], k.sh[i]) <= 0.f) d = 0.f;
+        if (MASK == 2 && fm[i] <= 0.f) d = 0.f;
+        s[i] += d;
+        q[i] = fmaf(d, (fx[i] - mu[i]) * is[i], q[i]);
+      }
+    }
+  }
+  cta_reduce_store<V>(s, q, ct, cvec, cl, rl, partial);
+}
+
+template <int DT, int MASK, bool DRES>
+__global__ void __launch_bounds__(kThreads) bn_bwd_elemt_kernel(const char* __restrict__ x, const char* __restrict__ dy,
+                                                                const char* __restrict__ ymask, char* __restrict__ dx,
+                                                                char* __restrict__ dres, int64_t chunks, int cvec,
+                                                                const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                const double* __restrict__ sums /*[2][C]*/,
+                                                                const double* __restrict__ count) {
+  constexpr int V = Elem<DT>::VEC;
+  const int C = cvec * V;
+  const float inv_n = static_cast<float>(1.0 / *count);
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
+  const bool fixed = (kThreads % cvec) == 0;
+  ChanConst<V> k;
+  float c_mu[V], c_is[V], c_m1[V], c_m2[V];
+  auto load_consts = [&](int ch0) {
+    k.load(ch0, mean, invstd, gamma, beta);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int ch = ch0 + i;
+      c_mu[i] = __ldg(mean + ch);
+      c_is[i] = __ldg(invstd + ch);
+      c_m1[i] = static_cast<float>(sums[ch]) * inv_n;
+      c_m2[i] = static_cast<float>(sums[C + ch]) * inv_n;
+    }
+  };
+  if (fixed) load_consts((threadIdx.x % cvec) * V);
+  for (int64_t e = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; e < chunks; e += 2 * stride) {
+    uint4 vx[2], vd[2], vm[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (e + u * stride < chunks) {
+        vx[u] = ldg_stream(x + (e + u * stride) * 16);
+        vd[u] = ldg_stream(dy + (e + u * stride) * 16);
+        if (MASK == 2) vm[u] = ldg_stream(ymask + (e + u * stride) * 16);
+      }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t idx = e + u * stride;
+      if (idx >= chunks) break;
+      if (!fixed) load_consts(static_cast<int>(idx % cvec) * V);
+      float fx[V], fd[V], fm[V];
+      Elem<DT>::unpack(vx[u], fx);
+      Elem<DT>::unpack(vd[u], fd);
+      if (MASK == 2) Elem<DT>::unpack(vm[u], fm);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        float d = fd[i];
+        if (MASK == 1 && fmaf(fx[i], k.sc[i], k.sh[i]) <= 0.f) d = 0.f;
+        if (MASK == 2 && fm[i] <= 0.f) d = 0.f;
+        fd[i] = d;
+        const float xh = (fx[i] - c_mu[i]) * c_is[i];
+        fx[i] = k.sc[i] * (d - c_m1[i] - xh * c_m2[i]);
+      }
+      stg_stream(dx + idx * 16, Elem<DT>::pack(fx));
+      if (DRES) stg_stream(dres + idx * 16, Elem<DT>::pack(fd));
+    }
+  }
+}
+
+// ---- stem: bn + relu + 3x3 stride-2 pad-1 max-pool ------------------------------------------------------------
+// Window (ph, pw) covers input rows 2ph-1..2ph+1 and columns 2pw-1..2pw+1; tap t = dr*3 + dc.  The arg-max is the
+// first maximum in (row, column) scan order (ATen's max_pool2d rule) of the fp32 batch-norm output.  Tap byte 255 = the
+// pooled value is 0 (ReLU-dead): no gradient.
+// Work items are (window, 16-byte chunk) pairs: `cpad` (power of two >= cvec) consecutive threads cover the chunks of
+// one window (threads with chunk >= cvec idle), kThreads/cpad windows per CTA step; every CTA walks a contiguous range
+// of window groups, so the input row shared by vertically adjacent windows is still in its L1.  32-bit index math
+// (the ABI requires N*PH*PW < 2^31); byte offsets are 64-bit.
+struct PoolGeom {
+  int H, W, PH, PW, cvec, cpad;
+  unsigned windows;  // N * PH * PW
+};
+
+struct WinPos {
+  int n, ph, pw;
+};
+__device__ __forceinline__ WinPos decode_window(unsigned w, const PoolGeom& g) {
+  WinPos p;
+  p.pw = static_cast<int>(w % static_cast<unsigned>(g.PW));
+  const unsigned t = w / static_cast<unsigned>(g.PW);
+  p.ph = static_cast<int>(t % static_cast<unsigned>(g.PH));
+  p.n = static_cast<int>(t / static_cast<unsigned>(g.PH));
+  return p;
+}
+__device__ __forceinline__ int64_t in_chunk(const PoolGeom& g, int n, int r, int c, int chunk) {
+  return ((static_cast<int64_t>(n) * g.H + r) * g.W + c) * g.cvec + chunk;
+}
+// contiguous range of window groups of this CTA
+__device__ __forceinline__ void cta_group_range(const PoolGeom& g, unsigned& g0, unsigned& g1, unsigned& wpi) {
+  wpi = kThreads / g.cpad;
+  const unsigned groups = (g.windows + wpi - 1) / wpi;
+  const unsigned per = (groups + gridDim.x - 1) / gridDim.x;
+  g0 = min(blockIdx.x * per, groups);
+  g1 = min(g0 + per, groups);
+}
+
+template <int V>
+__device__ __forceinline__ void store_taps(unsigned char* __restrict__ tap, int64_t e, const uint32_t* b) {
+  if (V == 8) {
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { lo |= b[i] << (8 * i); hi |= b[4 + i] << (8 * i); }
+    *reinterpret_cast<uint2*>(tap + e * 8) = make_uint2(lo, hi);
+  } else {
+    uint32_t lo = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) lo |= b[i] << (8 * i);
+    *reinterpret_cast<uint32_t*>(tap + e * 4) = lo;
+  }
+}
+template <int V>
+__device__ __forceinline__ void load_taps(const unsigned char* __restrict__ tap, int64_t e, uint32_t* b /*[V]*/) {
+  if (V == 8) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(tap + e * 8));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b[i] = ((i < 4 ? t.x : t.y) >> (8 * (i & 3))) & 255u;
+  } else {
+    const uint32_t t = __ldg(reinterpret_cast<const uint32_t*>(tap + e * 4));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) b[i] = (t >> (8 * i)) & 255u;
+  }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(kThreads) bn_apply_pool_kernel(const char* __restrict__ x, char* __restrict__ y,
+                                                                 unsigned char* __restrict__ tap, PoolGeom g,
+                                                                 const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                 const float* __restrict__ gamma, const float* __restrict__ beta) {
+  constexpr int V = Elem<DT>::VEC;
+  const int chunk = threadIdx.x % g.cpad;
+  if (chunk >= g.cvec) return;
+  const unsigned lane_w = threadIdx.x / g.cpad;
+  ChanConst<V> k;
+  k.load(chunk * V, mean, invstd, gamma, beta);
+  unsigned g0, g1, wpi;
+  cta_group_range(g, g0, g1, wpi);
+  for (unsigned grp = g0; grp < g1; ++grp) {
+    const unsigned w = grp * wpi + lane_w;
+    if (w >= g.windows) break;
+    const WinPos p = decode_window(w, g);
+    uint4 v[9];
+    bool ok[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int r = 2 * p.ph - 1 + t / 3, c = 2 * p.pw - 1 + t % 3;
+      ok[t] = r >= 0 && r < g.H && c >= 0 && c < g.W;
+      if (ok[t]) v[t] = ldg_keep(x + in_chunk(g, p.n, r, c, chunk) * 16);
+    }
+    float best[V];
+    uint32_t bi[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) { best[i] = -CUDART_INF_F; bi[i] = 0; }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      if (!ok[t]) continue;
+      float f[V];
+      Elem<DT>::unpack(v[t], f);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float o = fmaf(f[i], k.sc[i], k.sh[i]);
+        if (o > best[i]) { best[i] = o; bi[i] = t; }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      if (!(best[i] > 0.f)) bi[i] = 255u;
+      best[i] = fmaxf(best[i], 0.f);
+    }
+    const int64_t e = static_cast<int64_t>(w) * g.cvec + chunk;
+    stg_stream(y + e * 16, Elem<DT>::pack(best));
+    store_taps<V>(tap, e, bi);
+  }
+}
+
+// partial sums over the pooling windows: s = sum dpool (alive), q = sum dpool * xhat(arg-max position)
+template <int DT>
+__global__ void __launch_bounds__(kThreads) bn_pool_bwd_reduce_kernel(const char* __restrict__ x, const char* __restrict__ dpool,
+                                                                      const unsigned char* __restrict__ tap, PoolGeom g, int ct,
+                                                                      const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                      float* __restrict__ partial) {
+  constexpr int V = Elem<DT>::VEC;
+  const int cl = threadIdx.x % ct, rl = threadIdx.x / ct, rlanes = kThreads / ct;
+  const int chunk = blockIdx.y * ct + cl;
+  float mu[V], is[V], s[V], q[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    mu[i] = mean[chunk * V + i];
+    is[i] = invstd[chunk * V + i];
+    s[i] = q[i] = 0.f;
+  }
+  // contiguous window range per CTA (L1 reuse of the rows shared by vertically adjacent windows)
+  const unsigned per = (g.windows + gridDim.x - 1) / gridDim.x;
+  const unsigned w0 = min(blockIdx.x * per, g.windows), w1 = min(w0 + per, g.windows);
+  for (unsigned w = w0 + rl; w < w1; w += rlanes) {
+    const int64_t e = static_cast<int64_t>(w) * g.cvec + chunk;
+    uint32_t b[V];
+    load_taps<V>(tap, e, b);
+    float d[V];
+    Elem<DT>::unpack(ldg_stream(dpool + e * 16), d);
+    uint32_t used = 0;
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+      if (b[i] < 9u) { used |= 1u << b[i]; s[i] += d[i]; }
+    const WinPos p = decode_window(w, g);
+    while (used) {
+      const int t = __ffs(used) - 1;
+      used &= used - 1;
+      float f[V];
+      Elem<DT>::unpack(ldg_keep(x + in_chunk(g, p.n, 2 * p.ph - 1 + t / 3, 2 * p.pw - 1 + t % 3, chunk) * 16), f);
+#pragma unroll
+      for (int i = 0; i < V; ++i)
+        if (b[i] == static_cast<uint32_t>(t)) q[i] = fmaf(d[i], (f[i] - mu[i]) * is[i], q[i]);
+    }
+  }
+  cta_reduce_store<V>(s, q, ct, g.cvec, cl, rl, partial);
+}
+
+// One thread owns the 2x2 input positions (2a+i, 2b+j) of block (a, b) for one chunk.  They are covered by the windows
+// (a+da, b+db), da, db in {0,1}: position (i, j) is tap (i-2da+1)*3 + (j-2db+1) of window (da, db) when i >= da, j >= db.
+template <int V>
+__device__ __forceinline__ uint2 load_tap_words(const unsigned char* __restrict__ tap, int64_t e) {
+  if (V == 8) return __ldg(reinterpret_cast<const uint2*>(tap + e * 8));
+  return make_uint2(__ldg(reinterpret_cast<const uint32_t*>(tap + e * 4)), 0xffffffffu);
+}
+__device__ __forceinline__ uint32_t tap_byte(const uint2& t, int k) { return ((k < 4 ? t.x : t.y) >> (8 * (k & 3))) & 255u; }
+
+template <int DT>
+__global__ void __launch_bounds__(kThreads, 2) bn_pool_bwd_elemt_kernel(const char* __restrict__ x, const char* __restrict__ dpool,
+                                                                     const unsigned char* __restrict__ tap, char* __restrict__ dx,
+                                                                     PoolGeom g, const float* __restrict__ mean,
+                                                                     const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                                     const double* __restrict__ sums, const double* __restrict__ count) {
+  constexpr int V = Elem<DT>::VEC;
+  const int chunk = threadIdx.x % g.cpad;
+  if (chunk >= g.cvec) return;
+  const unsigned lane_w = threadIdx.x / g.cpad;
+  const int C = g.cvec * V;
+  const float inv_n = static_cast<float>(1.0 / *count);
+  float c_mu[V], c_is[V], c_sc[V], c_m1[V], c_m2[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int ch = chunk * V + i;
+    c_mu[i] = __ldg(mean + ch);
+    c_is[i] = __ldg(invstd + ch);
+    c_sc[i] = c_is[i] * (gamma ? __ldg(gamma + ch) : 1.f);
+    c_m1[i] = static_cast<float>(sums[ch]) * inv_n;
+    c_m2[i] = static_cast<float>(sums[C + ch]) * inv_n;
+  }
+  unsigned g0, g1, wpi;
+  cta_group_range(g, g0, g1, wpi);
+  for (unsigned grp = g0; grp < g1; ++grp) {
+    const unsigned w = grp * wpi + lane_w;
+    if (w >= g.windows) break;
+    const WinPos p = decode_window(w, g);
+    uint4 vx[2][2], vd[2][2];
+    uint2 tb[2][2];
+    bool okx[2][2], okw[2][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        okx[i][j] = 2 * p.ph + i < g.H && 2 * p.pw + j < g.W;
+        okw[i][j] = p.ph + i < g.PH && p.pw + j < g.PW;
+        if (okx[i][j]) vx[i][j] = ldg_stream(x + in_chunk(g, p.n, 2 * p.ph + i, 2 * p.pw + j, chunk) * 16);
+        if (okw[i][j]) {
+          const int64_t we = (static_cast<int64_t>(w) + i * g.PW + j) * g.cvec + chunk;
+          vd[i][j] = ldg_keep(dpool + we * 16);
+          tb[i][j] = load_tap_words<V>(tap, we);
+        } else {
+          vd[i][j] = make_uint4(0, 0, 0, 0);
+          tb[i][j] = make_uint2(0xffffffffu, 0xffffffffu);
+        }
+      }
+    float fd[2][2][V];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) Elem<DT>::unpack(vd[i][j], fd[i][j]);
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (!okx[i][j]) continue;
+        float d[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) d[k] = 0.f;
+#pragma unroll
+        for (int da = 0; da <= i; ++da)
+#pragma unroll
+          for (int db = 0; db <= j; ++db) {
+            const uint32_t me = static_cast<uint32_t>((i - 2 * da + 1) * 3 + (j - 2 * db + 1));
+#pragma unroll
+            for (int k = 0; k < V; ++k)
+              if (tap_byte(tb[da][db], k) == me) d[k] += fd[da][db][k];
+          }
+        float fx[V];
+        Elem<DT>::unpack(vx[i][j], fx);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          const float xh = (fx[k] - c_mu[k]) * c_is[k];
+          fx[k] = c_sc[k] * (d[k] - c_m1[k] - xh * c_m2[k]);
+        }
+        stg_stream(dx + in_chunk(g, p.n, 2 * p.ph + i, 2 * p.pw + j, chunk) * 16, Elem<DT>::pack(fx));
+      }
+  }
+}
+
+int check_bn(const void* x, int64_t rows, int C, int dtype) {
+  MSF_REQUIRE(dtype_ok(dtype), MSF_ERR_INVALID, "bad dtype %d", dtype);
+  const int vec = 16 / static_cast<int>(dtype_size(dtype));
+  MSF_REQUIRE(rows > 0 && C > 0 && C % vec == 0, MSF_ERR_INVALID, "C=%d must be a positive multiple of %d", C, vec);
+  MSF_REQUIRE(x && aligned16(x), MSF_ERR_INVALID, "NULL or misaligned activation pointer");
+  return MSF_OK;
+}
+
+inline unsigned stream_grid(int64_t items_per_thread_total) {
+  int64_t blocks = (items_per_thread_total + kThreads - 1) / kThreads;
+  const int64_t cap = static_cast<int64_t>(kNumSMs) * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<unsigned>(blocks);
+}
+
+template <typename Kern>
+inline unsigned resident_grid(Kern kern, int64_t max_useful) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, 0) != cudaSuccess || occ < 1) occ = 1;
+  int64_t g = static_cast<int64_t>(kNumSMs) * occ;
+  if (g > max_useful) g = max_useful;
+  if (g < 1) g = 1;
+  return static_cast<unsigned>(g);
+}
+
+}  // namespace
+}  // namespace msf
+
+using namespace msf;
+
+extern "C" size_t msf_bn2d_workspace_bytes(int64_t rows, int C) {
+  if (rows <= 0 || C <= 0) return 0;
+  return static_cast<size_t>(kMaxRowBlocks) * 2 * C * sizeof(float);  // partial[row blocks][2][C], one wave of CTAs at most
+}
+
+extern "C" int msf_bn2d_stats(const void* x, int64_t rows, int C, int dtype, double* sums_out, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  if (int rc = check_bn(x, rows, C, dtype)) return rc;
+  MSF_REQUIRE(sums_out && workspace && workspace_bytes >= msf_bn2d_workspace_bytes(rows, C), MSF_ERR_WORKSPACE, "workspace too small");
+  const int vec = 16 / static_cast<int>(dtype_size(dtype));
+  const Layout l = make_layout(C, vec);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t smem = static_cast<size_t>(kThreads) * 2 * vec * sizeof(float);
+  float* partial = static_cast<float*>(workspace);
+  int nblk = 1;
+  MSF_DISPATCH_DTYPE(dtype, {
+    nblk = reduce_grid(bn_stats_kernel<DT>, smem, l, rows, kStatsRows * l.rlanes);
+    dim3 grid(static_cast<unsigned>(nblk), static_cast<unsigned>(l.cgroups));
+    bn_stats_kernel<DT><<<grid, kThreads, smem, st>>>(static_cast<const char*>(x), rows, l.cvec, l.ct, partial);
+  });
+  MSF_LAUNCH_OK("bn_stats_kernel");
+  bn_combine_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(partial, nblk, C, sums_out, static_cast<double>(rows));
+  MSF_LAUNCH_OK("bn_combine_kernel");
+  return MSF_OK;
+}
+
+extern "C" int msf_bn2d_finalize(const double* sums, int C, float eps, float momentum, float* mean, float* invstd,
+                                 float* running_mean, float* running_var, void* stream) {
+  MSF_REQUIRE(sums && mean && invstd && C > 0, MSF_ERR_INVALID, "bad arguments");
+  MSF_REQUIRE((running_mean == nullptr) == (running_var == nullptr), MSF_ERR_INVALID, "running_mean / running_var must both be given or both be NULL");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(sums, C, eps, momentum, mean, invstd,
+                                                                                     running_mean, running_var);
+  MSF_LAUNCH_OK("bn_finalize_kernel");
+  return MSF_OK;
+}
+
+extern "C" int msf_bn2d_apply(const void* x, const void* res, void* y, int64_t rows, int C, int dtype, const float* mean,
+                              const float* invstd, const float* gamma, const float* beta, int relu, void* stream) {
+  if (int rc = check_bn(x, rows, C, dtype)) return rc;
+  MSF_REQUIRE(y && aligned16(y) && aligned16(res) && mean && invstd, MSF_ERR_INVALID, "bad arguments");
+  const int vec = 16 / static_cast<int>(dtype_size(dtype));
+  const int cvec = C / vec;
+  const int64_t chunks = rows * cvec;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const char* xp = static_cast<const char*>(x);
+  const char* rp = static_cast<const char*>(res);
+  char* yp = static_cast<char*>(y);
+  if (res) {
+    MSF_DISPATCH_DTYPE(dtype, (bn_apply_kernel<DT, true><<<stream_grid((chunks + 1) / 2), kThreads, 0, st>>>(xp, rp, yp, chunks, cvec, mean, invstd, gamma, beta, relu)));
+  } else {
+    MSF_DISPATCH_DTYPE(dtype, (bn_apply_kernel<DT, false><<<stream_grid((chunks + 3) / 4), kThreads, 0, st>>>(xp, rp, yp, chunks, cvec, mean, invstd, gamma, beta, relu)));
+  }
+  MSF_LAUNCH_OK("bn_apply_kernel");
+  return MSF_OK;
+}
+
+extern "C" int msf_bn2d_bwd_reduce(const void* x, const void* dy, const void* y_mask, int64_t rows, int C, int dtype,
+                                   const float* mean, const float* invstd, const float* gamma, const float* beta, int relu,
+                                   double* sums_out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_bn(x, rows, C, dtype)) return rc;
+  MSF_REQUIRE(dy && aligned16(dy) && aligned16(y_mask) && mean && invstd && sums_out, MSF_ERR_INVALID, "bad arguments");
+  MSF_REQUIRE(workspace && workspace_bytes >= msf_bn2d_workspace_bytes(rows, C), MSF_ERR_WORKSPACE, "workspace too small");
+  const int vec = 16 / static_cast<int>(dtype_size(dtype));
+  const Layout l = make_layout(C, vec);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t smem = static_cast<size_t>(kThreads) * 2 * vec * sizeof(float);
+  float* partial = static_cast<float*>(workspace);
+  const char* xp = static_cast<const char*>(x);
+  const char* dp = static_cast<const char*>(dy);
+  const char* mp = static_cast<const char*>(y_mask);
+  int nblk = 1;
+#define MSF_BWD_REDUCE(MASK)                                                                                          \
+  MSF_DISPATCH_DTYPE(dtype, {                                                                                         \
+    nblk = reduce_grid(bn_bwd_reduce_kernel<DT, MASK>, smem, l, rows, kReduceRows * l.rlanes);                        \
+    dim3 grid(static_cast<unsigned>(nblk), static_cast<unsigned>(l.cgroups));                                         \
+    bn_bwd_reduce_kernel<DT, MASK><<<grid, kThreads, smem, st>>>(xp, dp, mp, rows, l.cvec, l.ct, mean, invstd, gamma, beta, partial); \
+  })
+  if (!relu) { MSF_BWD_REDUCE(0); }
+  else if (!y_mask) { MSF_BWD_REDUCE(1); }
+  else { MSF_BWD_REDUCE(2); }
+#undef MSF_BWD_REDUCE
+  MSF_LAUNCH_OK("bn_bwd_reduce_kernel");
+  bn_combine_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(partial, nblk, C, sums_out, -1.0);
+  MSF_LAUNCH_OK("bn_combine_kernel");
+  return MSF_OK;
+}
+
+extern "C" int msf_bn2d_bwd_elemt(const void* x, const void* dy, const void* y_mask, void* dx, void* dres, int64_t rows, int C,
+                                  int dtype, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                                  int relu, const double* sums, const double* count, void* stream) {
+  if (int rc = check_bn(x, rows, C, dtype)) return rc;
+  MSF_REQUIRE(dy && dx && aligned16(dy) && aligned16(dx) && aligned16(y_mask) && aligned16(dres) && mean && invstd && sums && count,
+              MSF_ERR_INVALID, "bad arguments");
+  const int vec = 16 / static_cast<int>(dtype_size(dtype));
+  const int cvec = C / vec;
+  const int64_t chunks = rows * cvec;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned grid = stream_grid((chunks + 1) / 2);
+  const char* xp = static_cast<const char*>(x);
+  const char* dp = static_cast<const char*>(dy);
+  const char* mp = static_cast<const char*>(y_mask);
+  char* dxp = static_cast<char*>(dx);
+  char* drp = static_cast<char*>(dres);
+#define MSF_BWD_ELEMT(MASK, DRES) \
+  MSF_DISPATCH_DTYPE(dtype, (bn_bwd_elemt_kernel<DT, MASK, DRES><<<grid, kThreads, 0, st>>>(xp, dp, mp, dxp, drp, chunks, cvec, mean, invstd, gamma, beta, sums, count)))
+  const int mask = !relu ? 0 : (y_mask ? 2 : 1);
+  if (mask == 0 && !dres) { MSF_BWD_ELEMT(0, false); }
+  else if (mask == 0) { MSF_BWD_ELEMT(0, true); }
+  else if (mask == 1 && !dres) { MSF_BWD_ELEMT(1, false); }
+  else if (mask == 1) { MSF_BWD_ELEMT(1, true); }
+  else if (!dres) { MSF_BWD_ELEMT(2, false); }
+  else { MSF_BWD_ELEMT(2, true); }
+#undef MSF_BWD_ELEMT
+  MSF_LAUNCH_OK("bn_bwd_elemt_kernel");
+  return MSF_OK;
+}
+
+namespace {
+int check_pool(const void* x, int64_t N, int H, int W, int C, int dtype, PoolGeom* g) {
+  if (int rc = check_bn(x, N, C, dtype)) return rc;
+  MSF_REQUIRE(H >= 2 && W >= 2, MSF_ERR_INVALID, "pooling needs H, W >= 2 (got %d x %d)", H, W);
+  const int vec = 16 / static_cast<int>(dtype_size(dtype));
+  g->H = H; g->W = W; g->PH = (H - 1) / 2 + 1; g->PW = (W - 1) / 2 + 1; g->cvec = C / vec;
+  g->cpad = 1;
+  while (g->cpad < g->cvec) g->cpad *= 2;
+  MSF_REQUIRE(g->cpad <= kThreads, MSF_ERR_UNSUPPORTED, "C=%d is too wide for the pooled kernels", C);
+  const int64_t windows = N * g->PH * g->PW;
+  MSF_REQUIRE(windows < (int64_t{1} << 31), MSF_ERR_UNSUPPORTED, "N*PH*PW = %lld must be < 2^31", static_cast<long long>(windows));
+  g->windows = static_cast<unsigned>(windows);
+  return MSF_OK;
+}
+}  // namespace
+
+extern "C" int msf_bn2d_apply_pool(const void* x, void* y, uint8_t* tap, int64_t N, int H, int W, int C, int dtype,
+                                   const float* mean, const float* invstd, const float* gamma, const float* beta, void* stream) {
+  PoolGeom g;
+  if (int rc = check_pool(x, N, H, W, C, dtype, &g)) return rc;
+  MSF_REQUIRE(y && tap && aligned16(y) && aligned16(tap) && mean && invstd, MSF_ERR_INVALID, "bad arguments");
+  const int64_t groups = (static_cast<int64_t>(g.windows) + kThreads / g.cpad - 1) / (kThreads / g.cpad);
+  MSF_DISPATCH_DTYPE(dtype, (bn_apply_pool_kernel<DT><<<resident_grid(bn_apply_pool_kernel<DT>, groups), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+                                static_cast<const char*>(x), static_cast<char*>(y), tap, g, mean, invstd, gamma, beta)));
+  MSF_LAUNCH_OK("bn_apply_pool_kernel");
+  return MSF_OK;
+}
+
+extern "C" int msf_bn2d_pool_bwd_reduce(const void* x, const void* dpool, const uint8_t* tap, int64_t N, int H, int W, int C,
+                                        int dtype, const float* mean, const float* invstd, double* sums_out, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  PoolGeom g;
+  if (int rc = check_pool(x, N, H, W, C, dtype, &g)) return rc;
+  MSF_REQUIRE(dpool && tap && aligned16(dpool) && mean && invstd && sums_out, MSF_ERR_INVALID, "bad arguments");
+  MSF_REQUIRE(workspace && workspace_bytes >= msf_bn2d_workspace_bytes(g.windows, C), MSF_ERR_WORKSPACE, "workspace too small");
+  const int vec = 16 / static_cast<int>(dtype_size(dtype));
+  const Layout l = make_layout(C, vec);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t smem = static_cast<size_t>(kThreads) * 2 * vec * sizeof(float);
+  float* partial = static_cast<float*>(workspace);
+  int nblk = 1;
+  MSF_DISPATCH_DTYPE(dtype, {
+    nblk = reduce_grid(bn_pool_bwd_reduce_kernel<DT>, smem, l, g.windows, l.rlanes);
+    dim3 grid(static_cast<unsigned>(nblk), static_cast<unsigned>(l.cgroups));
+    bn_pool_bwd_reduce_kernel<DT><<<grid, kThreads, smem, st>>>(static_cast<const char*>(x), static_cast<const char*>(dpool), tap, g, l.ct, mean, invstd, partial);
+  });
+  MSF_LAUNCH_OK("bn_pool_bwd_reduce_kernel");
+  bn_combine_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(partial, nblk, C, sums_out, -1.0);
+  MSF_LAUNCH_OK("bn_combine_kernel");
+  return MSF_OK;
+}
+
+extern "C" int msf_bn2d_pool_bwd_elemt(const void* x, const void* dpool, const uint8_t* tap, void* dx, int64_t N, int H, int W,
+                                       int C, int dtype, const float* mean, const float* invstd, const float* gamma,
+                                       const double* sums, const double* count, void* stream) {
+  PoolGeom g;
+  if (int rc = check_pool(x, N, H, W, C, dtype, &g)) return rc;
+  MSF_REQUIRE(dpool && tap && dx && aligned16(dpool) && aligned16(dx) && mean && invstd && sums && count, MSF_ERR_INVALID, "bad arguments");
+  const int64_t groups = (static_cast<int64_t>(g.windows) + kThreads / g.cpad - 1) / (kThreads / g.cpad);
+  MSF_DISPATCH_DTYPE(dtype, (bn_pool_bwd_elemt_kernel<DT><<<resident_grid(bn_pool_bwd_elemt_kernel<DT>, groups), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+                                static_cast<const char*>(x), static_cast<const char*>(dpool), tap, static_cast<char*>(dx), g, mean, invstd,
+                                gamma, sums, count)));
+  MSF_LAUNCH_OK("bn_pool_bwd_elemt_kernel");
+  return MSF_OK;
+}

@@ -349,6 +349,125 @@ def footprint_boxes(B: int, scale: int, H: int, W: int, device) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------
+# N1: channels-last BatchNorm2d (+ReLU, +residual, +stem max-pool) of the encoders   (src/models/resnet.py:59-82, 244-247)
+# ------------------------------------------------------------------------------------------
+def _nhwc(t: torch.Tensor) -> torch.Tensor:
+    return t if t.is_contiguous(memory_format=torch.channels_last) else t.contiguous(memory_format=torch.channels_last)
+
+
+def _sync_world(group) -> int:
+    if group is None or not (dist.is_available() and dist.is_initialized()):
+        return 1
+    return dist.get_world_size(group)
+
+
+class _BNAct2d(torch.autograd.Function):
+    """act(batch_norm(x) (+ residual)) with batch statistics (train mode), optionally followed by the stem's
+    3x3/2 max-pool.  ``sync_group`` = process group the statistics are reduced over (SyncBatchNorm semantics), or None."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, running_mean, running_var, eps: float, momentum: float, relu: bool, pool: bool,
+                sync_group):
+        L.require_cuda(x, weight, bias, residual)
+        if x.dim() != 4:
+            raise ValueError(f"bn_act2d: expected (N,C,H,W), got {tuple(x.shape)}")
+        if pool and (residual is not None or not relu):
+            raise ValueError("bn_act2d: the pooled variant is bn -> relu -> maxpool without a residual")
+        x = _nhwc(x)
+        N, Cc, H, W = x.shape
+        dt, dev = x.dtype, x.device
+        code = L.dtype_code(dt)
+        rows = N * H * W
+        gamma = None if weight is None else _contig(weight.detach().float())
+        beta = None if bias is None else _contig(bias.detach().float())
+        lib, st = L.lib(), L.stream_ptr()
+        ws_bytes = lib.msf_bn2d_workspace_bytes(rows, Cc)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        sums = torch.empty(2 * Cc + 1, dtype=torch.float64, device=dev)
+        L.check(lib.msf_bn2d_stats(L.ptr(x), rows, Cc, code, L.ptr(sums), L.ptr(ws), ws_bytes, st), "msf_bn2d_stats")
+        world = _sync_world(sync_group)
+        if world > 1:
+            dist.all_reduce(sums, group=sync_group)
+        mean = torch.empty(Cc, dtype=torch.float32, device=dev)
+        invstd = torch.empty(Cc, dtype=torch.float32, device=dev)
+        L.check(lib.msf_bn2d_finalize(L.ptr(sums), Cc, eps, momentum, L.ptr(mean), L.ptr(invstd), L.ptr(running_mean), L.ptr(running_var), st),
+                "msf_bn2d_finalize")
+        tap = None
+        if pool:
+            PH, PW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+            y = torch.empty((N, Cc, PH, PW), dtype=dt, device=dev, memory_format=torch.channels_last)
+            tap = torch.empty((N, PH, PW, Cc), dtype=torch.uint8, device=dev)
+            L.check(lib.msf_bn2d_apply_pool(L.ptr(x), L.ptr(y), L.ptr(tap), N, H, W, Cc, code, L.ptr(mean), L.ptr(invstd), L.ptr(gamma),
+                                            L.ptr(beta), st), "msf_bn2d_apply_pool")
+        else:
+            res = None
+            if residual is not None:
+                if residual.shape != x.shape or residual.dtype != dt:
+                    raise ValueError(f"bn_act2d: residual {tuple(residual.shape)} {residual.dtype} vs x {tuple(x.shape)} {dt}")
+                res = _nhwc(residual)
+            y = torch.empty_like(x, memory_format=torch.channels_last)
+            L.check(lib.msf_bn2d_apply(L.ptr(x), L.ptr(res), L.ptr(y), rows, Cc, code, L.ptr(mean), L.ptr(invstd), L.ptr(gamma), L.ptr(beta),
+                                       int(relu), st), "msf_bn2d_apply")
+        L.launch_count += 4
+        # with a residual the ReLU mask of the backward comes from the output (no extra memory: the next layer keeps it anyway)
+        y_mask = y if (residual is not None and relu) else None
+        ctx.save_for_backward(x, gamma, beta, mean, invstd, sums, y_mask, tap)
+        ctx.meta = (N, Cc, H, W, code, relu, pool, residual is not None, sync_group, world,
+                    None if weight is None else weight.dtype, None if bias is None else bias.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, gamma, beta, mean, invstd, sums_fwd, y_mask, tap = ctx.saved_tensors
+        N, Cc, H, W, code, relu, pool, has_res, group, world, wdt, bdt = ctx.meta
+        dev = x.device
+        gy = _nhwc(gy if gy.dtype == x.dtype else gy.to(x.dtype))
+        lib, st = L.lib(), L.stream_ptr()
+        rows = N * H * W
+        sums = torch.empty(2 * Cc, dtype=torch.float64, device=dev)
+        count_ptr = sums_fwd.data_ptr() + 16 * Cc  # element 2C of the forward sums: the (global) element count
+        dx = torch.empty_like(x, memory_format=torch.channels_last)
+        dres = None
+        if pool:
+            PH, PW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+            ws_bytes = lib.msf_bn2d_workspace_bytes(N * PH * PW, Cc)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            L.check(lib.msf_bn2d_pool_bwd_reduce(L.ptr(x), L.ptr(gy), L.ptr(tap), N, H, W, Cc, code, L.ptr(mean), L.ptr(invstd), L.ptr(sums),
+                                                 L.ptr(ws), ws_bytes, st), "msf_bn2d_pool_bwd_reduce")
+        else:
+            ws_bytes = lib.msf_bn2d_workspace_bytes(rows, Cc)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            L.check(lib.msf_bn2d_bwd_reduce(L.ptr(x), L.ptr(gy), L.ptr(y_mask), rows, Cc, code, L.ptr(mean), L.ptr(invstd), L.ptr(gamma),
+                                            L.ptr(beta), int(relu), L.ptr(sums), L.ptr(ws), ws_bytes, st), "msf_bn2d_bwd_reduce")
+        # parameter gradients are the LOCAL sums (DDP averages them over ranks, as with SyncBatchNorm)
+        gw = None if wdt is None else sums[Cc:].to(wdt)
+        gb = None if bdt is None else sums[:Cc].to(bdt)
+        if world > 1:
+            dist.all_reduce(sums, group=group)
+        if pool:
+            L.check(lib.msf_bn2d_pool_bwd_elemt(L.ptr(x), L.ptr(gy), L.ptr(tap), L.ptr(dx), N, H, W, Cc, code, L.ptr(mean), L.ptr(invstd),
+                                                L.ptr(gamma), L.ptr(sums), count_ptr, st), "msf_bn2d_pool_bwd_elemt")
+        else:
+            if has_res and ctx.needs_input_grad[3]:
+                dres = torch.empty_like(x, memory_format=torch.channels_last)
+            L.check(lib.msf_bn2d_bwd_elemt(L.ptr(x), L.ptr(gy), L.ptr(y_mask), L.ptr(dx), L.ptr(dres), rows, Cc, code, L.ptr(mean),
+                                           L.ptr(invstd), L.ptr(gamma), L.ptr(beta), int(relu), L.ptr(sums), count_ptr, st),
+                    "msf_bn2d_bwd_elemt")
+        L.launch_count += 3
+        return dx, gw, gb, dres, None, None, None, None, None, None, None
+
+
+def bn_act2d(x: torch.Tensor, weight: Optional[torch.Tensor], bias: Optional[torch.Tensor], running_mean: Optional[torch.Tensor],
+             running_var: Optional[torch.Tensor], eps: float = 1e-5, momentum: float = 0.1, relu: bool = False,
+             residual: Optional[torch.Tensor] = None, pool: bool = False, sync_group=None) -> torch.Tensor:
+    """Train-mode ``[maxpool3x3/2](relu?(batch_norm(x) (+ residual)))`` on channels-last CUDA tensors.  Statistics are
+    biased batch statistics (all-reduced over ``sync_group`` when given); ``running_*`` receive the momentum update with
+    the unbiased variance.  x (N,C,H,W) in NHWC memory order (converted if not)."""
+    return _BNAct2d.apply(x, weight, bias, residual, running_mean, running_var, float(eps), float(momentum), bool(relu), bool(pool),
+                          sync_group)
+
+
+# ------------------------------------------------------------------------------------------
 # E1: multi-tensor EMA (extension)
 # ------------------------------------------------------------------------------------------
 class EmaUpdater:

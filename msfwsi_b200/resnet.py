@@ -16,97 +16,51 @@ import torch
 import torch.nn as nn
 
 
-_INT32_MAX = 2 ** 31 - 1
+class FusedBatchNorm2d(nn.Module):
+    """BatchNorm2d with the element-wise work around it fused in (same parameters / buffers / state-dict keys as
+    nn.BatchNorm2d): ``act`` = "none" | "relu" | "relu_pool" (the stem's bn -> relu -> 3x3/2 max-pool), and an optional
+    residual added before the ReLU (BasicBlock's ``relu(bn2(.) + identity)``).
 
+    On CUDA in train mode it runs on this repo's channels-last kernels (``ops.bn_act2d``: 3 streaming passes forward,
+    2 backward, 64-bit indexing -- ATen's kernels fall onto a ~20x slower path above 2^31 elements, which the stem of a
+    4096-image batch exceeds).  Deliberately NOT a ``_BatchNorm`` subclass: ``convert_sync_batchnorm`` leaves it alone
+    and it reduces its statistics over the default process group itself (SyncBatchNorm semantics, tools/ssl_train.py:160)
+    whenever torch.distributed is initialised with more than one rank.  Eval mode and CPU tensors use the plain ATen
+    sequence (not a hot path)."""
 
-def _batch_chunks(x: torch.Tensor):
-    """Split along the batch so that every piece has fewer than 2^31 elements (ATen's batch-norm / pooling kernels drop
-    to a ~20x slower 64-bit-index path above that; at 4096 x 64 x 112 x 112 the stem crosses it)."""
-    n = x.shape[0]
-    per = max(1, _INT32_MAX // max(1, x[0].numel()))
-    return [x] if n <= per else list(x.split(per, dim=0))
-
-
-class _StemBNFn(torch.autograd.Function):
-    """Train-mode batch norm with exact full-batch (and cross-rank) statistics, evaluated chunk by chunk with the same
-    ATen primitives torch.nn.SyncBatchNorm uses (batch_norm_stats / gather_stats_with_counts / elemt and the two
-    backward halves)."""
-
-    @staticmethod
-    def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, group):
-        chunks = _batch_chunks(x)
-        means, invstds, counts = [], [], []
-        for c in chunks:
-            m, iv = torch.batch_norm_stats(c, eps)
-            means.append(m)
-            invstds.append(iv)
-            counts.append(c.numel() // c.shape[1])
-        mean_all, invstd_all = torch.stack(means), torch.stack(invstds)
-        count_all = torch.tensor(counts, dtype=mean_all.dtype, device=x.device)
-        world = torch.distributed.get_world_size(group) if group is not None else 1
-        if world > 1:
-            packed = torch.cat([mean_all, invstd_all, count_all[:, None]], dim=1)
-            gathered = torch.empty((world,) + tuple(packed.shape), dtype=packed.dtype, device=x.device)
-            torch.distributed.all_gather_into_tensor(gathered, packed, group=group)
-            gathered = gathered.flatten(0, 1)
-            ch = x.shape[1]
-            mean_all, invstd_all, count_all = gathered[:, :ch].contiguous(), gathered[:, ch:2 * ch].contiguous(), gathered[:, 2 * ch].contiguous()
-        mean, invstd = torch.batch_norm_gather_stats_with_counts(chunks[0], mean_all, invstd_all, running_mean, running_var,
-                                                                 momentum, eps, count_all)
-        out = torch.empty_like(x)
-        for c, o in zip(chunks, _batch_chunks(out)):
-            o.copy_(torch.batch_norm_elemt(c, weight, bias, mean, invstd, eps))
-        ctx.save_for_backward(x, weight, mean, invstd, count_all.to(torch.int32))
-        ctx.group, ctx.world = group, world
-        return out
-
-    @staticmethod
-    def backward(ctx, grad_out):
-        x, weight, mean, invstd, count = ctx.saved_tensors
-        grad_out = grad_out.contiguous(memory_format=torch.channels_last) if x.is_contiguous(memory_format=torch.channels_last) else grad_out.contiguous()
-        xs, gs = _batch_chunks(x), _batch_chunks(grad_out)
-        sum_dy = sum_dy_xmu = gw = gb = None
-        for c, g in zip(xs, gs):
-            a, b2, w_, b_ = torch.batch_norm_backward_reduce(g, c, mean, invstd, weight, True, True, True)
-            sum_dy = a if sum_dy is None else sum_dy + a
-            sum_dy_xmu = b2 if sum_dy_xmu is None else sum_dy_xmu + b2
-            gw = w_ if gw is None else gw + w_
-            gb = b_ if gb is None else gb + b_
-        if ctx.world > 1:
-            packed = torch.cat([sum_dy, sum_dy_xmu])
-            torch.distributed.all_reduce(packed, group=ctx.group)
-            sum_dy, sum_dy_xmu = packed[:sum_dy.numel()], packed[sum_dy.numel():]
-        grad_in = torch.empty_like(x)
-        for c, g, o in zip(xs, gs, _batch_chunks(grad_in)):
-            o.copy_(torch.batch_norm_backward_elemt(g, c, mean, invstd, weight, sum_dy, sum_dy_xmu, count))
-        return grad_in, gw.to(weight.dtype), gb.to(weight.dtype), None, None, None, None, None
-
-
-class StemBatchNorm2d(nn.Module):
-    """BatchNorm2d of the stem (same parameters / buffers / state-dict keys as nn.BatchNorm2d).  Deliberately NOT a
-    ``_BatchNorm`` subclass: ``convert_sync_batchnorm`` leaves it alone and it synchronises its statistics across the
-    default process group itself (same math as SyncBatchNorm), while keeping every ATen call below 2^31 elements."""
-
-    def __init__(self, num_features: int, eps: float = 1e-5, momentum: float = 0.1):
+    def __init__(self, num_features: int, eps: float = 1e-5, momentum: float = 0.1, act: str = "none"):
         super().__init__()
-        self.num_features, self.eps, self.momentum = num_features, eps, momentum
+        if act not in ("none", "relu", "relu_pool"):
+            raise ValueError(f"act must be none | relu | relu_pool, got {act!r}")
+        self.num_features, self.eps, self.momentum, self.act = num_features, eps, momentum, act
         self.weight = nn.Parameter(torch.ones(num_features))
         self.bias = nn.Parameter(torch.zeros(num_features))
         self.register_buffer("running_mean", torch.zeros(num_features))
         self.register_buffer("running_var", torch.ones(num_features))
         self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
 
-    def forward(self, x):
-        import torch.distributed as dist
-        sync = self.training and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-        if not self.training or not x.is_cuda or (x.numel() <= _INT32_MAX and not sync):
-            if self.training:
-                self.num_batches_tracked.add_(1)
-            return nn.functional.batch_norm(x, self.running_mean, self.running_var, self.weight, self.bias, self.training,
-                                            self.momentum, self.eps)
-        self.num_batches_tracked.add_(1)
-        return _StemBNFn.apply(x, self.weight, self.bias, self.running_mean, self.running_var, self.eps, self.momentum,
-                               dist.group.WORLD if sync else None)
+    def extra_repr(self):
+        return f"{self.num_features}, eps={self.eps}, momentum={self.momentum}, act={self.act}"
+
+    def forward(self, x, residual=None):
+        if self.training and x.is_cuda:
+            import torch.distributed as dist
+            from . import ops
+            sync = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+            self.num_batches_tracked.add_(1)
+            return ops.bn_act2d(x, self.weight, self.bias, self.running_mean, self.running_var, self.eps, self.momentum,
+                                relu=self.act != "none", residual=residual, pool=self.act == "relu_pool",
+                                sync_group=dist.group.WORLD if sync else None)
+        if self.training:
+            self.num_batches_tracked.add_(1)
+        out = nn.functional.batch_norm(x, self.running_mean, self.running_var, self.weight, self.bias, self.training, self.momentum, self.eps)
+        if residual is not None:
+            out = out + residual
+        if self.act != "none":
+            out = nn.functional.relu(out)
+        if self.act == "relu_pool":
+            out = nn.functional.max_pool2d(out, 3, 2, 1)
+        return out
 
 
 class BasicBlock(nn.Module):
@@ -115,17 +69,16 @@ class BasicBlock(nn.Module):
     def __init__(self, inplanes: int, planes: int, stride: int = 1, downsample: nn.Module | None = None):
         super().__init__()
         self.conv1 = nn.Conv2d(inplanes, planes, 3, stride, 1, bias=False)
-        self.bn1 = nn.BatchNorm2d(planes)
-        self.relu = nn.ReLU(inplace=True)
+        self.bn1 = FusedBatchNorm2d(planes, act="relu")
+        self.relu = nn.ReLU(inplace=True)  # kept for module-tree compatibility; the ReLUs run inside bn1 / bn2
         self.conv2 = nn.Conv2d(planes, planes, 3, 1, 1, bias=False)
-        self.bn2 = nn.BatchNorm2d(planes)
+        self.bn2 = FusedBatchNorm2d(planes, act="relu")
         self.downsample = downsample
 
     def forward(self, x):
         idt = x if self.downsample is None else self.downsample(x)
-        out = self.relu(self.bn1(self.conv1(x)))
-        out = self.bn2(self.conv2(out))
-        return self.relu(out + idt)
+        out = self.bn1(self.conv1(x))            # relu(bn1(conv1 x))
+        return self.bn2(self.conv2(out), idt)    # relu(bn2(conv2 out) + identity)
 
 
 class ResNet(nn.Module):
@@ -134,9 +87,9 @@ class ResNet(nn.Module):
         self.return_features = return_features
         self.inplanes = 64
         self.conv1 = nn.Conv2d(3, 64, 7, 2, 3, bias=False)
-        self.bn1 = StemBatchNorm2d(64)
-        self.relu = nn.ReLU(inplace=True)
-        self.maxpool = nn.MaxPool2d(3, 2, 1)
+        self.bn1 = FusedBatchNorm2d(64, act="relu_pool")  # bn1 -> relu -> maxpool in one pass (resnet.py:244-247 of the reference)
+        self.relu = nn.ReLU(inplace=True)     # kept for module-tree compatibility (no parameters)
+        self.maxpool = nn.MaxPool2d(3, 2, 1)  # idem
         self.layer1 = self._make_layer(64, layers[0], 1)
         self.layer2 = self._make_layer(128, layers[1], 2)
         self.layer3 = self._make_layer(256, layers[2], 2)
@@ -146,7 +99,7 @@ class ResNet(nn.Module):
         for m in self.modules():
             if isinstance(m, nn.Conv2d):
                 nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
-            elif isinstance(m, (nn.BatchNorm2d, StemBatchNorm2d)):
+            elif isinstance(m, (nn.BatchNorm2d, FusedBatchNorm2d)):
                 nn.init.constant_(m.weight, 1)
                 nn.init.constant_(m.bias, 0)
         if zero_init_residual:
@@ -157,15 +110,14 @@ class ResNet(nn.Module):
     def _make_layer(self, planes: int, blocks: int, stride: int) -> nn.Sequential:
         downsample = None
         if stride != 1 or self.inplanes != planes:
-            downsample = nn.Sequential(nn.Conv2d(self.inplanes, planes, 1, stride, bias=False), nn.BatchNorm2d(planes))
+            downsample = nn.Sequential(nn.Conv2d(self.inplanes, planes, 1, stride, bias=False), FusedBatchNorm2d(planes))
         seq = [BasicBlock(self.inplanes, planes, stride, downsample)]
         self.inplanes = planes
         seq += [BasicBlock(planes, planes) for _ in range(1, blocks)]
         return nn.Sequential(*seq)
 
     def forward(self, x):
-        x = self.relu(self.bn1(self.conv1(x)))
-        x = torch.cat([self.maxpool(c) for c in _batch_chunks(x)], dim=0) if x.numel() > _INT32_MAX else self.maxpool(x)
+        x = self.bn1(self.conv1(x))
         x1 = self.layer1(x)
         x2 = self.layer2(x1)
         x3 = self.layer3(x2)

@@ -39,17 +39,24 @@ def _worker(rank, world, port, q):
             assert abs(t.item() / world - ref.item()) <= tol * abs(ref.item()), (dim, t.item() / world, ref.item())
             assert cos >= 0.9999, (dim, cos)
             res[dim] = (t.item() / world, ref.item(), cos)
-        # stem BatchNorm: self-synchronising statistics == BatchNorm2d over the concatenated batch
+        # encoder BatchNorm (fused kernels): self-synchronising statistics == BatchNorm2d over the concatenated batch
         import msfwsi_b200.resnet as R
         g = torch.Generator().manual_seed(3)
         x_all = torch.randn(world * 6, 64, 12, 12, generator=g)
         bn_ref = torch.nn.BatchNorm2d(64).train()
-        y_ref = bn_ref(x_all)
-        bn = R.StemBatchNorm2d(64).cuda().train()
-        xl = x_all[rank * 6:(rank + 1) * 6].cuda().contiguous(memory_format=torch.channels_last)
+        x_ref = x_all.clone().requires_grad_(True)
+        y_ref = bn_ref(x_ref)
+        w_all = torch.randn(x_all.shape, generator=g)
+        (y_ref * w_all).sum().backward()
+        bn = R.FusedBatchNorm2d(64).cuda().train()
+        xl = x_all[rank * 6:(rank + 1) * 6].cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
         y = bn(xl)
-        assert torch.allclose(y.cpu(), y_ref[rank * 6:(rank + 1) * 6], rtol=1e-4, atol=1e-4)
+        (y * w_all[rank * 6:(rank + 1) * 6].cuda()).sum().backward()
+        assert torch.allclose(y.detach().cpu(), y_ref[rank * 6:(rank + 1) * 6].detach(), rtol=1e-4, atol=1e-4)
         assert torch.allclose(bn.running_var.cpu(), bn_ref.running_var, rtol=1e-4, atol=1e-5)
+        assert torch.allclose(xl.grad.cpu(), x_ref.grad[rank * 6:(rank + 1) * 6], rtol=1e-3, atol=1e-4)  # cross-rank backward sums
+        gw = bn.weight.grad.clone(); dist.all_reduce(gw)  # local parameter gradients sum to the full-batch gradient
+        assert torch.allclose(gw.cpu(), bn_ref.weight.grad, rtol=1e-3, atol=1e-3)
         q.put((rank, "ok", res))
     except Exception as e:  # pragma: no cover
         import traceback

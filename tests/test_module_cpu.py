@@ -43,11 +43,11 @@ def test_survives_sync_batchnorm_conversion(model):
     import copy
     conv = torch.nn.SyncBatchNorm.convert_sync_batchnorm(copy.deepcopy(model))
     n_sync = sum(isinstance(m, torch.nn.SyncBatchNorm) for m in conv.modules())
-    # 48 in the heads + 38 in the encoders; the two stem BNs (bn1) are StemBatchNorm2d, which synchronise their
-    # statistics across ranks themselves (the reference converts all 88)
-    assert n_sync == 86
-    from msfwsi_b200.resnet import StemBatchNorm2d
-    assert sum(isinstance(m, StemBatchNorm2d) for m in conv.modules()) == 2
+    # the 48 BatchNorm1d of the heads are converted; the 40 encoder BNs are FusedBatchNorm2d, which reduce their
+    # statistics across ranks themselves with SyncBatchNorm semantics (the reference converts all 88)
+    assert n_sync == 48
+    from msfwsi_b200.resnet import FusedBatchNorm2d
+    assert sum(isinstance(m, FusedBatchNorm2d) for m in conv.modules()) == 40
     assert set(conv.state_dict()) == set(model.state_dict())
 
 

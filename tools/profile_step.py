@@ -40,6 +40,6 @@ from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     step(); torch.cuda.synchronize()
 if rank == 0:
-    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=18, max_name_column_width=70))
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=int(os.environ.get("ROWS", "18")), max_name_column_width=70))
 if world > 1:
     dist.destroy_process_group()
