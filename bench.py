@@ -224,7 +224,7 @@ def ours(args):
 
     # ---- timed region 1: inputs resident in HBM --------------------------------------------------------
     clocks = Clocks(local) if rank == 0 else None
-    ops.PROFILE = []
+    _lib.prof_begin(1 << 16)  # CUDA event pairs around every main kernel of this repo, on its launching stream
     launches0 = _lib.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -235,57 +235,92 @@ def ours(args):
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = _lib.launch_count - launches0
-    prof, ops.PROFILE = ops.PROFILE, None
+    prof, prof_dropped = _lib.prof_end()
     clk = clocks.stop() if clocks else None
     last_loss = float(loss.item())
     value = B * world * args.steps / (ms / 1e3)
 
     # ---- timed region 2: end to end from pinned host memory, loss read back every step -------------------
+    # Every step's inputs are copied host -> device inside the timed region (K copies for K steps); the copy of step
+    # i+1 is issued on a side stream while step i computes (double buffering), the first copy is exposed.
     del resident
-    d = to_dev()
-    step(d).item()
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream(dev)
+
+    def fetch():
+        with torch.cuda.stream(copy_stream):
+            d = to_dev()
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        for t in d.values():
+            t.record_stream(main_stream)
+        return d, ev
+
+    def e2e_steps(n):
+        nxt = fetch()
+        for i in range(n):
+            d, ev = nxt
+            main_stream.wait_event(ev)
+            nxt = fetch() if i + 1 < n else None
+            step(d).item()  # device -> host read of the step's result
+
+    e2e_steps(2)
     barrier()
     e0.record()
-    for _ in range(args.steps):
-        d = to_dev()
-        step(d).item()  # device -> host read of the step's result
+    e2e_steps(args.steps)
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     e2e = B * world * args.steps / (ms_e2e / 1e3)
 
     # ---- roofline of the dominant kernel of this repo inside the timed steps ----------------------------
+    # per kernel family: algorithmic work (bytes or FLOP) summed over the launches of the timed
+    # region / device time between the event pairs the library recorded around them
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        pass
+    hbm_peak, tc_peak = peaks.get("hbm_gbs", 6650.0), peaks.get("bf16_tflops_sustained", 1400.0)
+    kernels = []
+    for name, r in prof.items():
+        if r["ms"] <= 0:
+            continue
+        if r["bound"] == "h":
+            ach, peak, unit, bound = r["work"] / r["ms"] / 1e6, hbm_peak, "GB/s", "hbm"
+        else:
+            ach, peak, unit, bound = r["work"] / r["ms"] / 1e9, tc_peak, "TFLOP/s", "tensor"
+        kernels.append({"kernel": name, "bound": bound, "launches": r["launches"], "ms_per_step": r["ms"] / args.steps,
+                        "share_of_step": r["ms"] / ms, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                        "work_per_launch": r["work"] / r["launches"], "avg_us": 1e3 * r["ms"] / r["launches"]})
+    kernels.sort(key=lambda k: -k["ms_per_step"])
     roofline = None
-    if prof:
-        flash = [(a.elapsed_time(b), fl, d) for a, b, fl, kind, d in prof if kind == "flash"]
-        if flash:
-            t_ms, fl = sum(t for t, _, _ in flash), sum(f for _, f, _ in flash)
-            peak = peaks.get("bf16_tflops_sustained", 1400.0)
-            per_dim = {}
-            for t, f, d in flash:
-                e = per_dim.setdefault(str(d), [0.0, 0.0, 0])
-                e[0] += t; e[1] += f; e[2] += 1
-            roofline = {"kernel": "infonce_tc_kernel<D> (flash tcgen05 main kernel) inside the timed steps: N = 16*batch*gpus keys, "
-                                  "Nq = 16*batch (target branch) or batch rows, D in {64,128,256}",
-                        "bound": "tensor", "achieved": fl / t_ms / 1e9, "peak": peak,
-                        "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback", "unit": "TFLOP/s",
-                        "frac": fl / t_ms / 1e9 / peak, "traffic": None, "launches": len(flash), "avg_us": 1e3 * t_ms / len(flash),
-                        "flops_per_launch": fl / len(flash),
-                        "per_dim": {d: {"launches": v[2], "avg_us": 1e3 * v[0] / v[2], "tflops": v[1] / v[0] / 1e9} for d, v in per_dim.items()},
-                        "timing": "cudaEventRecord by the library immediately before/after the main kernel on its stream"}
-            other = [(a.elapsed_time(b), fl) for a, b, fl, kind, d in prof if kind != "flash"]
-            if other:
-                roofline["two_pass_gemm_paths"] = {"launches": len(other), "tflops": sum(f for _, f in other) / sum(t for t, _ in other) / 1e9}
+    if kernels:
+        top = kernels[0]
+        t = traffic.get(top["kernel"])
+        roofline = {"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"],
+                    "frac": top["frac"], "traffic": None if t is None else t.get("dram_bytes_per_launch"),
+                    "traffic_source": None if t is None else t.get("source"),
+                    "peak_source": ("MEASURED_PEAKS.json " + ("hbm_gbs" if top["bound"] == "hbm" else "bf16_tflops_sustained")) if peaks else "fallback (B200_PROFILING.md)",
+                    "launches": top["launches"], "avg_us": top["avg_us"], "work_per_launch": top["work_per_launch"],
+                    "share_of_step": top["share_of_step"],
+                    "timing": "cudaEventRecord by the library on the launching stream immediately before/after the kernel, "
+                              "summed over the timed steps (dominant kernel of this repo by device time)",
+                    "all_kernels_share_of_step": sum(k["share_of_step"] for k in kernels), "events_dropped": prof_dropped}
     micro = None
     if rank == 0 and not args.no_microbench:
         micro = infonce_microbench(torch, ops, _lib, dev, peaks)
     if roofline is None and micro:
         roofline = micro["roofline"]
+    if micro:
+        for k in kernels:  # the north-star kernel at its c5 size next to its in-step (N = 16 * batch) numbers
+            if k["kernel"] == "infonce_flash_fwd":
+                k["c5_microbench_frac_of_burst_peak"] = max(r["frac_fwd"] for r in micro["rows"])
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -302,6 +337,7 @@ def ours(args):
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline, "loss": last_loss,
                 "encoder_images_per_sec": value * 34}
+        line["roofline_kernels"] = kernels
         if micro:
             line["roofline_microbench"] = micro["rows"]
         emit(line)

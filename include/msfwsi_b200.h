@@ -247,6 +247,29 @@ int msf_bn2d_pool_bwd_elemt(const void* x, const void* dpool, const uint8_t* tap
                             int C, int dtype, const float* mean, const float* invstd, const float* gamma,
                             const double* sums /*2C*/, const double* count, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Measurement hook (bench.py): when switched on, every compute entry point records a CUDA event pair on its stream
+ * immediately around its main kernel(s); msf_prof_end synchronises those events and returns, per kernel id, the number
+ * of calls, the summed algorithmic work (bytes for HBM-bound kernels, FLOP for tensor-bound ones, as defined in
+ * DESIGN.md section 4) and the summed device time.  Off by default; the only global state of the library.
+ * ---------------------------------------------------------------------------------------- */
+typedef enum {
+  MSF_K_GATHER_FWD = 0, MSF_K_GATHER_BWD, MSF_K_COS_FWD, MSF_K_COS_BWD, MSF_K_ROWNORM, MSF_K_NCE_FLASH, MSF_K_NCE_TWOPASS,
+  MSF_K_NCE_SIMT, MSF_K_NCE_BWD, MSF_K_GEMM, MSF_K_CROP_FWD, MSF_K_CROP_BWD, MSF_K_EMA, MSF_K_BN_STATS, MSF_K_BN_APPLY,
+  MSF_K_BN_APPLY_RES, MSF_K_BN_BWD_REDUCE, MSF_K_BN_BWD_ELEMT, MSF_K_BN_APPLY_POOL, MSF_K_BN_POOL_BWD_REDUCE,
+  MSF_K_BN_POOL_BWD_ELEMT, MSF_K_ADAM, MSF_K_COUNT
+} msf_kernel_id;
+typedef struct {
+  int32_t kernel;   /* msf_kernel_id */
+  int32_t launches; /* profiled calls */
+  double work;      /* summed algorithmic bytes or FLOP */
+  double ms;        /* summed device time between the event pairs */
+} msf_prof_record;
+int msf_prof_begin(int capacity /* event pairs to pre-create; calls beyond it are dropped and counted */);
+int msf_prof_end(msf_prof_record* out /* host, MSF_K_COUNT entries */, int* dropped /* host, may be NULL */);
+const char* msf_prof_kernel_name(int kernel);
+int msf_prof_kernel_bound(int kernel); /* 'h' HBM, 't' tensor pipe, 'f' fp32 FMA */
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,6 +43,13 @@ class CosPair(C.Structure):
                 ("rows", C.c_int64), ("dim", C.c_int32), ("coef", C.c_float)]
 
 
+class ProfRecord(C.Structure):
+    _fields_ = [("kernel", C.c_int32), ("launches", C.c_int32), ("work", C.c_double), ("ms", C.c_double)]
+
+
+MSF_K_COUNT = 22
+
+
 class EmaEntry(C.Structure):
     _fields_ = [("teacher", C.c_void_p), ("student", C.c_void_p), ("numel", C.c_int64)]
 
@@ -88,6 +95,10 @@ _SIGS = {
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "msf_bn2d_pool_bwd_elemt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "msf_prof_begin": (C.c_int, [C.c_int]),
+    "msf_prof_end": (C.c_int, [C.POINTER(ProfRecord), C.POINTER(C.c_int)]),
+    "msf_prof_kernel_name": (C.c_char_p, [C.c_int]),
+    "msf_prof_kernel_bound": (C.c_int, [C.c_int]),
 }
 EXPORTS = tuple(_SIGS)
 
@@ -128,3 +139,21 @@ def require_cuda(*tensors) -> None:
     for t in tensors:
         if t is not None and not t.is_cuda:
             raise RuntimeError("msfwsi_b200 ops run on CUDA tensors only (there is no CPU fallback)")
+
+
+def prof_begin(capacity: int = 1 << 16) -> None:
+    """Switch the library's launch profiler on (CUDA event pairs around every main kernel; see msf_prof_begin)."""
+    check(lib().msf_prof_begin(capacity), "msf_prof_begin")
+
+
+def prof_end():
+    """Switch it off; returns ({kernel name: {"launches", "work", "ms", "bound"}}, dropped)."""
+    recs = (ProfRecord * MSF_K_COUNT)()
+    dropped = C.c_int(0)
+    check(lib().msf_prof_end(recs, C.byref(dropped)), "msf_prof_end")
+    out = {}
+    for r in recs:
+        if r.launches:
+            out[lib().msf_prof_kernel_name(r.kernel).decode()] = {"launches": r.launches, "work": r.work, "ms": r.ms,
+                                                                  "bound": chr(lib().msf_prof_kernel_bound(r.kernel))}
+    return out, dropped.value

@@ -614,6 +614,7 @@ extern "C" int msf_bn2d_stats(const void* x, int64_t rows, int C, int dtype, dou
   const size_t smem = static_cast<size_t>(kThreads) * 2 * vec * sizeof(float);
   float* partial = static_cast<float*>(workspace);
   int nblk = 1;
+  ProfScope prof(stream, MSF_K_BN_STATS, static_cast<double>(rows) * C * dtype_size(dtype));
   MSF_DISPATCH_DTYPE(dtype, {
     nblk = reduce_grid(bn_stats_kernel<DT>, smem, l, rows, kStatsRows * l.rlanes);
     dim3 grid(static_cast<unsigned>(nblk), static_cast<unsigned>(l.cgroups));
@@ -646,6 +647,7 @@ extern "C" int msf_bn2d_apply(const void* x, const void* res, void* y, int64_t r
   const char* xp = static_cast<const char*>(x);
   const char* rp = static_cast<const char*>(res);
   char* yp = static_cast<char*>(y);
+  ProfScope prof(stream, res ? MSF_K_BN_APPLY_RES : MSF_K_BN_APPLY, static_cast<double>(rows) * C * dtype_size(dtype) * (res ? 3 : 2));
   if (res) {
     MSF_DISPATCH_DTYPE(dtype, (bn_apply_kernel<DT, true><<<stream_grid((chunks + 1) / 2), kThreads, 0, st>>>(xp, rp, yp, chunks, cvec, mean, invstd, gamma, beta, relu)));
   } else {
@@ -670,6 +672,7 @@ extern "C" int msf_bn2d_bwd_reduce(const void* x, const void* dy, const void* y_
   const char* dp = static_cast<const char*>(dy);
   const char* mp = static_cast<const char*>(y_mask);
   int nblk = 1;
+  ProfScope prof(stream, MSF_K_BN_BWD_REDUCE, static_cast<double>(rows) * C * dtype_size(dtype) * ((relu && y_mask) ? 3 : 2));
 #define MSF_BWD_REDUCE(MASK)                                                                                          \
   MSF_DISPATCH_DTYPE(dtype, {                                                                                         \
     nblk = reduce_grid(bn_bwd_reduce_kernel<DT, MASK>, smem, l, rows, kReduceRows * l.rlanes);                        \
@@ -702,6 +705,7 @@ extern "C" int msf_bn2d_bwd_elemt(const void* x, const void* dy, const void* y_m
   const char* mp = static_cast<const char*>(y_mask);
   char* dxp = static_cast<char*>(dx);
   char* drp = static_cast<char*>(dres);
+  ProfScope prof(stream, MSF_K_BN_BWD_ELEMT, static_cast<double>(rows) * C * dtype_size(dtype) * (3 + ((relu && y_mask) ? 1 : 0) + (dres ? 1 : 0)));
 #define MSF_BWD_ELEMT(MASK, DRES) \
   MSF_DISPATCH_DTYPE(dtype, (bn_bwd_elemt_kernel<DT, MASK, DRES><<<grid, kThreads, 0, st>>>(xp, dp, mp, dxp, drp, chunks, cvec, mean, invstd, gamma, beta, sums, count)))
   const int mask = !relu ? 0 : (y_mask ? 2 : 1);
@@ -738,6 +742,7 @@ extern "C" int msf_bn2d_apply_pool(const void* x, void* y, uint8_t* tap, int64_t
   if (int rc = check_pool(x, N, H, W, C, dtype, &g)) return rc;
   MSF_REQUIRE(y && tap && aligned16(y) && aligned16(tap) && mean && invstd, MSF_ERR_INVALID, "bad arguments");
   const int64_t groups = (static_cast<int64_t>(g.windows) + kThreads / g.cpad - 1) / (kThreads / g.cpad);
+  ProfScope prof(stream, MSF_K_BN_APPLY_POOL, (static_cast<double>(N) * H * W + static_cast<double>(g.windows)) * C * dtype_size(dtype) + static_cast<double>(g.windows) * C);
   MSF_DISPATCH_DTYPE(dtype, (bn_apply_pool_kernel<DT><<<resident_grid(bn_apply_pool_kernel<DT>, groups), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
                                 static_cast<const char*>(x), static_cast<char*>(y), tap, g, mean, invstd, gamma, beta)));
   MSF_LAUNCH_OK("bn_apply_pool_kernel");
@@ -757,6 +762,8 @@ extern "C" int msf_bn2d_pool_bwd_reduce(const void* x, const void* dpool, const 
   const size_t smem = static_cast<size_t>(kThreads) * 2 * vec * sizeof(float);
   float* partial = static_cast<float*>(workspace);
   int nblk = 1;
+  // x counted once (only arg-max positions are needed, at most the whole map), dpool + tap read
+  ProfScope prof(stream, MSF_K_BN_POOL_BWD_REDUCE, (static_cast<double>(N) * H * W + static_cast<double>(g.windows)) * C * dtype_size(dtype) + static_cast<double>(g.windows) * C);
   MSF_DISPATCH_DTYPE(dtype, {
     nblk = reduce_grid(bn_pool_bwd_reduce_kernel<DT>, smem, l, g.windows, l.rlanes);
     dim3 grid(static_cast<unsigned>(nblk), static_cast<unsigned>(l.cgroups));
@@ -775,6 +782,7 @@ extern "C" int msf_bn2d_pool_bwd_elemt(const void* x, const void* dpool, const u
   if (int rc = check_pool(x, N, H, W, C, dtype, &g)) return rc;
   MSF_REQUIRE(dpool && tap && dx && aligned16(dpool) && aligned16(dx) && mean && invstd && sums && count, MSF_ERR_INVALID, "bad arguments");
   const int64_t groups = (static_cast<int64_t>(g.windows) + kThreads / g.cpad - 1) / (kThreads / g.cpad);
+  ProfScope prof(stream, MSF_K_BN_POOL_BWD_ELEMT, (2.0 * N * H * W + static_cast<double>(g.windows)) * C * dtype_size(dtype) + static_cast<double>(g.windows) * C);
   MSF_DISPATCH_DTYPE(dtype, (bn_pool_bwd_elemt_kernel<DT><<<resident_grid(bn_pool_bwd_elemt_kernel<DT>, groups), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
                                 static_cast<const char*>(x), static_cast<const char*>(dpool), tap, static_cast<char*>(dx), g, mean, invstd,
                                 gamma, sums, count)));

@@ -12,6 +12,20 @@ namespace msf {
 
 void set_error(const char* fmt, ...);  // thread-local message behind msf_last_error()
 
+// Opt-in launch profiler (msf_prof_begin / msf_prof_end): records a CUDA event pair on `stream` around the scope when
+// profiling is on, otherwise costs one branch.  `work` = algorithmic bytes (HBM-bound kernels) or FLOP (tensor-bound).
+class ProfScope {
+ public:
+  ProfScope(void* stream, int kernel, double work);
+  ~ProfScope();
+  ProfScope(const ProfScope&) = delete;
+  ProfScope& operator=(const ProfScope&) = delete;
+
+ private:
+  int slot_;
+  void* stream_;
+};
+
 #define MSF_REQUIRE(cond, code, ...)   \
   do {                                 \
     if (!(cond)) {                     \

@@ -249,6 +249,9 @@ extern "C" int msf_cosine_loss_fwd(const msf_cos_pair* pairs, int n_pairs, int d
   MSF_REQUIRE(workspace && workspace_bytes >= P.total_blocks * sizeof(float), MSF_ERR_WORKSPACE,
               "workspace of %zu bytes < %zu required", workspace_bytes, P.total_blocks * sizeof(float));
   float* partials = static_cast<float*>(workspace);
+  double bytes = 0.0;  // p and z read, 16 B of row statistics written per row
+  for (int i = 0; i < n_pairs; ++i) bytes += 2.0 * pairs[i].rows * pairs[i].dim * dtype_size(dtype) + 16.0 * pairs[i].rows;
+  ProfScope prof(stream, MSF_K_COS_FWD, bytes);
   MSF_DISPATCH_DTYPE(dtype, (cos_fwd_kernel<DT><<<P.total_blocks, kThreads, 0, st>>>(P, partials)));
   MSF_LAUNCH_OK("cos_fwd_kernel");
   cos_final_kernel<<<1, 256, 0, st>>>(partials, P.total_blocks, loss_out);
@@ -263,6 +266,9 @@ extern "C" int msf_cosine_loss_bwd(const msf_cos_pair* pairs, int n_pairs, int d
   MSF_REQUIRE(grad_out, MSF_ERR_INVALID, "grad_out is NULL");
   if (P.total_blocks == 0) return MSF_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double bytes = 0.0;  // p, z and the row statistics read, grad_p written
+  for (int i = 0; i < n_pairs; ++i) bytes += 3.0 * pairs[i].rows * pairs[i].dim * dtype_size(dtype) + 16.0 * pairs[i].rows;
+  ProfScope prof(stream, MSF_K_COS_BWD, bytes);
   MSF_DISPATCH_DTYPE(dtype, (cos_bwd_kernel<DT><<<P.total_blocks, kThreads, 0, st>>>(P, grad_out)));
   MSF_LAUNCH_OK("cos_bwd_kernel");
   return MSF_OK;

@@ -288,6 +288,7 @@ extern "C" int msf_crop_resample_fwd(const void* feat, int64_t B, int C, int H, 
   int kroll = 4;
   while (kroll < 32 && kroll * 2 * ow <= 1024) kroll *= 2;
   const size_t fast_smem = (static_cast<size_t>((3 * oh + 3) & ~3) + static_cast<size_t>(8) * kroll * ow) * 4;
+  ProfScope prof(stream, MSF_K_CROP_FWD, (static_cast<double>(B) * C * H * W + static_cast<double>(rows) * ow) * dtype_size(dtype) + 16.0 * B * K);
   const bool fast_ok = vec_ok && ow % 32 == 0 && ow <= 32 * kMaxOxPerLane && owv <= 32 && (owv & (owv - 1)) == 0 &&
                        fast_smem <= 48 * 1024 && B * K < (1ll << 24);
   if (fast_ok) {
@@ -310,6 +311,7 @@ extern "C" int msf_crop_resample_bwd(const void* grad_out, int64_t B, int C, int
   if (B == 0) return MSF_OK;
   const Geo g{B, C, H, W, K, oh, ow};
   const int64_t total = B * K * static_cast<int64_t>(C) * oh * ow;
+  ProfScope prof(stream, MSF_K_CROP_BWD, static_cast<double>(total) * dtype_size(dtype) + 4.0 * B * C * H * W + 16.0 * B * K);
   MSF_DISPATCH_DTYPE(dtype, (crop_bwd_kernel<DT><<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(grad_out, boxes, grad_feat, g, total)));
   MSF_LAUNCH_OK("crop_bwd_kernel");
   return MSF_OK;

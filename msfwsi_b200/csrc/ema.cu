@@ -121,6 +121,8 @@ extern "C" int msf_ema_multi(const msf_ema_entry* entries, const int32_t* chunk_
   MSF_REQUIRE(dtype_ok(teacher_dtype) && dtype_ok(student_dtype), MSF_ERR_INVALID, "bad dtype");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const float m = momentum, om = one_minus_momentum;
+  // upper bound on the bytes (the last chunk of every tensor may be partial; numels live on the device)
+  ProfScope prof(stream, MSF_K_EMA, static_cast<double>(total_chunks) * MSF_EMA_CHUNK * (2.0 * dtype_size(teacher_dtype) + dtype_size(student_dtype)));
 #define MSF_EMA_CASE(T, S)                                                                                   \
   if (teacher_dtype == T && student_dtype == S) {                                                            \
     ema_kernel<T, S><<<total_chunks, kThreads, 0, st>>>(entries, chunk_prefix, n_tensors, m, om);            \

@@ -184,6 +184,9 @@ extern "C" int msf_gather_concat_fwd(const msf_gather_item* items, int n_items, 
   }
   P.K = K;
   P.n_keep = n_keep;
+  double bytes = 0.0;  // per item: tgt read + sorted written, ctx read, ms written, rev read
+  for (int i = 0; i < n_items; ++i) bytes += (2.0 * B * K + B + (n_keep + 1.0) * B) * items[i].d * dtype_size(dtype) + 8.0 * B * K;
+  ProfScope prof(stream, MSF_K_GATHER_FWD, bytes);
   return launch(P, dtype, status_flag, static_cast<cudaStream_t>(stream));
 }
 
@@ -210,5 +213,8 @@ extern "C" int msf_gather_concat_bwd(const msf_gather_grad_item* items, int n_it
   }
   P.K = K;
   P.n_keep = n_keep;
+  double bytes = 0.0;
+  for (int i = 0; i < n_items; ++i) bytes += (2.0 * B * K + B + (n_keep + 1.0) * B) * items[i].d * dtype_size(dtype) + 8.0 * B * K;
+  ProfScope prof(stream, MSF_K_GATHER_BWD, bytes);
   return launch(P, dtype, nullptr, static_cast<cudaStream_t>(stream));
 }

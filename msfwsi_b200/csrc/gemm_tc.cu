@@ -249,6 +249,7 @@ using namespace msf;
 extern "C" int msf_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t M, int64_t N,
                              int64_t K, int a_is_km, int b_is_kn, int out_dtype, float alpha, const float* bias, void* stream) {
   MSF_REQUIRE(out_dtype == MSF_F32 || out_dtype == MSF_BF16, MSF_ERR_INVALID, "out_dtype must be MSF_F32 or MSF_BF16");
+  ProfScope prof(stream, MSF_K_GEMM, 2.0 * static_cast<double>(M) * static_cast<double>(N) * static_cast<double>(K));
   return launch_gemm_tc(A, lda, B, ldb, C, ldc, M, N, K, b_is_kn, out_dtype == MSF_F32 ? 0 : 1, alpha, bias, nullptr, 0,
                         static_cast<cudaStream_t>(stream), a_is_km);
 }

@@ -333,6 +333,7 @@ extern "C" int msf_rownorm(const void* x, int64_t rows, int dim, int in_dtype, f
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const char* xi = static_cast<const char*>(x);
   char* xo = static_cast<char*>(x_hat);
+  ProfScope prof(stream, MSF_K_ROWNORM, static_cast<double>(rows) * dim * (dtype_size(in_dtype) + dtype_size(out_dtype)) + 4.0 * rows);
 #define MSF_RN(I, O)                                                                                                 \
   if (in_dtype == I && out_dtype == O) {                                                                             \
     rownorm_kernel<I, O><<<static_cast<unsigned>(blocks), 256, 0, st>>>(xi, rows, dim, eps, xo, inv_norm, lanes);    \
@@ -383,6 +384,9 @@ extern "C" int msf_infonce_fwd_timed(const void* q_hat, const void* k_hat, int64
   float* partials = reinterpret_cast<float*>(ws + plan.off_part);
   const float a = kLog2e / tau;
   if (ev_main_start) MSF_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(ev_main_start), st));
+  {
+  ProfScope prof(stream, plan.mode == 0 ? MSF_K_NCE_FLASH : (plan.mode == 2 ? MSF_K_NCE_TWOPASS : MSF_K_NCE_SIMT),
+                 4.0 * static_cast<double>(nq) * static_cast<double>(n_keys) * dim);  // S = QK^T and O = PK
   if (plan.mode == 0) {
     if (int rc = launch_infonce_tc(q_hat, k_hat, nq, n_keys, dim, tau, plan, rowsum, o_part, st)) return rc;
   } else if (plan.mode == 2) {
@@ -397,6 +401,7 @@ extern "C" int msf_infonce_fwd_timed(const void* q_hat, const void* k_hat, int64
     infonce_simt_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(q_hat), static_cast<const float*>(k_hat), nq,
                                               n_keys, dim, a, a, plan.tiles_per_split, plan.nq_pad, rowsum, o_part);
     MSF_LAUNCH_OK("infonce_simt_kernel");
+  }
   }
   if (ev_main_stop) MSF_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(ev_main_stop), st));
   const uint32_t cpr = dim / (precision == MSF_BF16 ? 8 : 4);
@@ -435,6 +440,8 @@ extern "C" int msf_infonce_bwd(const void* q_hat, const void* k_hat, const float
   const char* qh = static_cast<const char*>(q_hat);
   const char* kh = static_cast<const char*>(k_hat);
   char* gq = static_cast<char*>(grad_q);
+  // O partials + q_hat + the positive key rows read, grad_q written
+  ProfScope prof(stream, MSF_K_NCE_BWD, static_cast<double>(nq) * dim * (4.0 * plan.splits + 2.0 * (precision == MSF_BF16 ? 2 : 4) + dtype_size(grad_dtype)));
 #define MSF_NB(P, G)                                                                                              \
   if (precision == P && grad_dtype == G) {                                                                        \
     nce_bwd_kernel<P, G><<<blocks, 256, 0, st>>>(qh, kh, q_inv_norm, nq, dim, pos_offset, 1.f / tau, plan.splits, \

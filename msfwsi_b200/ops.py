@@ -12,7 +12,6 @@ import torch.distributed as dist
 from . import _lib as L
 
 COS_EPS = 1e-8  # nn.CosineSimilarity default (tools/ssl_train.py:422)
-PROFILE = None  # bench.py sets this to a list: (start_event, end_event, algorithmic_flops, path, dim) per InfoNCE forward main kernel
 
 
 def _contig(t: torch.Tensor) -> torch.Tensor:
@@ -205,17 +204,8 @@ class _InfoNCE(torch.autograd.Function):
         ws_bytes = L.lib().msf_infonce_workspace_bytes(nq, n_keys, dim, prec)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=p.device)
         loss_sum = torch.empty((), dtype=torch.float32, device=p.device)
-        if PROFILE is not None:  # bench.py: CUDA events recorded by the library right around the main kernel
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev0.record()  # creates the underlying cudaEvent_t handles
-            ev1.record()
-            L.check(L.lib().msf_infonce_fwd_timed(L.ptr(q_hat), L.ptr(k_all), nq, n_keys, dim, pos_offset, tau, prec, L.ptr(loss_sum), 0,
-                                                  L.ptr(ws), ws_bytes, L.stream_ptr(), ev0.cuda_event, ev1.cuda_event), "msf_infonce_fwd_timed")
-            kind = "flash" if (precision == torch.bfloat16 and dim in (64, 128, 256)) else ("twopass" if precision == torch.bfloat16 else "simt")
-            PROFILE.append((ev0, ev1, 4.0 * nq * n_keys * dim, kind, dim))
-        else:
-            L.check(L.lib().msf_infonce_fwd(L.ptr(q_hat), L.ptr(k_all), nq, n_keys, dim, pos_offset, tau, prec, L.ptr(loss_sum), 0,
-                                            L.ptr(ws), ws_bytes, L.stream_ptr()), "msf_infonce_fwd")
+        L.check(L.lib().msf_infonce_fwd(L.ptr(q_hat), L.ptr(k_all), nq, n_keys, dim, pos_offset, tau, prec, L.ptr(loss_sum), 0,
+                                        L.ptr(ws), ws_bytes, L.stream_ptr()), "msf_infonce_fwd")
         L.launch_count += 3
         ctx.save_for_backward(q_hat, k_all, q_inv, ws)
         ctx.meta = (nq, n_keys, dim, pos_offset, tau, prec, ws_bytes, p.dtype)
