@@ -210,7 +210,7 @@ int msf_ema_multi(const msf_ema_entry* entries /*device*/, const int32_t* chunk_
  * The activation is a [rows = N*H*W][C] matrix, C contiguous (NHWC), C a multiple of 8 (16-bit) or 4 (fp32).
  *
  * forward : msf_bn2d_stats -> (all-reduce `sums` over ranks for SyncBN) -> msf_bn2d_finalize -> msf_bn2d_apply[_pool]
- * backward: msf_bn2d[_pool]_bwd_reduce -> (all-reduce) -> msf_bn2d[_pool]_bwd_elemt
+ * backward: msf_bn2d_bwd_reduce -> (all-reduce) -> msf_bn2d[_pool]_bwd_elemt
  *   sums (forward)  : 2C+1 doubles {sum x, sum x^2 per channel, element count} -- sum-reducible over ranks
  *   sums (backward) : 2C doubles {sum dy', sum dy' * xhat}; grad_beta = sums[0:C], grad_gamma = sums[C:2C] (local part)
  *   dy' = dy * (y > 0) when relu != 0; y is recomputed from x, or read from `y_mask` (the saved output) when the
@@ -226,23 +226,28 @@ int msf_bn2d_finalize(const double* sums /*2C+1*/, int C, float eps, float momen
 /* y = act(gamma * (x - mean) * invstd + beta (+ res)); res may be NULL; relu != 0 applies max(., 0). */
 int msf_bn2d_apply(const void* x, const void* res, void* y, int64_t rows, int C, int dtype, const float* mean,
                    const float* invstd, const float* gamma, const float* beta, int relu, void* stream);
+/* gpool (may be NULL): gradient of the global average pool of the same output y (src/models/resnet.py:250-254 pools the
+ * layer outputs), (N, C) in the activation dtype with hw = H*W rows per image: dy of every row of image n is taken as
+ * dy + gpool[n, :] / hw, i.e. the pooled branch's gradient is folded in instead of being expanded and added by ATen.
+ * Only with relu != 0 and y_mask given (the BasicBlock output); rows*C/vec must be < 2^32. */
 int msf_bn2d_bwd_reduce(const void* x, const void* dy, const void* y_mask, int64_t rows, int C, int dtype,
                         const float* mean, const float* invstd, const float* gamma, const float* beta, int relu,
-                        double* sums_out /*2C*/, void* workspace, size_t workspace_bytes, void* stream);
+                        const void* gpool, int64_t hw, double* sums_out /*2C*/, void* workspace, size_t workspace_bytes,
+                        void* stream);
 /* dx = gamma*invstd * (dy' - sums[c]/count - xhat * sums[C+c]/count); dres (may be NULL) = dy'.
  * `count` is a DEVICE double (element 2C of the forward sums). */
 int msf_bn2d_bwd_elemt(const void* x, const void* dy, const void* y_mask, void* dx, void* dres, int64_t rows, int C,
                        int dtype, const float* mean, const float* invstd, const float* gamma, const float* beta,
-                       int relu, const double* sums /*2C*/, const double* count, void* stream);
-/* Stem: y (N,PH,PW,C) = maxpool3x3/stride2/pad1(relu(bn(x))), x (N,H,W,C), PH = (H-1)/2+1, PW = (W-1)/2+1;
- * tap (N,PH,PW,C) uint8 = arg-max tap dr*3+dc of each output (first maximum in scan order over the values as
- * rounded to `dtype`, ATen's max_pool2d rule), 255 where the output is 0 (no gradient). */
-int msf_bn2d_apply_pool(const void* x, void* y, uint8_t* tap, int64_t N, int H, int W, int C, int dtype,
+                       int relu, const void* gpool, int64_t hw, const double* sums /*2C*/, const double* count,
+                       void* stream);
+/* Stem: y (N,PH,PW,C) = maxpool3x3/stride2/pad1(relu(bn(x))), x (N,H,W,C), PH = (H-1)/2+1, PW = (W-1)/2+1, N*PH*PW < 2^31.
+ * tap (N,PH,PW,C) uint8 = arg-max tap dr*3+dc of each output (first maximum in scan order, ATen's max_pool2d rule),
+ * 255 where the output is 0 (no gradient); x_arg (N,PH,PW,C) = the x value at the arg-max.
+ * Backward: dy' lives on the pooled grid, so the reduction is msf_bn2d_bwd_reduce(x_arg, dpool, y_mask = y, rows = N*PH*PW,
+ * relu = 1) -- a streaming pass over pooled-size tensors -- followed by msf_bn2d_pool_bwd_elemt, which scatters the pooled
+ * gradient to the arg-max positions and applies the batch-norm input gradient in one pass over x. */
+int msf_bn2d_apply_pool(const void* x, void* y, uint8_t* tap, void* x_arg, int64_t N, int H, int W, int C, int dtype,
                         const float* mean, const float* invstd, const float* gamma, const float* beta, void* stream);
-int msf_bn2d_pool_bwd_reduce(const void* x, const void* dpool, const uint8_t* tap, int64_t N, int H, int W, int C,
-                             int dtype, const float* mean, const float* invstd, double* sums_out /*2C*/,
-                             void* workspace, size_t workspace_bytes /* msf_bn2d_workspace_bytes(N*PH*PW, C) */,
-                             void* stream);
 int msf_bn2d_pool_bwd_elemt(const void* x, const void* dpool, const uint8_t* tap, void* dx, int64_t N, int H, int W,
                             int C, int dtype, const float* mean, const float* invstd, const float* gamma,
                             const double* sums /*2C*/, const double* count, void* stream);
@@ -256,8 +261,8 @@ int msf_bn2d_pool_bwd_elemt(const void* x, const void* dpool, const uint8_t* tap
 typedef enum {
   MSF_K_GATHER_FWD = 0, MSF_K_GATHER_BWD, MSF_K_COS_FWD, MSF_K_COS_BWD, MSF_K_ROWNORM, MSF_K_NCE_FLASH, MSF_K_NCE_TWOPASS,
   MSF_K_NCE_SIMT, MSF_K_NCE_BWD, MSF_K_GEMM, MSF_K_CROP_FWD, MSF_K_CROP_BWD, MSF_K_EMA, MSF_K_BN_STATS, MSF_K_BN_APPLY,
-  MSF_K_BN_APPLY_RES, MSF_K_BN_BWD_REDUCE, MSF_K_BN_BWD_ELEMT, MSF_K_BN_APPLY_POOL, MSF_K_BN_POOL_BWD_REDUCE,
-  MSF_K_BN_POOL_BWD_ELEMT, MSF_K_ADAM, MSF_K_COUNT
+  MSF_K_BN_APPLY_RES, MSF_K_BN_BWD_REDUCE, MSF_K_BN_BWD_ELEMT, MSF_K_BN_APPLY_POOL, MSF_K_BN_POOL_BWD_ELEMT,
+  MSF_K_ADAM, MSF_K_COUNT
 } msf_kernel_id;
 typedef struct {
   int32_t kernel;   /* msf_kernel_id */

@@ -116,25 +116,20 @@ __global__ void __launch_bounds__(kThreads) bn_stats_kernel(const char* __restri
   cta_reduce_store<V>(s, q, ct, cvec, cl, rl, partial);
 }
 
-// partial [nblk][2][C] -> sums[2][C] (fp64); sums[2C] = count when count >= 0.  32 consecutive (which, channel) entries
-// per CTA, 8 block lanes each summing every 8th row block, combined in fixed order.
-__global__ void __launch_bounds__(256) bn_combine_kernel(const float* __restrict__ partial, int nblk, int C, double* __restrict__ sums,
-                                                         double count) {
-  __shared__ double sh[8][32];
-  const int lane = threadIdx.x & 31, sub = threadIdx.x >> 5;
-  const int e = blockIdx.x * 32 + lane;
+// partial [nblk][2][C] -> sums[2][C] (fp64); sums[2C] = count when count >= 0.  One warp per (which, channel) entry:
+// lane l sums the row blocks l, l+32, ... in fp64, then a fixed butterfly over the lanes (deterministic).
+constexpr int kCombineWarps = 8;
+__global__ void __launch_bounds__(kCombineWarps * 32) bn_combine_kernel(const float* __restrict__ partial, int nblk, int C,
+                                                                        double* __restrict__ sums, double count) {
+  const int lane = threadIdx.x & 31;
+  const int e = blockIdx.x * kCombineWarps + (threadIdx.x >> 5);
   if (blockIdx.x == 0 && threadIdx.x == 0 && count >= 0.0) sums[2 * C] = count;
+  if (e >= 2 * C) return;
   double t = 0.0;
-  if (e < 2 * C)
-    for (int b = sub; b < nblk; b += 8) t += static_cast<double>(partial[static_cast<size_t>(b) * 2 * C + e]);
-  sh[sub][lane] = t;
-  __syncthreads();
-  if (sub == 0 && e < 2 * C) {
-    double a = sh[0][lane];
+  for (int b = lane; b < nblk; b += 32) t += static_cast<double>(partial[static_cast<size_t>(b) * 2 * C + e]);
 #pragma unroll
-    for (int j = 1; j < 8; ++j) a += sh[j][lane];
-    sums[e] = a;
-  }
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if (lane == 0) sums[e] = t;
 }
 
 // sums[2C+1] (possibly all-reduced over ranks) -> mean, invstd, running stats (momentum update, unbiased variance)
@@ -210,11 +205,14 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const char* __restri
 
 // MASK: 0 none, 1 relu mask recomputed from x, 2 relu mask from the saved output y
 constexpr int kReduceRows = 4;  // rows in flight per thread (x 2 or 3 tensors)
-template <int DT, int MASK>
+// GP: a per-(image, channel) gradient gp[n][c] * gp_scale is added to every dy of that image before the mask (the
+// backward of a global average pool over the same output, folded in instead of being materialised and added).
+template <int DT, int MASK, bool GP>
 __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const char* __restrict__ x, const char* __restrict__ dy,
                                                                  const char* __restrict__ ymask, int64_t rows, int cvec, int ct,
                                                                  const float* __restrict__ mean, const float* __restrict__ invstd,
                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                 const char* __restrict__ gp, unsigned hw, float gp_scale,
                                                                  float* __restrict__ partial) {
   constexpr int V = Elem<DT>::VEC;
   constexpr int U = kReduceRows;
@@ -231,26 +229,28 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const char* __r
   }
   const int64_t step = static_cast<int64_t>(gridDim.x) * U * rlanes;
   for (int64_t r = static_cast<int64_t>(blockIdx.x) * U * rlanes + rl; r < rows; r += step) {
-    uint4 a[U], b[U], m[U];
+    uint4 a[U], b[U], m[U], p[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t rr = r + u * rlanes;
-      a[u] = b[u] = m[u] = make_uint4(0, 0, 0, 0);  // dy = 0 contributes nothing
+      a[u] = b[u] = m[u] = p[u] = make_uint4(0, 0, 0, 0);  // dy = 0 (and y = 0 for the mask) contributes nothing
       if (rr < rows) {
         a[u] = ldg_stream(x + (rr * cvec + chunk) * 16);
         b[u] = ldg_stream(dy + (rr * cvec + chunk) * 16);
         if (MASK == 2) m[u] = ldg_stream(ymask + (rr * cvec + chunk) * 16);
+        if (GP) p[u] = ldg_keep(gp + (static_cast<int64_t>(static_cast<unsigned>(rr) / hw) * cvec + chunk) * 16);
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      float fx[V], fd[V], fm[V];
+      float fx[V], fd[V], fm[V], fp[V];
       Elem<DT>::unpack(a[u], fx);
       Elem<DT>::unpack(b[u], fd);
       if (MASK == 2) Elem<DT>::unpack(m[u], fm);
+      if (GP) Elem<DT>::unpack(p[u], fp);
 #pragma unroll
       for (int i = 0; i < V; ++i) {
-        float d = fd[i];
+        float d = GP ? fmaf(fp[i], gp_scale, fd[i]) : fd[i];
         if (MASK == 1 && fmaf(fx[i], k.sc[i], k.sh[i]) <= 0.f) d = 0.f;
         if (MASK == 2 && fm[i] <= 0.f) d = 0.f;
         s[i] += d;
@@ -261,59 +261,80 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const char* __r
   cta_reduce_store<V>(s, q, ct, cvec, cl, rl, partial);
 }
 
-template <int DT, int MASK, bool DRES>
+// per-channel constants of the input-gradient pass:  dx = sc*(d - m1 - xhat*m2) = sc*d + (ca*x + cb),
+// m1 = sum(dy')/n, m2 = sum(dy'*xhat)/n, ca = -sc*m2*invstd, cb = sc*(m2*invstd*mean - m1)
+template <int V>
+struct GradConst {
+  float sc[V], ca[V], cb[V];
+  __device__ __forceinline__ void load(int ch0, int C, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                       const float* __restrict__ gamma, const double* __restrict__ sums, float inv_n) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int ch = ch0 + i;
+      const float is = __ldg(invstd + ch), mu = __ldg(mean + ch);
+      sc[i] = is * (gamma ? __ldg(gamma + ch) : 1.f);
+      const float m1 = static_cast<float>(sums[ch]) * inv_n, m2 = static_cast<float>(sums[C + ch]) * inv_n;
+      ca[i] = -sc[i] * m2 * is;
+      cb[i] = sc[i] * (m2 * is * mu - m1);
+    }
+  }
+};
+
+template <int DT, int MASK, bool DRES, bool GP>
 __global__ void __launch_bounds__(kThreads) bn_bwd_elemt_kernel(const char* __restrict__ x, const char* __restrict__ dy,
                                                                 const char* __restrict__ ymask, char* __restrict__ dx,
                                                                 char* __restrict__ dres, int64_t chunks, int cvec,
                                                                 const float* __restrict__ mean, const float* __restrict__ invstd,
                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                 const double* __restrict__ sums /*[2][C]*/,
-                                                                const double* __restrict__ count) {
+                                                                const double* __restrict__ count, const char* __restrict__ gp,
+                                                                unsigned hw_chunks /* H*W*cvec */, float gp_scale) {
   constexpr int V = Elem<DT>::VEC;
   const int C = cvec * V;
   const float inv_n = static_cast<float>(1.0 / *count);
   const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
   const bool fixed = (kThreads % cvec) == 0;
-  ChanConst<V> k;
-  float c_mu[V], c_is[V], c_m1[V], c_m2[V];
+  GradConst<V> g;
+  float sh[V];  // relu mask recomputation: y = x*sc + sh
   auto load_consts = [&](int ch0) {
-    k.load(ch0, mean, invstd, gamma, beta);
+    g.load(ch0, C, mean, invstd, gamma, sums, inv_n);
+    if (MASK == 1) {
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const int ch = ch0 + i;
-      c_mu[i] = __ldg(mean + ch);
-      c_is[i] = __ldg(invstd + ch);
-      c_m1[i] = static_cast<float>(sums[ch]) * inv_n;
-      c_m2[i] = static_cast<float>(sums[C + ch]) * inv_n;
+      for (int i = 0; i < V; ++i) sh[i] = fmaf(-__ldg(mean + ch0 + i), g.sc[i], beta ? __ldg(beta + ch0 + i) : 0.f);
     }
   };
   if (fixed) load_consts((threadIdx.x % cvec) * V);
   for (int64_t e = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; e < chunks; e += 2 * stride) {
-    uint4 vx[2], vd[2], vm[2];
+    uint4 vx[2], vd[2], vm[2], vp[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u)
       if (e + u * stride < chunks) {
-        vx[u] = ldg_stream(x + (e + u * stride) * 16);
-        vd[u] = ldg_stream(dy + (e + u * stride) * 16);
-        if (MASK == 2) vm[u] = ldg_stream(ymask + (e + u * stride) * 16);
+        const int64_t idx = e + u * stride;
+        vx[u] = ldg_stream(x + idx * 16);
+        vd[u] = ldg_stream(dy + idx * 16);
+        if (MASK == 2) vm[u] = ldg_stream(ymask + idx * 16);
+        if (GP) {  // chunk (n, c) of the pooled gradient; 32-bit index math (the ABI requires rows*cvec < 2^32 here)
+          const unsigned i32 = static_cast<unsigned>(idx);
+          vp[u] = ldg_keep(gp + (static_cast<int64_t>(i32 / hw_chunks) * cvec + i32 % static_cast<unsigned>(cvec)) * 16);
+        }
       }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int64_t idx = e + u * stride;
       if (idx >= chunks) break;
       if (!fixed) load_consts(static_cast<int>(idx % cvec) * V);
-      float fx[V], fd[V], fm[V];
+      float fx[V], fd[V], fm[V], fp[V];
       Elem<DT>::unpack(vx[u], fx);
       Elem<DT>::unpack(vd[u], fd);
       if (MASK == 2) Elem<DT>::unpack(vm[u], fm);
+      if (GP) Elem<DT>::unpack(vp[u], fp);
 #pragma unroll
       for (int i = 0; i < V; ++i) {
-        float d = fd[i];
-        if (MASK == 1 && fmaf(fx[i], k.sc[i], k.sh[i]) <= 0.f) d = 0.f;
+        float d = GP ? fmaf(fp[i], gp_scale, fd[i]) : fd[i];
+        if (MASK == 1 && fmaf(fx[i], g.sc[i], sh[i]) <= 0.f) d = 0.f;
         if (MASK == 2 && fm[i] <= 0.f) d = 0.f;
         fd[i] = d;
-        const float xh = (fx[i] - c_mu[i]) * c_is[i];
-        fx[i] = k.sc[i] * (d - c_m1[i] - xh * c_m2[i]);
+        fx[i] = fmaf(g.sc[i], d, fmaf(g.ca[i], fx[i], g.cb[i]));
       }
       stg_stream(dx + idx * 16, Elem<DT>::pack(fx));
       if (DRES) stg_stream(dres + idx * 16, Elem<DT>::pack(fd));
@@ -372,23 +393,49 @@ __device__ __forceinline__ void store_taps(unsigned char* __restrict__ tap, int6
   }
 }
 template <int V>
-__device__ __forceinline__ void load_taps(const unsigned char* __restrict__ tap, int64_t e, uint32_t* b /*[V]*/) {
-  if (V == 8) {
-    const uint2 t = __ldg(reinterpret_cast<const uint2*>(tap + e * 8));
-#pragma unroll
-    for (int i = 0; i < 8; ++i) b[i] = ((i < 4 ? t.x : t.y) >> (8 * (i & 3))) & 255u;
-  } else {
-    const uint32_t t = __ldg(reinterpret_cast<const uint32_t*>(tap + e * 4));
-#pragma unroll
-    for (int i = 0; i < 4; ++i) b[i] = (t >> (8 * i)) & 255u;
-  }
+__device__ __forceinline__ uint2 load_tap_words(const unsigned char* __restrict__ tap, int64_t e) {
+  if (V == 8) return __ldg(reinterpret_cast<const uint2*>(tap + e * 8));
+  return make_uint2(__ldg(reinterpret_cast<const uint32_t*>(tap + e * 4)), 0xffffffffu);
 }
+__device__ __forceinline__ uint32_t tap_byte(const uint2& t, int k) { return ((k < 4 ? t.x : t.y) >> (8 * (k & 3))) & 255u; }
 
+// packed pair arithmetic on the 16-bit dtypes
+template <int DT>
+struct Pk;
+template <>
+struct Pk<MSF_BF16> {
+  static constexpr uint32_t kNegInf2 = 0xff80ff80u;
+  __device__ static __forceinline__ uint32_t gt_mask(uint32_t a, uint32_t b) {
+    return __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  }
+  __device__ static __forceinline__ uint32_t add(uint32_t a, uint32_t b) {
+    const __nv_bfloat162 r = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
+};
+template <>
+struct Pk<MSF_F16> {
+  static constexpr uint32_t kNegInf2 = 0xfc00fc00u;
+  __device__ static __forceinline__ uint32_t gt_mask(uint32_t a, uint32_t b) {
+    return __hgt2_mask(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+  }
+  __device__ static __forceinline__ uint32_t add(uint32_t a, uint32_t b) {
+    const __half2 r = __hadd2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
+};
+
+// Forward.  y = relu(max over the window of bn(x)); because bn is monotone in x per channel (increasing for sc > 0,
+// decreasing for sc < 0, constant for sc == 0) the arg-max is found on the stored x values themselves: key = x with
+// the sign flipped where sc < 0 and zeroed where sc == 0, compared two channels at a time for the 16-bit dtypes.
+// Writes the pooled output, the arg-max tap byte (255 = ReLU-dead) and the x value at the arg-max (x_arg), which
+// turns the backward reduction into a plain streaming pass over pooled-size tensors.
 template <int DT>
 __global__ void __launch_bounds__(kThreads) bn_apply_pool_kernel(const char* __restrict__ x, char* __restrict__ y,
-                                                                 unsigned char* __restrict__ tap, PoolGeom g,
-                                                                 const float* __restrict__ mean, const float* __restrict__ invstd,
-                                                                 const float* __restrict__ gamma, const float* __restrict__ beta) {
+                                                                 unsigned char* __restrict__ tap, char* __restrict__ xarg,
+                                                                 PoolGeom g, const float* __restrict__ mean,
+                                                                 const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta) {
   constexpr int V = Elem<DT>::VEC;
   const int chunk = threadIdx.x % g.cpad;
   if (chunk >= g.cvec) return;
@@ -397,118 +444,129 @@ __global__ void __launch_bounds__(kThreads) bn_apply_pool_kernel(const char* __r
   k.load(chunk * V, mean, invstd, gamma, beta);
   unsigned g0, g1, wpi;
   cta_group_range(g, g0, g1, wpi);
-  for (unsigned grp = g0; grp < g1; ++grp) {
-    const unsigned w = grp * wpi + lane_w;
-    if (w >= g.windows) break;
-    const WinPos p = decode_window(w, g);
-    uint4 v[9];
-    bool ok[9];
+  if constexpr (DT == MSF_F32) {
+    for (unsigned grp = g0; grp < g1; ++grp) {
+      const unsigned w = grp * wpi + lane_w;
+      if (w >= g.windows) break;
+      const WinPos p = decode_window(w, g);
+      uint4 v[9];
+      bool ok[9];
+      // tap (dr, dc) lives (dr*W + dc)*cvec chunks after tap (0, 0); only in-range taps are dereferenced
+      const char* p0 = x + in_chunk(g, p.n, 2 * p.ph - 1, 2 * p.pw - 1, chunk) * 16;
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const int r = 2 * p.ph - 1 + t / 3, c = 2 * p.pw - 1 + t % 3;
-      ok[t] = r >= 0 && r < g.H && c >= 0 && c < g.W;
-      if (ok[t]) v[t] = ldg_keep(x + in_chunk(g, p.n, r, c, chunk) * 16);
+      for (int t = 0; t < 9; ++t) {
+        const int r = 2 * p.ph - 1 + t / 3, c = 2 * p.pw - 1 + t % 3;
+        ok[t] = r >= 0 && r < g.H && c >= 0 && c < g.W;
+        if (ok[t]) v[t] = ldg_keep(p0 + static_cast<int64_t>(((t / 3) * g.W + (t % 3)) * g.cvec) * 16);
+      }
+      float best[V], bx[V];
+      uint32_t bi[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) { best[i] = -CUDART_INF_F; bx[i] = 0.f; bi[i] = 0; }
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        if (!ok[t]) continue;
+        float f[V];
+        Elem<DT>::unpack(v[t], f);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          const float key = k.sc[i] > 0.f ? f[i] : (k.sc[i] < 0.f ? -f[i] : 0.f);
+          if (key > best[i]) { best[i] = key; bx[i] = f[i]; bi[i] = t; }
+        }
+      }
+      float out[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float o = fmaf(bx[i], k.sc[i], k.sh[i]);
+        if (!(o > 0.f)) bi[i] = 255u;
+        out[i] = fmaxf(o, 0.f);
+      }
+      const int64_t e = static_cast<int64_t>(w) * g.cvec + chunk;
+      stg_stream(y + e * 16, Elem<DT>::pack(out));
+      stg_stream(xarg + e * 16, Elem<DT>::pack(bx));
+      store_taps<V>(tap, e, bi);
     }
-    float best[V];
-    uint32_t bi[V];
+  } else {
+    uint32_t flip[4], keep[4], some_zero = 0u;
 #pragma unroll
-    for (int i = 0; i < V; ++i) { best[i] = -CUDART_INF_F; bi[i] = 0; }
+    for (int i = 0; i < 4; ++i) {
+      const float lo = k.sc[2 * i], hi = k.sc[2 * i + 1];
+      flip[i] = (lo < 0.f ? 0x8000u : 0u) | (hi < 0.f ? 0x80000000u : 0u);
+      keep[i] = (lo != 0.f ? 0xffffu : 0u) | (hi != 0.f ? 0xffff0000u : 0u);
+      some_zero |= ~keep[i];
+      // opaque to the optimiser: otherwise it re-derives the masks from sc (8 FSETP + 8 SEL) for every tap
+      asm volatile("" : "+r"(flip[i]), "+r"(keep[i]));
+    }
+    asm volatile("" : "+r"(some_zero));
+    const bool has_zero = some_zero != 0u;  // a channel with sc == 0 (gamma == 0): x_arg cannot be recovered from the key
+    for (unsigned grp = g0; grp < g1; ++grp) {
+      const unsigned w = grp * wpi + lane_w;
+      if (w >= g.windows) break;
+      const WinPos p = decode_window(w, g);
+      uint4 v[9];
+      bool ok[9];
+      // tap (dr, dc) lives (dr*W + dc)*cvec chunks after tap (0, 0); only in-range taps are dereferenced
+      const char* p0 = x + in_chunk(g, p.n, 2 * p.ph - 1, 2 * p.pw - 1, chunk) * 16;
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      if (!ok[t]) continue;
-      float f[V];
-      Elem<DT>::unpack(v[t], f);
+      for (int t = 0; t < 9; ++t) {
+        const int r = 2 * p.ph - 1 + t / 3, c = 2 * p.pw - 1 + t % 3;
+        ok[t] = r >= 0 && r < g.H && c >= 0 && c < g.W;
+        if (ok[t]) v[t] = ldg_keep(p0 + static_cast<int64_t>(((t / 3) * g.W + (t % 3)) * g.cvec) * 16);
+      }
+      uint32_t best[4], bx[4], bi[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { best[i] = Pk<DT>::kNegInf2; bx[i] = 0u; bi[i] = 0u; }
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        if (!ok[t]) continue;
+        const uint32_t wv[4] = {v[t].x, v[t].y, v[t].z, v[t].w};
+        const uint32_t tc = static_cast<uint32_t>(t) * 0x00010001u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t key = (wv[i] ^ flip[i]) & keep[i];
+          const uint32_t m = Pk<DT>::gt_mask(key, best[i]);
+          best[i] = (key & m) | (best[i] & ~m);
+          bi[i] = (tc & m) | (bi[i] & ~m);
+          if (has_zero) bx[i] = (wv[i] & m) | (bx[i] & ~m);
+        }
+      }
+      if (!has_zero) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bx[i] = best[i] ^ flip[i];
+      }
+      float f[V], out[V];
+      Elem<DT>::unpack(make_uint4(bx[0], bx[1], bx[2], bx[3]), f);
+      uint32_t tb[V];
 #pragma unroll
       for (int i = 0; i < V; ++i) {
         const float o = fmaf(f[i], k.sc[i], k.sh[i]);
-        if (o > best[i]) { best[i] = o; bi[i] = t; }
+        tb[i] = o > 0.f ? ((bi[i >> 1] >> (16 * (i & 1))) & 255u) : 255u;
+        out[i] = fmaxf(o, 0.f);
       }
+      const int64_t e = static_cast<int64_t>(w) * g.cvec + chunk;
+      stg_stream(y + e * 16, Elem<DT>::pack(out));
+      stg_stream(xarg + e * 16, make_uint4(bx[0], bx[1], bx[2], bx[3]));
+      store_taps<V>(tap, e, tb);
     }
-#pragma unroll
-    for (int i = 0; i < V; ++i) {
-      if (!(best[i] > 0.f)) bi[i] = 255u;
-      best[i] = fmaxf(best[i], 0.f);
-    }
-    const int64_t e = static_cast<int64_t>(w) * g.cvec + chunk;
-    stg_stream(y + e * 16, Elem<DT>::pack(best));
-    store_taps<V>(tap, e, bi);
   }
 }
 
-// partial sums over the pooling windows: s = sum dpool (alive), q = sum dpool * xhat(arg-max position)
-template <int DT>
-__global__ void __launch_bounds__(kThreads) bn_pool_bwd_reduce_kernel(const char* __restrict__ x, const char* __restrict__ dpool,
-                                                                      const unsigned char* __restrict__ tap, PoolGeom g, int ct,
-                                                                      const float* __restrict__ mean, const float* __restrict__ invstd,
-                                                                      float* __restrict__ partial) {
-  constexpr int V = Elem<DT>::VEC;
-  const int cl = threadIdx.x % ct, rl = threadIdx.x / ct, rlanes = kThreads / ct;
-  const int chunk = blockIdx.y * ct + cl;
-  float mu[V], is[V], s[V], q[V];
-#pragma unroll
-  for (int i = 0; i < V; ++i) {
-    mu[i] = mean[chunk * V + i];
-    is[i] = invstd[chunk * V + i];
-    s[i] = q[i] = 0.f;
-  }
-  // contiguous window range per CTA (L1 reuse of the rows shared by vertically adjacent windows)
-  const unsigned per = (g.windows + gridDim.x - 1) / gridDim.x;
-  const unsigned w0 = min(blockIdx.x * per, g.windows), w1 = min(w0 + per, g.windows);
-  for (unsigned w = w0 + rl; w < w1; w += rlanes) {
-    const int64_t e = static_cast<int64_t>(w) * g.cvec + chunk;
-    uint32_t b[V];
-    load_taps<V>(tap, e, b);
-    float d[V];
-    Elem<DT>::unpack(ldg_stream(dpool + e * 16), d);
-    uint32_t used = 0;
-#pragma unroll
-    for (int i = 0; i < V; ++i)
-      if (b[i] < 9u) { used |= 1u << b[i]; s[i] += d[i]; }
-    const WinPos p = decode_window(w, g);
-    while (used) {
-      const int t = __ffs(used) - 1;
-      used &= used - 1;
-      float f[V];
-      Elem<DT>::unpack(ldg_keep(x + in_chunk(g, p.n, 2 * p.ph - 1 + t / 3, 2 * p.pw - 1 + t % 3, chunk) * 16), f);
-#pragma unroll
-      for (int i = 0; i < V; ++i)
-        if (b[i] == static_cast<uint32_t>(t)) q[i] = fmaf(d[i], (f[i] - mu[i]) * is[i], q[i]);
-    }
-  }
-  cta_reduce_store<V>(s, q, ct, g.cvec, cl, rl, partial);
-}
-
-// One thread owns the 2x2 input positions (2a+i, 2b+j) of block (a, b) for one chunk.  They are covered by the windows
-// (a+da, b+db), da, db in {0,1}: position (i, j) is tap (i-2da+1)*3 + (j-2db+1) of window (da, db) when i >= da, j >= db.
-template <int V>
-__device__ __forceinline__ uint2 load_tap_words(const unsigned char* __restrict__ tap, int64_t e) {
-  if (V == 8) return __ldg(reinterpret_cast<const uint2*>(tap + e * 8));
-  return make_uint2(__ldg(reinterpret_cast<const uint32_t*>(tap + e * 4)), 0xffffffffu);
-}
-__device__ __forceinline__ uint32_t tap_byte(const uint2& t, int k) { return ((k < 4 ? t.x : t.y) >> (8 * (k & 3))) & 255u; }
-
+// Input gradient through pool + relu + bn.  One thread owns the 2x2 input positions (2a+i, 2b+j) of block (a, b) for
+// one chunk.  They are covered by the windows (a+da, b+db), da, db in {0,1}: position (i, j) is tap
+// (i-2da+1)*3 + (j-2db+1) of window (da, db) when i >= da and j >= db.  dy' of a position = sum of the pooled gradients
+// of the windows whose arg-max it is (for the 16-bit dtypes selected with byte compares and summed as packed pairs).
 template <int DT>
 __global__ void __launch_bounds__(kThreads, 2) bn_pool_bwd_elemt_kernel(const char* __restrict__ x, const char* __restrict__ dpool,
-                                                                     const unsigned char* __restrict__ tap, char* __restrict__ dx,
-                                                                     PoolGeom g, const float* __restrict__ mean,
-                                                                     const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                                                     const double* __restrict__ sums, const double* __restrict__ count) {
+                                                                        const unsigned char* __restrict__ tap, char* __restrict__ dx,
+                                                                        PoolGeom g, const float* __restrict__ mean,
+                                                                        const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                                        const double* __restrict__ sums, const double* __restrict__ count) {
   constexpr int V = Elem<DT>::VEC;
   const int chunk = threadIdx.x % g.cpad;
   if (chunk >= g.cvec) return;
   const unsigned lane_w = threadIdx.x / g.cpad;
-  const int C = g.cvec * V;
-  const float inv_n = static_cast<float>(1.0 / *count);
-  float c_mu[V], c_is[V], c_sc[V], c_m1[V], c_m2[V];
-#pragma unroll
-  for (int i = 0; i < V; ++i) {
-    const int ch = chunk * V + i;
-    c_mu[i] = __ldg(mean + ch);
-    c_is[i] = __ldg(invstd + ch);
-    c_sc[i] = c_is[i] * (gamma ? __ldg(gamma + ch) : 1.f);
-    c_m1[i] = static_cast<float>(sums[ch]) * inv_n;
-    c_m2[i] = static_cast<float>(sums[C + ch]) * inv_n;
-  }
+  GradConst<V> gc;
+  gc.load(chunk * V, g.cvec * V, mean, invstd, gamma, sums, static_cast<float>(1.0 / *count));
   unsigned g0, g1, wpi;
   cta_group_range(g, g0, g1, wpi);
   for (unsigned grp = g0; grp < g1; ++grp) {
@@ -517,16 +575,17 @@ __global__ void __launch_bounds__(kThreads, 2) bn_pool_bwd_elemt_kernel(const ch
     const WinPos p = decode_window(w, g);
     uint4 vx[2][2], vd[2][2];
     uint2 tb[2][2];
-    bool okx[2][2], okw[2][2];
+    bool okx[2][2];
+    const int64_t xe = in_chunk(g, p.n, 2 * p.ph, 2 * p.pw, chunk);   // chunk index of position (0, 0) of the block
+    const int64_t we0 = static_cast<int64_t>(w) * g.cvec + chunk;     // chunk index of window (a, b)
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         okx[i][j] = 2 * p.ph + i < g.H && 2 * p.pw + j < g.W;
-        okw[i][j] = p.ph + i < g.PH && p.pw + j < g.PW;
-        if (okx[i][j]) vx[i][j] = ldg_stream(x + in_chunk(g, p.n, 2 * p.ph + i, 2 * p.pw + j, chunk) * 16);
-        if (okw[i][j]) {
-          const int64_t we = (static_cast<int64_t>(w) + i * g.PW + j) * g.cvec + chunk;
+        if (okx[i][j]) vx[i][j] = ldg_stream(x + (xe + (i * g.W + j) * g.cvec) * 16);
+        if (p.ph + i < g.PH && p.pw + j < g.PW) {
+          const int64_t we = we0 + (i * g.PW + j) * g.cvec;
           vd[i][j] = ldg_keep(dpool + we * 16);
           tb[i][j] = load_tap_words<V>(tap, we);
         } else {
@@ -534,36 +593,48 @@ __global__ void __launch_bounds__(kThreads, 2) bn_pool_bwd_elemt_kernel(const ch
           tb[i][j] = make_uint2(0xffffffffu, 0xffffffffu);
         }
       }
-    float fd[2][2][V];
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-      for (int j = 0; j < 2; ++j) Elem<DT>::unpack(vd[i][j], fd[i][j]);
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         if (!okx[i][j]) continue;
         float d[V];
+        if constexpr (DT == MSF_F32) {
 #pragma unroll
-        for (int k = 0; k < V; ++k) d[k] = 0.f;
+          for (int k = 0; k < V; ++k) d[k] = 0.f;
 #pragma unroll
-        for (int da = 0; da <= i; ++da)
+          for (int da = 0; da <= i; ++da)
 #pragma unroll
-          for (int db = 0; db <= j; ++db) {
-            const uint32_t me = static_cast<uint32_t>((i - 2 * da + 1) * 3 + (j - 2 * db + 1));
+            for (int db = 0; db <= j; ++db) {
+              const uint32_t me = static_cast<uint32_t>((i - 2 * da + 1) * 3 + (j - 2 * db + 1));
+              float fd[V];
+              Elem<DT>::unpack(vd[da][db], fd);
 #pragma unroll
-            for (int k = 0; k < V; ++k)
-              if (tap_byte(tb[da][db], k) == me) d[k] += fd[da][db][k];
-          }
+              for (int k = 0; k < V; ++k)
+                if (tap_byte(tb[da][db], k) == me) d[k] += fd[k];
+            }
+        } else {
+          uint32_t acc[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+          for (int da = 0; da <= i; ++da)
+#pragma unroll
+            for (int db = 0; db <= j; ++db) {
+              const uint32_t me = static_cast<uint32_t>((i - 2 * da + 1) * 3 + (j - 2 * db + 1)) * 0x01010101u;
+              const uint32_t mlo = __vcmpeq4(tb[da][db].x, me), mhi = __vcmpeq4(tb[da][db].y, me);
+              const uint32_t wd[4] = {vd[da][db].x, vd[da][db].y, vd[da][db].z, vd[da][db].w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {  // byte mask of channels 2q, 2q+1 -> half-word mask
+                const uint32_t hm = __byte_perm(q < 2 ? mlo : mhi, 0u, (q & 1) ? 0x3322u : 0x1100u);
+                acc[q] = Pk<DT>::add(acc[q], wd[q] & hm);
+              }
+            }
+          Elem<DT>::unpack(make_uint4(acc[0], acc[1], acc[2], acc[3]), d);
+        }
         float fx[V];
         Elem<DT>::unpack(vx[i][j], fx);
 #pragma unroll
-        for (int k = 0; k < V; ++k) {
-          const float xh = (fx[k] - c_mu[k]) * c_is[k];
-          fx[k] = c_sc[k] * (d[k] - c_m1[k] - xh * c_m2[k]);
-        }
-        stg_stream(dx + in_chunk(g, p.n, 2 * p.ph + i, 2 * p.pw + j, chunk) * 16, Elem<DT>::pack(fx));
+        for (int k = 0; k < V; ++k) fx[k] = fmaf(gc.sc[k], d[k], fmaf(gc.ca[k], fx[k], gc.cb[k]));
+        stg_stream(dx + (xe + (i * g.W + j) * g.cvec) * 16, Elem<DT>::pack(fx));
       }
   }
 }
@@ -621,7 +692,7 @@ extern "C" int msf_bn2d_stats(const void* x, int64_t rows, int C, int dtype, dou
     bn_stats_kernel<DT><<<grid, kThreads, smem, st>>>(static_cast<const char*>(x), rows, l.cvec, l.ct, partial);
   });
   MSF_LAUNCH_OK("bn_stats_kernel");
-  bn_combine_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(partial, nblk, C, sums_out, static_cast<double>(rows));
+  bn_combine_kernel<<<(2 * C + kCombineWarps - 1) / kCombineWarps, kCombineWarps * 32, 0, st>>>(partial, nblk, C, sums_out, static_cast<double>(rows));
   MSF_LAUNCH_OK("bn_combine_kernel");
   return MSF_OK;
 }
@@ -657,11 +728,29 @@ extern "C" int msf_bn2d_apply(const void* x, const void* res, void* y, int64_t r
   return MSF_OK;
 }
 
+namespace {
+// the optional pooled-gradient term: gp (N, C) in the activation dtype, hw = rows per image
+int check_gp(const void* gp, int64_t hw, int64_t rows, int C, int dtype, const void* y_mask, int relu) {
+  if (!gp) return MSF_OK;
+  MSF_REQUIRE(aligned16(gp) && hw > 0 && rows % hw == 0, MSF_ERR_INVALID, "pooled gradient: rows=%lld is not a multiple of hw=%lld",
+              static_cast<long long>(rows), static_cast<long long>(hw));
+  MSF_REQUIRE(relu && y_mask, MSF_ERR_UNSUPPORTED, "the pooled-gradient term is implemented for the relu + saved-output-mask variant");
+  const int64_t chunks = rows * (C / (16 / static_cast<int>(dtype_size(dtype))));
+  MSF_REQUIRE(chunks < (int64_t{1} << 32), MSF_ERR_UNSUPPORTED, "pooled-gradient variant needs rows*C/vec < 2^32");
+  return MSF_OK;
+}
+}  // namespace
+
 extern "C" int msf_bn2d_bwd_reduce(const void* x, const void* dy, const void* y_mask, int64_t rows, int C, int dtype,
                                    const float* mean, const float* invstd, const float* gamma, const float* beta, int relu,
-                                   double* sums_out, void* workspace, size_t workspace_bytes, void* stream) {
+                                   const void* gpool, int64_t hw, double* sums_out, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
   if (int rc = check_bn(x, rows, C, dtype)) return rc;
   MSF_REQUIRE(dy && aligned16(dy) && aligned16(y_mask) && mean && invstd && sums_out, MSF_ERR_INVALID, "bad arguments");
+  if (int rc = check_gp(gpool, hw, rows, C, dtype, y_mask, relu)) return rc;
+  const char* gpp = static_cast<const char*>(gpool);
+  const unsigned hw32 = gpool ? static_cast<unsigned>(hw) : 1u;
+  const float gp_scale = gpool ? 1.f / static_cast<float>(hw) : 0.f;
   MSF_REQUIRE(workspace && workspace_bytes >= msf_bn2d_workspace_bytes(rows, C), MSF_ERR_WORKSPACE, "workspace too small");
   const int vec = 16 / static_cast<int>(dtype_size(dtype));
   const Layout l = make_layout(C, vec);
@@ -673,26 +762,31 @@ extern "C" int msf_bn2d_bwd_reduce(const void* x, const void* dy, const void* y_
   const char* mp = static_cast<const char*>(y_mask);
   int nblk = 1;
   ProfScope prof(stream, MSF_K_BN_BWD_REDUCE, static_cast<double>(rows) * C * dtype_size(dtype) * ((relu && y_mask) ? 3 : 2));
-#define MSF_BWD_REDUCE(MASK)                                                                                          \
+#define MSF_BWD_REDUCE(MASK, GP)                                                                                      \
   MSF_DISPATCH_DTYPE(dtype, {                                                                                         \
-    nblk = reduce_grid(bn_bwd_reduce_kernel<DT, MASK>, smem, l, rows, kReduceRows * l.rlanes);                        \
+    nblk = reduce_grid(bn_bwd_reduce_kernel<DT, MASK, GP>, smem, l, rows, kReduceRows * l.rlanes);                    \
     dim3 grid(static_cast<unsigned>(nblk), static_cast<unsigned>(l.cgroups));                                         \
-    bn_bwd_reduce_kernel<DT, MASK><<<grid, kThreads, smem, st>>>(xp, dp, mp, rows, l.cvec, l.ct, mean, invstd, gamma, beta, partial); \
+    bn_bwd_reduce_kernel<DT, MASK, GP><<<grid, kThreads, smem, st>>>(xp, dp, mp, rows, l.cvec, l.ct, mean, invstd, gamma, beta, gpp, \
+                                                                     hw32, gp_scale, partial);                       \
   })
-  if (!relu) { MSF_BWD_REDUCE(0); }
-  else if (!y_mask) { MSF_BWD_REDUCE(1); }
-  else { MSF_BWD_REDUCE(2); }
+  if (!relu) { MSF_BWD_REDUCE(0, false); }
+  else if (!y_mask) { MSF_BWD_REDUCE(1, false); }
+  else if (!gpool) { MSF_BWD_REDUCE(2, false); }
+  else { MSF_BWD_REDUCE(2, true); }
 #undef MSF_BWD_REDUCE
   MSF_LAUNCH_OK("bn_bwd_reduce_kernel");
-  bn_combine_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(partial, nblk, C, sums_out, -1.0);
+  bn_combine_kernel<<<(2 * C + kCombineWarps - 1) / kCombineWarps, kCombineWarps * 32, 0, st>>>(partial, nblk, C, sums_out, -1.0);
   MSF_LAUNCH_OK("bn_combine_kernel");
   return MSF_OK;
 }
 
 extern "C" int msf_bn2d_bwd_elemt(const void* x, const void* dy, const void* y_mask, void* dx, void* dres, int64_t rows, int C,
                                   int dtype, const float* mean, const float* invstd, const float* gamma, const float* beta,
-                                  int relu, const double* sums, const double* count, void* stream) {
+                                  int relu, const void* gpool, int64_t hw, const double* sums, const double* count, void* stream) {
   if (int rc = check_bn(x, rows, C, dtype)) return rc;
+  if (int rc = check_gp(gpool, hw, rows, C, dtype, y_mask, relu)) return rc;
+  const char* gpp = static_cast<const char*>(gpool);
+  const float gp_scale = gpool ? 1.f / static_cast<float>(hw) : 0.f;
   MSF_REQUIRE(dy && dx && aligned16(dy) && aligned16(dx) && aligned16(y_mask) && aligned16(dres) && mean && invstd && sums && count,
               MSF_ERR_INVALID, "bad arguments");
   const int vec = 16 / static_cast<int>(dtype_size(dtype));
@@ -706,15 +800,18 @@ extern "C" int msf_bn2d_bwd_elemt(const void* x, const void* dy, const void* y_m
   char* dxp = static_cast<char*>(dx);
   char* drp = static_cast<char*>(dres);
   ProfScope prof(stream, MSF_K_BN_BWD_ELEMT, static_cast<double>(rows) * C * dtype_size(dtype) * (3 + ((relu && y_mask) ? 1 : 0) + (dres ? 1 : 0)));
-#define MSF_BWD_ELEMT(MASK, DRES) \
-  MSF_DISPATCH_DTYPE(dtype, (bn_bwd_elemt_kernel<DT, MASK, DRES><<<grid, kThreads, 0, st>>>(xp, dp, mp, dxp, drp, chunks, cvec, mean, invstd, gamma, beta, sums, count)))
+  const unsigned hwc = gpool ? static_cast<unsigned>(hw * cvec) : 1u;
+#define MSF_BWD_ELEMT(MASK, DRES, GP) \
+  MSF_DISPATCH_DTYPE(dtype, (bn_bwd_elemt_kernel<DT, MASK, DRES, GP><<<grid, kThreads, 0, st>>>(xp, dp, mp, dxp, drp, chunks, cvec, mean, invstd, gamma, beta, sums, count, gpp, hwc, gp_scale)))
   const int mask = !relu ? 0 : (y_mask ? 2 : 1);
-  if (mask == 0 && !dres) { MSF_BWD_ELEMT(0, false); }
-  else if (mask == 0) { MSF_BWD_ELEMT(0, true); }
-  else if (mask == 1 && !dres) { MSF_BWD_ELEMT(1, false); }
-  else if (mask == 1) { MSF_BWD_ELEMT(1, true); }
-  else if (!dres) { MSF_BWD_ELEMT(2, false); }
-  else { MSF_BWD_ELEMT(2, true); }
+  if (mask == 0 && !dres) { MSF_BWD_ELEMT(0, false, false); }
+  else if (mask == 0) { MSF_BWD_ELEMT(0, true, false); }
+  else if (mask == 1 && !dres) { MSF_BWD_ELEMT(1, false, false); }
+  else if (mask == 1) { MSF_BWD_ELEMT(1, true, false); }
+  else if (!dres && !gpool) { MSF_BWD_ELEMT(2, false, false); }
+  else if (!gpool) { MSF_BWD_ELEMT(2, true, false); }
+  else if (!dres) { MSF_BWD_ELEMT(2, false, true); }
+  else { MSF_BWD_ELEMT(2, true, true); }
 #undef MSF_BWD_ELEMT
   MSF_LAUNCH_OK("bn_bwd_elemt_kernel");
   return MSF_OK;
@@ -736,42 +833,17 @@ int check_pool(const void* x, int64_t N, int H, int W, int C, int dtype, PoolGeo
 }
 }  // namespace
 
-extern "C" int msf_bn2d_apply_pool(const void* x, void* y, uint8_t* tap, int64_t N, int H, int W, int C, int dtype,
+extern "C" int msf_bn2d_apply_pool(const void* x, void* y, uint8_t* tap, void* x_arg, int64_t N, int H, int W, int C, int dtype,
                                    const float* mean, const float* invstd, const float* gamma, const float* beta, void* stream) {
   PoolGeom g;
   if (int rc = check_pool(x, N, H, W, C, dtype, &g)) return rc;
-  MSF_REQUIRE(y && tap && aligned16(y) && aligned16(tap) && mean && invstd, MSF_ERR_INVALID, "bad arguments");
+  MSF_REQUIRE(y && tap && x_arg && aligned16(y) && aligned16(tap) && aligned16(x_arg) && mean && invstd, MSF_ERR_INVALID, "bad arguments");
   const int64_t groups = (static_cast<int64_t>(g.windows) + kThreads / g.cpad - 1) / (kThreads / g.cpad);
-  ProfScope prof(stream, MSF_K_BN_APPLY_POOL, (static_cast<double>(N) * H * W + static_cast<double>(g.windows)) * C * dtype_size(dtype) + static_cast<double>(g.windows) * C);
+  // x read once; y, x_arg and one tap byte written per pooled element
+  ProfScope prof(stream, MSF_K_BN_APPLY_POOL, (static_cast<double>(N) * H * W + 2.0 * g.windows) * C * dtype_size(dtype) + static_cast<double>(g.windows) * C);
   MSF_DISPATCH_DTYPE(dtype, (bn_apply_pool_kernel<DT><<<resident_grid(bn_apply_pool_kernel<DT>, groups), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-                                static_cast<const char*>(x), static_cast<char*>(y), tap, g, mean, invstd, gamma, beta)));
+                                static_cast<const char*>(x), static_cast<char*>(y), tap, static_cast<char*>(x_arg), g, mean, invstd, gamma, beta)));
   MSF_LAUNCH_OK("bn_apply_pool_kernel");
-  return MSF_OK;
-}
-
-extern "C" int msf_bn2d_pool_bwd_reduce(const void* x, const void* dpool, const uint8_t* tap, int64_t N, int H, int W, int C,
-                                        int dtype, const float* mean, const float* invstd, double* sums_out, void* workspace,
-                                        size_t workspace_bytes, void* stream) {
-  PoolGeom g;
-  if (int rc = check_pool(x, N, H, W, C, dtype, &g)) return rc;
-  MSF_REQUIRE(dpool && tap && aligned16(dpool) && mean && invstd && sums_out, MSF_ERR_INVALID, "bad arguments");
-  MSF_REQUIRE(workspace && workspace_bytes >= msf_bn2d_workspace_bytes(g.windows, C), MSF_ERR_WORKSPACE, "workspace too small");
-  const int vec = 16 / static_cast<int>(dtype_size(dtype));
-  const Layout l = make_layout(C, vec);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t smem = static_cast<size_t>(kThreads) * 2 * vec * sizeof(float);
-  float* partial = static_cast<float*>(workspace);
-  int nblk = 1;
-  // x counted once (only arg-max positions are needed, at most the whole map), dpool + tap read
-  ProfScope prof(stream, MSF_K_BN_POOL_BWD_REDUCE, (static_cast<double>(N) * H * W + static_cast<double>(g.windows)) * C * dtype_size(dtype) + static_cast<double>(g.windows) * C);
-  MSF_DISPATCH_DTYPE(dtype, {
-    nblk = reduce_grid(bn_pool_bwd_reduce_kernel<DT>, smem, l, g.windows, l.rlanes);
-    dim3 grid(static_cast<unsigned>(nblk), static_cast<unsigned>(l.cgroups));
-    bn_pool_bwd_reduce_kernel<DT><<<grid, kThreads, smem, st>>>(static_cast<const char*>(x), static_cast<const char*>(dpool), tap, g, l.ct, mean, invstd, partial);
-  });
-  MSF_LAUNCH_OK("bn_pool_bwd_reduce_kernel");
-  bn_combine_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(partial, nblk, C, sums_out, -1.0);
-  MSF_LAUNCH_OK("bn_combine_kernel");
   return MSF_OK;
 }
 

@@ -357,12 +357,14 @@ class _BNAct2d(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, residual, running_mean, running_var, eps: float, momentum: float, relu: bool, pool: bool,
-                sync_group):
+                sync_group, want_mean: bool = False):
         L.require_cuda(x, weight, bias, residual)
         if x.dim() != 4:
             raise ValueError(f"bn_act2d: expected (N,C,H,W), got {tuple(x.shape)}")
         if pool and (residual is not None or not relu):
             raise ValueError("bn_act2d: the pooled variant is bn -> relu -> maxpool without a residual")
+        if want_mean and (pool or residual is None or not relu):
+            raise ValueError("bn_act2d: the spatial mean output is implemented for relu(bn(x) + residual) (a BasicBlock output)")
         x = _nhwc(x)
         N, Cc, H, W = x.shape
         dt, dev = x.dtype, x.device
@@ -382,12 +384,13 @@ class _BNAct2d(torch.autograd.Function):
         invstd = torch.empty(Cc, dtype=torch.float32, device=dev)
         L.check(lib.msf_bn2d_finalize(L.ptr(sums), Cc, eps, momentum, L.ptr(mean), L.ptr(invstd), L.ptr(running_mean), L.ptr(running_var), st),
                 "msf_bn2d_finalize")
-        tap = None
+        tap = x_arg = None
         if pool:
             PH, PW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
             y = torch.empty((N, Cc, PH, PW), dtype=dt, device=dev, memory_format=torch.channels_last)
             tap = torch.empty((N, PH, PW, Cc), dtype=torch.uint8, device=dev)
-            L.check(lib.msf_bn2d_apply_pool(L.ptr(x), L.ptr(y), L.ptr(tap), N, H, W, Cc, code, L.ptr(mean), L.ptr(invstd), L.ptr(gamma),
+            x_arg = torch.empty((N, PH, PW, Cc), dtype=dt, device=dev)
+            L.check(lib.msf_bn2d_apply_pool(L.ptr(x), L.ptr(y), L.ptr(tap), L.ptr(x_arg), N, H, W, Cc, code, L.ptr(mean), L.ptr(invstd), L.ptr(gamma),
                                             L.ptr(beta), st), "msf_bn2d_apply_pool")
         else:
             res = None
@@ -400,18 +403,28 @@ class _BNAct2d(torch.autograd.Function):
                                        int(relu), st), "msf_bn2d_apply")
         L.launch_count += 4
         # with a residual the ReLU mask of the backward comes from the output (no extra memory: the next layer keeps it anyway)
-        y_mask = y if (residual is not None and relu) else None
-        ctx.save_for_backward(x, gamma, beta, mean, invstd, sums, y_mask, tap)
+        y_mask = y if ((residual is not None and relu) or pool) else None
+        ctx.save_for_backward(x, gamma, beta, mean, invstd, sums, y_mask, tap, x_arg)
         ctx.meta = (N, Cc, H, W, code, relu, pool, residual is not None, sync_group, world,
-                    None if weight is None else weight.dtype, None if bias is None else bias.dtype)
+                    None if weight is None else weight.dtype, None if bias is None else bias.dtype, want_mean)
+        if want_mean:
+            # global average pool of the block output (src/models/resnet.py:250-254); its backward is folded into the
+            # batch-norm backward kernels below instead of being expanded and added to the main gradient by ATen
+            return y, y.mean(dim=(2, 3))
         return y
 
     @staticmethod
-    def backward(ctx, gy):
-        x, gamma, beta, mean, invstd, sums_fwd, y_mask, tap = ctx.saved_tensors
-        N, Cc, H, W, code, relu, pool, has_res, group, world, wdt, bdt = ctx.meta
+    def backward(ctx, gy, gmean=None):
+        x, gamma, beta, mean, invstd, sums_fwd, y_mask, tap, x_arg = ctx.saved_tensors
+        N, Cc, H, W, code, relu, pool, has_res, group, world, wdt, bdt, want_mean = ctx.meta
         dev = x.device
+        if gy is None:  # only the pooled branch carries gradient
+            gy = torch.zeros_like(x, memory_format=torch.channels_last)
         gy = _nhwc(gy if gy.dtype == x.dtype else gy.to(x.dtype))
+        gp = None
+        if want_mean and gmean is not None:
+            gp = _contig(gmean if gmean.dtype == x.dtype else gmean.to(x.dtype))
+        hw = H * W
         lib, st = L.lib(), L.stream_ptr()
         rows = N * H * W
         sums = torch.empty(2 * Cc, dtype=torch.float64, device=dev)
@@ -422,13 +435,14 @@ class _BNAct2d(torch.autograd.Function):
             PH, PW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
             ws_bytes = lib.msf_bn2d_workspace_bytes(N * PH * PW, Cc)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            L.check(lib.msf_bn2d_pool_bwd_reduce(L.ptr(x), L.ptr(gy), L.ptr(tap), N, H, W, Cc, code, L.ptr(mean), L.ptr(invstd), L.ptr(sums),
-                                                 L.ptr(ws), ws_bytes, st), "msf_bn2d_pool_bwd_reduce")
+            # dy' lives on the pooled grid: reduce over (x at the arg-max, pooled gradient, pooled output as ReLU mask)
+            L.check(lib.msf_bn2d_bwd_reduce(L.ptr(x_arg), L.ptr(gy), L.ptr(y_mask), N * PH * PW, Cc, code, L.ptr(mean), L.ptr(invstd),
+                                            L.ptr(gamma), L.ptr(beta), 1, None, 0, L.ptr(sums), L.ptr(ws), ws_bytes, st), "msf_bn2d_bwd_reduce")
         else:
             ws_bytes = lib.msf_bn2d_workspace_bytes(rows, Cc)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             L.check(lib.msf_bn2d_bwd_reduce(L.ptr(x), L.ptr(gy), L.ptr(y_mask), rows, Cc, code, L.ptr(mean), L.ptr(invstd), L.ptr(gamma),
-                                            L.ptr(beta), int(relu), L.ptr(sums), L.ptr(ws), ws_bytes, st), "msf_bn2d_bwd_reduce")
+                                            L.ptr(beta), int(relu), L.ptr(gp), hw, L.ptr(sums), L.ptr(ws), ws_bytes, st), "msf_bn2d_bwd_reduce")
         # parameter gradients are the LOCAL sums (DDP averages them over ranks, as with SyncBatchNorm)
         gw = None if wdt is None else sums[Cc:].to(wdt)
         gb = None if bdt is None else sums[:Cc].to(bdt)
@@ -441,20 +455,22 @@ class _BNAct2d(torch.autograd.Function):
             if has_res and ctx.needs_input_grad[3]:
                 dres = torch.empty_like(x, memory_format=torch.channels_last)
             L.check(lib.msf_bn2d_bwd_elemt(L.ptr(x), L.ptr(gy), L.ptr(y_mask), L.ptr(dx), L.ptr(dres), rows, Cc, code, L.ptr(mean),
-                                           L.ptr(invstd), L.ptr(gamma), L.ptr(beta), int(relu), L.ptr(sums), count_ptr, st),
+                                           L.ptr(invstd), L.ptr(gamma), L.ptr(beta), int(relu), L.ptr(gp), hw, L.ptr(sums), count_ptr, st),
                     "msf_bn2d_bwd_elemt")
         L.launch_count += 3
-        return dx, gw, gb, dres, None, None, None, None, None, None, None
+        return dx, gw, gb, dres, None, None, None, None, None, None, None, None
 
 
 def bn_act2d(x: torch.Tensor, weight: Optional[torch.Tensor], bias: Optional[torch.Tensor], running_mean: Optional[torch.Tensor],
              running_var: Optional[torch.Tensor], eps: float = 1e-5, momentum: float = 0.1, relu: bool = False,
-             residual: Optional[torch.Tensor] = None, pool: bool = False, sync_group=None) -> torch.Tensor:
+             residual: Optional[torch.Tensor] = None, pool: bool = False, sync_group=None, want_mean: bool = False):
     """Train-mode ``[maxpool3x3/2](relu?(batch_norm(x) (+ residual)))`` on channels-last CUDA tensors.  Statistics are
     biased batch statistics (all-reduced over ``sync_group`` when given); ``running_*`` receive the momentum update with
-    the unbiased variance.  x (N,C,H,W) in NHWC memory order (converted if not)."""
+    the unbiased variance.  x (N,C,H,W) in NHWC memory order (converted if not).  ``want_mean=True`` additionally
+    returns the spatial mean (N,C) of the output (the encoder's pooled pyramid feature), whose gradient is folded into
+    the batch-norm backward kernels."""
     return _BNAct2d.apply(x, weight, bias, residual, running_mean, running_var, float(eps), float(momentum), bool(relu), bool(pool),
-                          sync_group)
+                          sync_group, bool(want_mean))
 
 
 # ------------------------------------------------------------------------------------------

@@ -42,15 +42,21 @@ class FusedBatchNorm2d(nn.Module):
     def extra_repr(self):
         return f"{self.num_features}, eps={self.eps}, momentum={self.momentum}, act={self.act}"
 
-    def forward(self, x, residual=None):
+    def forward(self, x, residual=None, want_mean=False):
+        """``want_mean=True`` returns ``(out, out.mean((2, 3)))``: the spatial mean rides along so that its gradient is
+        folded into the fused backward (only for the relu(bn(x) + residual) form)."""
         if self.training and x.is_cuda:
             import torch.distributed as dist
             from . import ops
             sync = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
             self.num_batches_tracked.add_(1)
-            return ops.bn_act2d(x, self.weight, self.bias, self.running_mean, self.running_var, self.eps, self.momentum,
-                                relu=self.act != "none", residual=residual, pool=self.act == "relu_pool",
-                                sync_group=dist.group.WORLD if sync else None)
+            fused_mean = want_mean and residual is not None and self.act == "relu"
+            out = ops.bn_act2d(x, self.weight, self.bias, self.running_mean, self.running_var, self.eps, self.momentum,
+                               relu=self.act != "none", residual=residual, pool=self.act == "relu_pool",
+                               sync_group=dist.group.WORLD if sync else None, want_mean=fused_mean)
+            if want_mean and not fused_mean:
+                return out, out.mean(dim=(2, 3))
+            return out
         if self.training:
             self.num_batches_tracked.add_(1)
         out = nn.functional.batch_norm(x, self.running_mean, self.running_var, self.weight, self.bias, self.training, self.momentum, self.eps)
@@ -60,7 +66,7 @@ class FusedBatchNorm2d(nn.Module):
             out = nn.functional.relu(out)
         if self.act == "relu_pool":
             out = nn.functional.max_pool2d(out, 3, 2, 1)
-        return out
+        return (out, out.mean(dim=(2, 3))) if want_mean else out
 
 
 class BasicBlock(nn.Module):
@@ -75,10 +81,10 @@ class BasicBlock(nn.Module):
         self.bn2 = FusedBatchNorm2d(planes, act="relu")
         self.downsample = downsample
 
-    def forward(self, x):
+    def forward(self, x, want_mean=False):
         idt = x if self.downsample is None else self.downsample(x)
-        out = self.bn1(self.conv1(x))            # relu(bn1(conv1 x))
-        return self.bn2(self.conv2(out), idt)    # relu(bn2(conv2 out) + identity)
+        out = self.bn1(self.conv1(x))                       # relu(bn1(conv1 x))
+        return self.bn2(self.conv2(out), idt, want_mean)    # relu(bn2(conv2 out) + identity) [, its spatial mean]
 
 
 class ResNet(nn.Module):
@@ -118,15 +124,18 @@ class ResNet(nn.Module):
 
     def forward(self, x):
         x = self.bn1(self.conv1(x))
-        x1 = self.layer1(x)
-        x2 = self.layer2(x1)
-        x3 = self.layer3(x2)
-        x4 = self.layer4(x3)
-        out = self.fc(torch.flatten(self.avgpool(x4), 1))
+        # the global average pool of each layer's output (src/models/resnet.py:244-254) is produced by the layer's last
+        # block together with the feature map, so the fused backward sees both gradients at once
+        pooled = []
+        for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
+            for blk in layer[:-1]:
+                x = blk(x)
+            x, m = layer[-1](x, want_mean=True)
+            pooled.append(m)
+        out = self.fc(pooled[3])
         if not self.return_features:
             return out
-        pooled = tuple(torch.flatten(self.avgpool(t), 1) for t in (x1, x2, x3))
-        return (*pooled, out)
+        return (*pooled[:3], out)
 
 
 def _build(layers, pretrained, **kw):

@@ -92,6 +92,40 @@ def test_stem_bn_relu_pool_vs_torch(dtype, shape):
     assert _cos(w.grad, wr.grad) >= 0.9999 and _cos(b.grad, br.grad) >= 0.9999
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(5, 64, 7, 7), (3, 128, 14, 14), (40, 64, 56, 56)])
+def test_block_output_with_folded_average_pool_gradient(dtype, shape):
+    """relu(bn(x) + identity) with its global average pool as a second output: the pooled branch's gradient is folded
+    into the batch-norm backward kernels (src/models/resnet.py:250-254 pools every layer output)."""
+    g = torch.Generator(device=DEV).manual_seed(sum(shape) + 7)
+    mk = lambda: torch.randn(shape, device=DEV, generator=g).to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    x, r = mk(), mk()
+    w = torch.empty(shape[1], device=DEV).uniform_(0.5, 1.5, generator=g).requires_grad_(True)
+    b = torch.empty(shape[1], device=DEV).uniform_(-0.5, 0.5, generator=g).requires_grad_(True)
+    y, m = ops.bn_act2d(x, w, b, None, None, 1e-5, 0.1, relu=True, residual=r, want_mean=True)
+    assert m.shape == shape[:2]
+    gy = torch.randn(shape, device=DEV, generator=g).to(dtype).contiguous(memory_format=torch.channels_last)
+    gm = (torch.randn(shape[:2], device=DEV, generator=g) * shape[2] * shape[3] ** 0.5).to(dtype)  # comparable magnitude per pixel
+    torch.autograd.backward([y, m], [gy, gm])
+    xr, wr, br, rr, yr, _, _ = _ref(x, w, b, r, True, False)
+    mr = yr.mean(dim=(2, 3))
+    torch.autograd.backward([yr, mr], [gy.double(), gm.double()])
+    tol = 2e-5 if dtype == torch.float32 else 2 ** -7
+    assert torch.allclose(m.double(), mr, rtol=tol, atol=tol)
+    if dtype == torch.float32:
+        assert (x.grad.double() - xr.grad).norm() / xr.grad.norm() <= 1e-4
+        assert (r.grad.double() - rr.grad).norm() / rr.grad.norm() <= 1e-4
+    assert _cos(x.grad, xr.grad) >= 0.9999 and _cos(r.grad, rr.grad) >= 0.9999
+    assert _cos(w.grad, wr.grad) >= 0.9999 and _cos(b.grad, br.grad) >= 0.9999
+    # pooled branch alone (no gradient on the feature map)
+    x2, r2 = x.detach().clone().requires_grad_(True), r.detach().clone().requires_grad_(True)
+    _, m2 = ops.bn_act2d(x2, w, b, None, None, 1e-5, 0.1, relu=True, residual=r2, want_mean=True)
+    m2.backward(gm)
+    xr2, _, _, rr2, yr2, _, _ = _ref(x, w, b, r, True, False)
+    yr2.mean(dim=(2, 3)).backward(gm.double())
+    assert _cos(x2.grad, xr2.grad) >= 0.9999 and _cos(r2.grad, rr2.grad) >= 0.9999
+
+
 def test_stem_pool_tie_rule_matches_aten_bf16():
     """Same dtype, same unfused op order on ATen: with bf16 storage the arg-max ties must resolve like max_pool2d
     (first maximum in scan order), so the input gradients agree to bf16 rounding."""
@@ -152,13 +186,14 @@ def test_resnet18_encoder_matches_plain_torch_resnet():
             self.bn.load_state_dict(f.state_dict())
             self.act = f.act
 
-        def forward(self, x, residual=None):
+        def forward(self, x, residual=None, want_mean=False):
             y = self.bn(x)
             if residual is not None:
                 y = y + residual
             if self.act != "none":
                 y = F.relu(y)
-            return F.max_pool2d(y, 3, 2, 1) if self.act == "relu_pool" else y
+            y = F.max_pool2d(y, 3, 2, 1) if self.act == "relu_pool" else y
+            return (y, y.mean(dim=(2, 3))) if want_mean else y
 
     ref = copy.deepcopy(enc)
     for name, m in list(ref.named_modules()):

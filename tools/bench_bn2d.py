@@ -18,7 +18,14 @@ from msfwsi_b200 import _lib as L  # noqa: E402
 dev = "cuda:0"
 
 
+ONCE = False
+
+
 def timeit(fn, iters=10):
+    if ONCE:  # ncu capture mode: one launch per kernel
+        fn()
+        torch.cuda.synchronize()
+        return 1.0
     for _ in range(3):
         fn()
     ts = []
@@ -37,7 +44,12 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
     ap.add_argument("--aten", action="store_true", help="also time ATen's kernels for the same work")
+    ap.add_argument("--once", action="store_true", help="launch every kernel exactly once (for an ncu capture)")
+    ap.add_argument("--stem-n", type=int, default=2048)
+    ap.add_argument("--only", default=None, help="comma-separated shape tags (stem,layer1,...)")
     args = ap.parse_args()
+    global ONCE
+    ONCE = args.once
     try:
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
@@ -51,8 +63,10 @@ def main():
         print(json.dumps(r), flush=True)
 
     dt, code, e = torch.bfloat16, L.MSF_BF16, 2
-    for (N, C, H, W, tag) in ((2048, 64, 112, 112, "stem"), (4096, 64, 56, 56, "layer1"), (4096, 128, 28, 28, "layer2"),
+    for (N, C, H, W, tag) in ((args.stem_n, 64, 112, 112, "stem"), (4096, 64, 56, 56, "layer1"), (4096, 128, 28, 28, "layer2"),
                               (4096, 256, 14, 14, "layer3"), (4096, 512, 7, 7, "layer4")):
+        if args.only and tag not in args.only.split(","):
+            continue
         x = torch.randn(N, H, W, C, device=dev).to(dt)
         dy = torch.randn(N, H, W, C, device=dev).to(dt)
         y, dx = torch.empty_like(x), torch.empty_like(x)
@@ -72,10 +86,10 @@ def main():
                                                      gamma.data_ptr(), beta.data_ptr(), 1, st), "apply")
         rec("bn_apply+relu", 2 * nb, timeit(f_apply), shape)
         f_red = lambda: L.check(lib.msf_bn2d_bwd_reduce(x.data_ptr(), dy.data_ptr(), None, rows_, C, code, mean.data_ptr(), invstd.data_ptr(),
-                                                        gamma.data_ptr(), beta.data_ptr(), 1, sums2.data_ptr(), ws.data_ptr(), wsb, st), "red")
+                                                        gamma.data_ptr(), beta.data_ptr(), 1, None, 0, sums2.data_ptr(), ws.data_ptr(), wsb, st), "red")
         rec("bn_bwd_reduce (relu mask recomputed)", 2 * nb, timeit(f_red), shape)
         f_el = lambda: L.check(lib.msf_bn2d_bwd_elemt(x.data_ptr(), dy.data_ptr(), None, dx.data_ptr(), None, rows_, C, code, mean.data_ptr(),
-                                                      invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1, sums2.data_ptr(), cnt, st), "el")
+                                                      invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1, None, 0, sums2.data_ptr(), cnt, st), "el")
         rec("bn_bwd_elemt (relu mask recomputed)", 3 * nb, timeit(f_el), shape)
         if tag != "stem":
             res, dres = torch.randn_like(x), torch.empty_like(x)
@@ -83,11 +97,11 @@ def main():
                                                            invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1, st), "apply")
             rec("bn_apply+residual+relu", 3 * nb, timeit(f_apply_r), shape)
             f_red_r = lambda: L.check(lib.msf_bn2d_bwd_reduce(x.data_ptr(), dy.data_ptr(), y.data_ptr(), rows_, C, code, mean.data_ptr(),
-                                                              invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1, sums2.data_ptr(), ws.data_ptr(),
+                                                              invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1, None, 0, sums2.data_ptr(), ws.data_ptr(),
                                                               wsb, st), "red")
             rec("bn_bwd_reduce (mask from y)", 3 * nb, timeit(f_red_r), shape)
             f_el_r = lambda: L.check(lib.msf_bn2d_bwd_elemt(x.data_ptr(), dy.data_ptr(), y.data_ptr(), dx.data_ptr(), dres.data_ptr(), rows_, C, code,
-                                                            mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1, sums2.data_ptr(),
+                                                            mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1, None, 0, sums2.data_ptr(),
                                                             cnt, st), "el")
             rec("bn_bwd_elemt (mask from y, + dres)", 5 * nb, timeit(f_el_r), shape)
             del res, dres
@@ -99,16 +113,18 @@ def main():
             npool = yp.numel()
             wsb2 = lib.msf_bn2d_workspace_bytes(N * PH * PW, C)
             ws2 = torch.empty(wsb2, dtype=torch.uint8, device=dev)
-            f_ap = lambda: L.check(lib.msf_bn2d_apply_pool(x.data_ptr(), yp.data_ptr(), tap.data_ptr(), N, H, W, C, code, mean.data_ptr(),
-                                                           invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), st), "apply_pool")
-            rec("bn_apply+relu+maxpool", nb + npool * (e + 1), timeit(f_ap), shape)
-            f_pr = lambda: L.check(lib.msf_bn2d_pool_bwd_reduce(x.data_ptr(), dp.data_ptr(), tap.data_ptr(), N, H, W, C, code, mean.data_ptr(),
-                                                                invstd.data_ptr(), sums2.data_ptr(), ws2.data_ptr(), wsb2, st), "pool_red")
-            rec("bn_pool_bwd_reduce", nb + npool * (e + 1), timeit(f_pr), shape + " (x counted once: only arg-max positions are needed)")
+            xarg = torch.empty(N, PH, PW, C, device=dev, dtype=dt)
+            f_ap = lambda: L.check(lib.msf_bn2d_apply_pool(x.data_ptr(), yp.data_ptr(), tap.data_ptr(), xarg.data_ptr(), N, H, W, C, code,
+                                                           mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), st), "apply_pool")
+            rec("bn_apply+relu+maxpool", nb + npool * (2 * e + 1), timeit(f_ap), shape)
+            f_pr = lambda: L.check(lib.msf_bn2d_bwd_reduce(xarg.data_ptr(), dp.data_ptr(), yp.data_ptr(), N * PH * PW, C, code, mean.data_ptr(),
+                                                           invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1, None, 0, sums2.data_ptr(), ws2.data_ptr(),
+                                                           wsb2, st), "pool_red")
+            rec("bn_bwd_reduce on the pooled grid (x_arg, dpool, y)", 3 * npool * e, timeit(f_pr), shape)
             f_pe = lambda: L.check(lib.msf_bn2d_pool_bwd_elemt(x.data_ptr(), dp.data_ptr(), tap.data_ptr(), dx.data_ptr(), N, H, W, C, code,
                                                                mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(), sums2.data_ptr(), cnt, st), "pool_el")
             rec("bn_pool_bwd_elemt", 2 * nb + npool * (e + 1), timeit(f_pe), shape)
-            del yp, tap, dp
+            del yp, tap, dp, xarg
         if args.aten:
             xa = x.permute(0, 3, 1, 2)  # NCHW view of the NHWC buffer = channels_last
             dya = dy.permute(0, 3, 1, 2)
