@@ -96,12 +96,14 @@ __global__ void __launch_bounds__(kThreads) bn_stats_kernel(const char* __restri
   float s[V], q[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) s[i] = q[i] = 0.f;
-  const int64_t step = static_cast<int64_t>(gridDim.x) * U * rlanes;
-  for (int64_t r = static_cast<int64_t>(blockIdx.x) * U * rlanes + rl; r < rows; r += step) {
+  // the U rows a thread has in flight are a whole grid sweep apart (gridDim.x * rlanes rows): every sweep is one
+  // contiguous window of memory read by all CTAs together
+  const int64_t sweep = static_cast<int64_t>(gridDim.x) * rlanes;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * rlanes + rl; r < rows; r += U * sweep) {
     uint4 v[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t rr = r + u * rlanes;
+      const int64_t rr = r + u * sweep;
       v[u] = make_uint4(0, 0, 0, 0);
       if (rr < rows) v[u] = ldg_stream(x + (rr * cvec + chunk) * 16);
     }
@@ -227,6 +229,8 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const char* __r
     is[i] = invstd[chunk * V + i];
     s[i] = q[i] = 0.f;
   }
+  // (two or three streams already spread the requests; adjacent row groups measured faster here than the grid-sweep
+  // spacing bn_stats_kernel uses)
   const int64_t step = static_cast<int64_t>(gridDim.x) * U * rlanes;
   for (int64_t r = static_cast<int64_t>(blockIdx.x) * U * rlanes + rl; r < rows; r += step) {
     uint4 a[U], b[U], m[U], p[U];

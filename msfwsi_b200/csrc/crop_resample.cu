@@ -228,6 +228,105 @@ __global__ void __launch_bounds__(kFastThreads) crop_fwd_fast_kernel(const void*
   }
 }
 
+// ---- strip path: one thread per (plane, 16-byte output strip), walking down the output rows ----------------------
+// CTA = one box (b,k) x (256 / strips) consecutive channels, strips = ow / VEC (power of two).  A thread owns the VEC
+// consecutive output columns of its strip and keeps the horizontally interpolated values of the two source rows the
+// current output row blends (h_top, h_bot) in registers: a source row is interpolated along x once and reused by all the
+// output rows that read it (`zoom` of them), every output row costs one vertical blend + one 128-bit store.  No shared
+// memory traffic on the row path, no warp synchronisation; the row taps (shared by the whole box) sit in shared memory.
+// Weights equal to zero short-circuit, so an integer box of the output size is a bit-exact copy (and takes a pure
+// 128-bit copy loop when the source is 16-byte aligned).
+template <int DT>
+__global__ void __launch_bounds__(256) crop_fwd_strip_kernel(const void* __restrict__ feat, const float* __restrict__ boxes,
+                                                             void* __restrict__ out, Geo g, int strips) {
+  constexpr int VEC = Elem<DT>::VEC;
+  constexpr int ES = 16 / VEC;
+  extern __shared__ __align__(16) float sm[];
+  int* y_i0 = reinterpret_cast<int*>(sm);
+  int* y_i1 = y_i0 + g.oh;
+  float* y_w = reinterpret_cast<float*>(y_i1 + g.oh);
+  const int planes_cta = 256 / strips;
+  const int groups_c = (g.C + planes_cta - 1) / planes_cta;
+  const int64_t bk = blockIdx.x / groups_c;
+  const int c = static_cast<int>(blockIdx.x % groups_c) * planes_cta + static_cast<int>(threadIdx.x) / strips;
+  const int sx = static_cast<int>(threadIdx.x) % strips;
+  const int64_t b = bk / g.K;
+  const float4 bx = __ldg(reinterpret_cast<const float4*>(boxes) + bk);  // y0,x0,y1,x1
+  for (int o = threadIdx.x; o < g.oh; o += 256) axis_taps(bx.x, bx.z - bx.x, o, g.oh, g.H, y_i0[o], y_i1[o], y_w[o]);
+  __syncthreads();
+  if (c >= g.C) return;
+  const char* src = static_cast<const char*>(feat) + (b * g.C + c) * static_cast<int64_t>(g.H) * g.W * ES;
+  char* dst = static_cast<char*>(out) + ((bk * g.C + c) * static_cast<int64_t>(g.oh) * g.ow + sx * VEC) * ES;
+  const int64_t src_pitch = static_cast<int64_t>(g.W) * ES, dst_pitch = static_cast<int64_t>(g.ow) * ES;
+
+  const bool is_copy = bx.x == floorf(bx.x) && bx.y == floorf(bx.y) && bx.z - bx.x == static_cast<float>(g.oh) &&
+                       bx.w - bx.y == static_cast<float>(g.ow) && bx.x >= 0.f && bx.y >= 0.f &&
+                       bx.z <= static_cast<float>(g.H) && bx.w <= static_cast<float>(g.W);
+  if (is_copy) {
+    const char* sp = src + (static_cast<int64_t>(bx.x) * g.W + static_cast<int64_t>(bx.y) + sx * VEC) * ES;
+    if (((reinterpret_cast<uintptr_t>(sp) | static_cast<uintptr_t>(src_pitch)) & 15u) == 0) {
+      int oy = 0;
+      for (; oy + 4 <= g.oh; oy += 4) {  // four independent 128-bit loads in flight
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ldg_stream(sp + (oy + u) * src_pitch);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) stg_stream(dst + (oy + u) * dst_pitch, v[u]);
+      }
+      for (; oy < g.oh; ++oy) stg_stream(dst + oy * dst_pitch, ldg_stream(sp + oy * src_pitch));
+      return;
+    }
+  }
+
+  int xa[VEC], xb[VEC];
+  float xw[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) axis_taps(bx.y, bx.w - bx.y, sx * VEC + v, g.ow, g.W, xa[v], xb[v], xw[v]);
+  auto hpass = [&](int y, float* h) {
+    const char* row = src + static_cast<int64_t>(y) * src_pitch;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const float a = ld1<DT>(row, xa[v]);
+      h[v] = xw[v] == 0.f ? a : fmaf(ld1<DT>(row, xb[v]), xw[v], a * (1.f - xw[v]));
+    }
+  };
+  float h_top[VEC], h_bot[VEC];
+  int cur0 = -1, cur1 = -1;  // source rows held in h_top / h_bot
+  for (int oy = 0; oy < g.oh; ++oy) {
+    const int i0 = y_i0[oy], i1 = y_i1[oy];
+    const float wy = y_w[oy];
+    if (i0 != cur0) {
+      if (i0 == cur1) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) h_top[v] = h_bot[v];
+      } else {
+        hpass(i0, h_top);
+      }
+      cur0 = i0;
+    }
+    float res[VEC];
+    if (wy != 0.f) {
+      if (i1 != cur1) {
+        hpass(i1, h_bot);
+        cur1 = i1;
+      }
+      // packed fp32x2 multiply / fma: same roundings as the scalar fmaf(h_bot, wy, h_top * om), half the issue slots
+      const float2 wy2 = make_float2(wy, wy), om2 = make_float2(1.f - wy, 1.f - wy);
+#pragma unroll
+      for (int v = 0; v < VEC; v += 2) {
+        const float2 t = __fmul2_rn(make_float2(h_top[v], h_top[v + 1]), om2);
+        const float2 r = __ffma2_rn(make_float2(h_bot[v], h_bot[v + 1]), wy2, t);
+        res[v] = r.x;
+        res[v + 1] = r.y;
+      }
+    } else {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) res[v] = h_top[v];
+    }
+    stg_stream(dst + oy * dst_pitch, Elem<DT>::pack(res));
+  }
+}
+
 template <int DT>
 __global__ void __launch_bounds__(256) crop_bwd_kernel(const void* __restrict__ gout, const float* __restrict__ boxes,
                                                        float* __restrict__ gfeat, Geo g, int64_t total) {
@@ -291,7 +390,15 @@ extern "C" int msf_crop_resample_fwd(const void* feat, int64_t B, int C, int H, 
   ProfScope prof(stream, MSF_K_CROP_FWD, (static_cast<double>(B) * C * H * W + static_cast<double>(rows) * ow) * dtype_size(dtype) + 16.0 * B * K);
   const bool fast_ok = vec_ok && ow % 32 == 0 && ow <= 32 * kMaxOxPerLane && owv <= 32 && (owv & (owv - 1)) == 0 &&
                        fast_smem <= 48 * 1024 && B * K < (1ll << 24);
-  if (fast_ok) {
+  // strip path: ow/vec strips per plane (power of two <= 256); the row taps of one box fit shared memory
+  const bool strip_ok = vec_ok && owv >= 1 && owv <= 256 && (owv & (owv - 1)) == 0 && oh <= 4000 &&
+                        B * K * static_cast<int64_t>((C + 256 / owv - 1) / (256 / owv)) < (1ll << 31);
+  if (strip_ok) {
+    const int planes_cta = 256 / owv;
+    const int64_t ctas = B * K * ((C + planes_cta - 1) / planes_cta);
+    const size_t smem = static_cast<size_t>(3) * oh * 4;
+    MSF_DISPATCH_DTYPE(dtype, (crop_fwd_strip_kernel<DT><<<static_cast<unsigned>(ctas), 256, smem, st>>>(feat, boxes, out, g, owv)));
+  } else if (fast_ok) {
     const int64_t ctas = B * K * ((C + 7) / 8);
     MSF_DISPATCH_DTYPE(dtype, (crop_fwd_fast_kernel<DT><<<static_cast<unsigned>(ctas), kFastThreads, fast_smem, st>>>(feat, boxes, out, g, kroll)));
   } else if (vec_ok) {
