@@ -203,10 +203,13 @@ int msf_ema_multi(const msf_ema_entry* entries /*device*/, const int32_t* chunk_
                   void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * N1  channels-last train-mode BatchNorm2d of the encoders with the element-wise work around it fused in
- * (caller side of the hot path: src/models/resnet.py:59-82 BasicBlock `bn -> relu`, `bn -> (+identity) -> relu`,
- * and the stem `bn1 -> relu -> maxpool` of src/models/resnet.py:244-247; statistics follow
- * torch.nn.BatchNorm2d / SyncBatchNorm, tools/ssl_train.py:160).  The convolutions stay on cuDNN.
+ * N1  train-mode batch normalisation over [rows][C] matrices with the element-wise work around it fused in:
+ * the BatchNorm1d + ReLU of the projector / predictor heads (src/models/backbone.py:15-16,18-19,21,28-29; rows = batch rows)
+ * and the channels-last BatchNorm2d of the encoders (caller side of the hot path: src/models/resnet.py:59-82 BasicBlock
+ * `bn -> relu`, `bn -> (+identity) -> relu`, and the stem `bn1 -> relu -> maxpool` of src/models/resnet.py:244-247;
+ * rows = N*H*W).  Statistics follow torch.nn.BatchNorm{1,2}d / SyncBatchNorm (tools/ssl_train.py:160): one sum-reducible
+ * fp64 vector per layer and direction instead of SyncBatchNorm's all_gather + per-rank recombination.  The convolutions
+ * and Linears stay on cuDNN / the tcgen05 GEMM.
  * The activation is a [rows = N*H*W][C] matrix, C contiguous (NHWC), C a multiple of 8 (16-bit) or 4 (fp32).
  *
  * forward : msf_bn2d_stats -> (all-reduce `sums` over ranks for SyncBN) -> msf_bn2d_finalize -> msf_bn2d_apply[_pool]
@@ -219,6 +222,11 @@ int msf_ema_multi(const msf_ema_entry* entries /*device*/, const int32_t* chunk_
 size_t msf_bn2d_workspace_bytes(int64_t rows, int C);
 int msf_bn2d_stats(const void* x, int64_t rows, int C, int dtype, double* sums_out /*2C+1*/, void* workspace,
                    size_t workspace_bytes, void* stream);
+/* Single-process forward: msf_bn2d_stats and msf_bn2d_finalize in two launches instead of three (no cross-rank reduction
+ * in between); sums_out still receives the 2C+1 doubles the backward needs. */
+int msf_bn2d_stats_finalize(const void* x, int64_t rows, int C, int dtype, float eps, float momentum, double* sums_out /*2C+1*/,
+                            float* mean, float* invstd, float* running_mean, float* running_var, void* workspace,
+                            size_t workspace_bytes, void* stream);
 /* mean / invstd (fp32, C each) from sums; running_mean / running_var (both or neither) get the momentum update with
  * the unbiased variance, like torch.nn.BatchNorm2d. */
 int msf_bn2d_finalize(const double* sums /*2C+1*/, int C, float eps, float momentum, float* mean, float* invstd,

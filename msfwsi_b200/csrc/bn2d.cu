@@ -86,41 +86,125 @@ __device__ __forceinline__ void cta_reduce_store(const float* s, const float* q,
 }
 
 constexpr int kStatsRows = 8;  // rows in flight per thread
+// Shifted sums: every CTA accumulates d = x - K with K = its first row (per channel), so sum d^2 - (sum d)^2/n does not
+// cancel when |mean| >> std.  partial layout [blk][3][C] = {sum d, sum d^2, K}, followed by cnt[blk] (rows of the block).
 template <int DT>
 __global__ void __launch_bounds__(kThreads) bn_stats_kernel(const char* __restrict__ x, int64_t rows, int cvec, int ct,
-                                                            float* __restrict__ partial) {
+                                                            float* __restrict__ partial, float* __restrict__ cnt) {
   constexpr int V = Elem<DT>::VEC;
   constexpr int U = kStatsRows;
+  extern __shared__ float sm[];
   const int cl = threadIdx.x % ct, rl = threadIdx.x / ct, rlanes = kThreads / ct;
   const int chunk = blockIdx.y * ct + cl;
-  float s[V], q[V];
+  const int C = cvec * V;
+  const int64_t first = static_cast<int64_t>(blockIdx.x) * rlanes;  // first row of this CTA
+  float kshift[V], s[V], q[V];
 #pragma unroll
-  for (int i = 0; i < V; ++i) s[i] = q[i] = 0.f;
+  for (int i = 0; i < V; ++i) kshift[i] = s[i] = q[i] = 0.f;
+  if (first < rows) Elem<DT>::unpack(ldg_keep(x + (first * cvec + chunk) * 16), kshift);
   // the U rows a thread has in flight are a whole grid sweep apart (gridDim.x * rlanes rows): every sweep is one
   // contiguous window of memory read by all CTAs together
   const int64_t sweep = static_cast<int64_t>(gridDim.x) * rlanes;
-  for (int64_t r = static_cast<int64_t>(blockIdx.x) * rlanes + rl; r < rows; r += U * sweep) {
+  auto accumulate = [&](const uint4& v) {
+    float f[V];
+    Elem<DT>::unpack(v, f);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float d = f[i] - kshift[i];
+      s[i] += d;
+      q[i] = fmaf(d, d, q[i]);
+    }
+  };
+  int64_t r = first + rl;
+  const int64_t mine = r < rows ? (rows - r + sweep - 1) / sweep : 0;  // rows this thread accumulates
+  for (; r + (U - 1) * sweep < rows; r += U * sweep) {  // full groups: U unconditional loads in flight
     uint4 v[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t rr = r + u * sweep;
-      v[u] = make_uint4(0, 0, 0, 0);
-      if (rr < rows) v[u] = ldg_stream(x + (rr * cvec + chunk) * 16);
-    }
+    for (int u = 0; u < U; ++u) v[u] = ldg_stream(x + ((r + u * sweep) * cvec + chunk) * 16);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      float f[V];
-      Elem<DT>::unpack(v[u], f);
-#pragma unroll
-      for (int i = 0; i < V; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
-    }
+    for (int u = 0; u < U; ++u) accumulate(v[u]);
   }
-  cta_reduce_store<V>(s, q, ct, cvec, cl, rl, partial);
+  for (; r < rows; r += sweep) accumulate(ldg_stream(x + (r * cvec + chunk) * 16));
+  // fixed-order reduction over the row lanes -> partial[blk][0..1][C]; K -> partial[blk][2][C]; row count -> cnt[blk]
+  float* slot = sm + (static_cast<size_t>(rl) * ct + cl) * (2 * V);
+#pragma unroll
+  for (int i = 0; i < V; ++i) { slot[i] = s[i]; slot[V + i] = q[i]; }
+  __syncthreads();
+  for (int e = threadIdx.x; e < ct * 2 * V; e += kThreads) {
+    const int c2 = e / (2 * V), k = e % (2 * V);
+    float t = 0.f;
+    for (int j = 0; j < rlanes; ++j) t += sm[(static_cast<size_t>(j) * ct + c2) * (2 * V) + k];
+    const int ch = (blockIdx.y * ct + c2) * V + (k % V);
+    partial[(static_cast<size_t>(blockIdx.x) * 3 + (k / V)) * C + ch] = t;
+  }
+  if (rl == 0) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) partial[(static_cast<size_t>(blockIdx.x) * 3 + 2) * C + chunk * V + i] = kshift[i];
+  }
+  // rows of this block = sum over its row lanes (every column group sees the same rows)
+  __shared__ int lane_rows[kThreads];
+  if (cl == 0) lane_rows[rl] = static_cast<int>(mine);
+  __syncthreads();
+  if (blockIdx.y == 0 && threadIdx.x == 0) {
+    int t = 0;
+    for (int j = 0; j < rlanes; ++j) t += lane_rows[j];
+    cnt[blockIdx.x] = static_cast<float>(t);
+  }
+}
+
+// (n, mean, M2) merge of two groups (Chan et al.), fp64
+struct Moments {
+  double n, mean, m2;
+};
+__device__ __forceinline__ Moments merge(const Moments& a, const Moments& b) {
+  if (b.n == 0.0) return a;
+  if (a.n == 0.0) return b;
+  Moments r;
+  r.n = a.n + b.n;
+  const double delta = b.mean - a.mean;
+  r.mean = a.mean + delta * (b.n / r.n);
+  r.m2 = a.m2 + b.m2 + delta * delta * (a.n * b.n / r.n);
+  return r;
+}
+// moments of one channel over all row blocks of the forward partials; one warp per channel, result in every lane
+__device__ __forceinline__ Moments channel_moments(const float* __restrict__ partial, const float* __restrict__ cnt, int nblk, int C,
+                                                   int ch, int lane) {
+  Moments acc{0.0, 0.0, 0.0};
+  for (int b = lane; b < nblk; b += 32) {
+    const double n = static_cast<double>(cnt[b]);
+    if (n == 0.0) continue;
+    const double sd = static_cast<double>(partial[(static_cast<size_t>(b) * 3 + 0) * C + ch]);
+    const double sq = static_cast<double>(partial[(static_cast<size_t>(b) * 3 + 1) * C + ch]);
+    const double k = static_cast<double>(partial[(static_cast<size_t>(b) * 3 + 2) * C + ch]);
+    Moments m{n, k + sd / n, fmax(sq - sd * sd / n, 0.0)};
+    acc = merge(acc, m);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Moments other{__shfl_xor_sync(0xffffffffu, acc.n, o), __shfl_xor_sync(0xffffffffu, acc.mean, o), __shfl_xor_sync(0xffffffffu, acc.m2, o)};
+    // order the pair by lane so both partners compute the same bits
+    acc = (lane & o) ? merge(other, acc) : merge(acc, other);
+  }
+  return acc;
+}
+
+// forward partials -> the sum-reducible fp64 vector {sum x, sum x^2 per channel, count} (exact to fp64 rounding)
+constexpr int kCombineWarps = 8;
+__global__ void __launch_bounds__(kCombineWarps * 32) bn_stats_combine_kernel(const float* __restrict__ partial, const float* __restrict__ cnt,
+                                                                              int nblk, int C, double* __restrict__ sums, double count) {
+  const int lane = threadIdx.x & 31;
+  const int ch = blockIdx.x * kCombineWarps + (threadIdx.x >> 5);
+  if (blockIdx.x == 0 && threadIdx.x == 0) sums[2 * C] = count;
+  if (ch >= C) return;
+  const Moments m = channel_moments(partial, cnt, nblk, C, ch, lane);
+  if (lane == 0) {
+    sums[ch] = m.n * m.mean;
+    sums[C + ch] = m.m2 + m.n * m.mean * m.mean;
+  }
 }
 
 // partial [nblk][2][C] -> sums[2][C] (fp64); sums[2C] = count when count >= 0.  One warp per (which, channel) entry:
 // lane l sums the row blocks l, l+32, ... in fp64, then a fixed butterfly over the lanes (deterministic).
-constexpr int kCombineWarps = 8;
 __global__ void __launch_bounds__(kCombineWarps * 32) bn_combine_kernel(const float* __restrict__ partial, int nblk, int C,
                                                                         double* __restrict__ sums, double count) {
   const int lane = threadIdx.x & 31;
@@ -132,6 +216,30 @@ __global__ void __launch_bounds__(kCombineWarps * 32) bn_combine_kernel(const fl
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
   if (lane == 0) sums[e] = t;
+}
+
+// single-process forward: combine + finalize in one launch (one warp per channel)
+__global__ void __launch_bounds__(kCombineWarps * 32) bn_combine_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ cnt,
+                                                                                 int nblk, int C, double* __restrict__ sums, double count,
+                                                                                 float eps, float momentum, float* __restrict__ mean,
+                                                                                 float* __restrict__ invstd, float* __restrict__ running_mean,
+                                                                                 float* __restrict__ running_var) {
+  const int lane = threadIdx.x & 31;
+  const int ch = blockIdx.x * kCombineWarps + (threadIdx.x >> 5);
+  if (blockIdx.x == 0 && threadIdx.x == 0) sums[2 * C] = count;
+  if (ch >= C) return;
+  const Moments mo = channel_moments(partial, cnt, nblk, C, ch, lane);
+  if (lane != 0) return;
+  sums[ch] = mo.n * mo.mean;
+  sums[C + ch] = mo.m2 + mo.n * mo.mean * mo.mean;
+  const double var = mo.m2 / mo.n;
+  mean[ch] = static_cast<float>(mo.mean);
+  invstd[ch] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  if (running_mean) {
+    const double unbiased = mo.n > 1.0 ? mo.m2 / (mo.n - 1.0) : var;
+    running_mean[ch] = static_cast<float>((1.0 - momentum) * running_mean[ch] + momentum * mo.mean);
+    running_var[ch] = static_cast<float>((1.0 - momentum) * running_var[ch] + momentum * unbiased);
+  }
 }
 
 // sums[2C+1] (possibly all-reduced over ranks) -> mean, invstd, running stats (momentum update, unbiased variance)
@@ -676,11 +784,33 @@ using namespace msf;
 
 extern "C" size_t msf_bn2d_workspace_bytes(int64_t rows, int C) {
   if (rows <= 0 || C <= 0) return 0;
-  return static_cast<size_t>(kMaxRowBlocks) * 2 * C * sizeof(float);  // partial[row blocks][2][C], one wave of CTAs at most
+  return static_cast<size_t>(kMaxRowBlocks) * (3 * C + 1) * sizeof(float);  // partial[row blocks][3][C] + cnt[row blocks], one wave of CTAs at most
+}
+
+namespace {
+int bn_stats_impl(const void* x, int64_t rows, int C, int dtype, double* sums_out, void* workspace, size_t workspace_bytes,
+                  void* stream, bool finalize, float eps, float momentum, float* mean, float* invstd, float* running_mean,
+                  float* running_var);
 }
 
 extern "C" int msf_bn2d_stats(const void* x, int64_t rows, int C, int dtype, double* sums_out, void* workspace,
                               size_t workspace_bytes, void* stream) {
+  return bn_stats_impl(x, rows, C, dtype, sums_out, workspace, workspace_bytes, stream, false, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr);
+}
+
+extern "C" int msf_bn2d_stats_finalize(const void* x, int64_t rows, int C, int dtype, float eps, float momentum, double* sums_out,
+                                       float* mean, float* invstd, float* running_mean, float* running_var, void* workspace,
+                                       size_t workspace_bytes, void* stream) {
+  MSF_REQUIRE(mean && invstd, MSF_ERR_INVALID, "mean / invstd are NULL");
+  MSF_REQUIRE((running_mean == nullptr) == (running_var == nullptr), MSF_ERR_INVALID, "running_mean / running_var must both be given or both be NULL");
+  return bn_stats_impl(x, rows, C, dtype, sums_out, workspace, workspace_bytes, stream, true, eps, momentum, mean, invstd, running_mean,
+                       running_var);
+}
+
+namespace {
+int bn_stats_impl(const void* x, int64_t rows, int C, int dtype, double* sums_out, void* workspace, size_t workspace_bytes,
+                  void* stream, bool finalize, float eps, float momentum, float* mean, float* invstd, float* running_mean,
+                  float* running_var) {
   if (int rc = check_bn(x, rows, C, dtype)) return rc;
   MSF_REQUIRE(sums_out && workspace && workspace_bytes >= msf_bn2d_workspace_bytes(rows, C), MSF_ERR_WORKSPACE, "workspace too small");
   const int vec = 16 / static_cast<int>(dtype_size(dtype));
@@ -688,18 +818,26 @@ extern "C" int msf_bn2d_stats(const void* x, int64_t rows, int C, int dtype, dou
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t smem = static_cast<size_t>(kThreads) * 2 * vec * sizeof(float);
   float* partial = static_cast<float*>(workspace);
+  float* cnt = partial + static_cast<size_t>(kMaxRowBlocks) * 3 * C;
   int nblk = 1;
   ProfScope prof(stream, MSF_K_BN_STATS, static_cast<double>(rows) * C * dtype_size(dtype));
   MSF_DISPATCH_DTYPE(dtype, {
-    nblk = reduce_grid(bn_stats_kernel<DT>, smem, l, rows, kStatsRows * l.rlanes);
+    nblk = reduce_grid(bn_stats_kernel<DT>, smem, l, rows, l.rlanes);
     dim3 grid(static_cast<unsigned>(nblk), static_cast<unsigned>(l.cgroups));
-    bn_stats_kernel<DT><<<grid, kThreads, smem, st>>>(static_cast<const char*>(x), rows, l.cvec, l.ct, partial);
+    bn_stats_kernel<DT><<<grid, kThreads, smem, st>>>(static_cast<const char*>(x), rows, l.cvec, l.ct, partial, cnt);
   });
   MSF_LAUNCH_OK("bn_stats_kernel");
-  bn_combine_kernel<<<(2 * C + kCombineWarps - 1) / kCombineWarps, kCombineWarps * 32, 0, st>>>(partial, nblk, C, sums_out, static_cast<double>(rows));
+  if (finalize) {
+    bn_combine_finalize_kernel<<<(C + kCombineWarps - 1) / kCombineWarps, kCombineWarps * 32, 0, st>>>(
+        partial, cnt, nblk, C, sums_out, static_cast<double>(rows), eps, momentum, mean, invstd, running_mean, running_var);
+  } else {
+    bn_stats_combine_kernel<<<(C + kCombineWarps - 1) / kCombineWarps, kCombineWarps * 32, 0, st>>>(partial, cnt, nblk, C, sums_out,
+                                                                                                   static_cast<double>(rows));
+  }
   MSF_LAUNCH_OK("bn_combine_kernel");
   return MSF_OK;
 }
+}  // namespace
 
 extern "C" int msf_bn2d_finalize(const double* sums, int C, float eps, float momentum, float* mean, float* invstd,
                                  float* running_mean, float* running_var, void* stream) {

@@ -7,8 +7,9 @@ filter of the optimizer at ssl_train.py:281-307 and checkpoints keep working).  
 hot path after the encoder calls: the inverse-jigsaw gather + fuser concat run as one CUDA launch
 (``ops.gather_concat``) and the loss block as one fused launch (``ops.cosine_loss``) or the
 flash-style InfoNCE kernel (``ops.infonce_loss``).  Under bf16 autocast the head Linears (forward, dX, dW) run
-on this repo's persistent tcgen05 GEMM (``TCLinear`` -> ``ops.linear_tc``); BatchNorm1d stays on ATen this round
-(fusing its statistics into the GEMM epilogue is SURVEY 8f rank 1, the next widening step).
+on this repo's persistent tcgen05 GEMM (``TCLinear`` -> ``ops.linear_tc``) and the heads' BatchNorm1d + ReLU on this
+repo's batch-norm kernels (``FusedBatchNorm1d`` -> ``ops.bn_act2d``), which also carry the cross-rank statistics
+(SyncBatchNorm semantics) in one fp64 all-reduce per layer and direction.
 """
 from __future__ import annotations
 
@@ -40,20 +41,65 @@ class TCLinear(nn.Linear):
         return super().forward(x)
 
 
+class FusedBatchNorm1d(nn.Module):
+    """BatchNorm1d (+ fused ReLU) of the heads on this repo's batch-norm kernels (``ops.bn_act2d`` over a [rows][C]
+    matrix).  Same parameters / buffers / state-dict keys as nn.BatchNorm1d.  Like the encoders' ``FusedBatchNorm2d`` it
+    is NOT a ``_BatchNorm`` subclass: ``convert_sync_batchnorm`` (tools/ssl_train.py:160) leaves it alone and it reduces
+    its statistics over the default process group itself -- one fp64 all-reduce per direction instead of
+    torch.nn.SyncBatchNorm's all_gather + Python-side recombination (1.5 ms of host time per call at these sizes).
+    CPU tensors and eval mode take the plain ATen path."""
+
+    def __init__(self, num_features: int, eps: float = 1e-5, momentum: float = 0.1, affine: bool = True, act: str = "none"):
+        super().__init__()
+        if act not in ("none", "relu"):
+            raise ValueError(f"act must be none | relu, got {act!r}")
+        self.num_features, self.eps, self.momentum, self.affine, self.act = num_features, eps, momentum, affine, act
+        if affine:
+            self.weight = nn.Parameter(torch.ones(num_features))
+            self.bias = nn.Parameter(torch.zeros(num_features))
+        else:
+            self.register_parameter("weight", None)
+            self.register_parameter("bias", None)
+        self.register_buffer("running_mean", torch.zeros(num_features))
+        self.register_buffer("running_var", torch.ones(num_features))
+        self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+
+    def extra_repr(self):
+        return f"{self.num_features}, eps={self.eps}, momentum={self.momentum}, affine={self.affine}, act={self.act}"
+
+    def forward(self, x):
+        vec = 8 if x.dtype in (torch.bfloat16, torch.float16) else 4
+        if self.training and x.is_cuda and x.dim() == 2 and self.num_features % vec == 0:
+            import torch.distributed as dist
+            sync = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+            self.num_batches_tracked.add_(1)
+            return ops.bn_act2d(x, self.weight, self.bias, self.running_mean, self.running_var, self.eps, self.momentum,
+                                relu=self.act == "relu", sync_group=dist.group.WORLD if sync else None)
+        if self.training:
+            self.num_batches_tracked.add_(1)
+        out = nn.functional.batch_norm(x, self.running_mean, self.running_var, self.weight, self.bias, self.training, self.momentum, self.eps)
+        return nn.functional.relu(out) if self.act == "relu" else out
+
+
+class FusedAway(nn.Identity):
+    """Placeholder that keeps the reference's nn.Sequential indices: the ReLU at this position runs inside the preceding
+    FusedBatchNorm1d."""
+
+
 def make_projector(in_dim: int, out_dim: int) -> nn.Sequential:
     """3-layer projector, indices 0..7 as in backbone.py:12-22 (last BN has no affine)."""
     layers = []
     for width_out, affine, act in ((in_dim, True, True), (in_dim, True, True), (out_dim, False, False)):
         layers.append(TCLinear(in_dim, width_out, bias=False))
-        layers.append(nn.BatchNorm1d(width_out, affine=affine))
+        layers.append(FusedBatchNorm1d(width_out, affine=affine, act="relu" if act else "none"))
         if act:
-            layers.append(nn.ReLU(inplace=True))
+            layers.append(FusedAway())
     return nn.Sequential(*layers)
 
 
 def make_predictor(in_dim: int, hidden_dim: int) -> nn.Sequential:
     """2-layer bottleneck predictor, indices 0..3 as in backbone.py:25-31."""
-    return nn.Sequential(TCLinear(in_dim, hidden_dim, bias=False), nn.BatchNorm1d(hidden_dim), nn.ReLU(inplace=True),
+    return nn.Sequential(TCLinear(in_dim, hidden_dim, bias=False), FusedBatchNorm1d(hidden_dim, act="relu"), FusedAway(),
                          TCLinear(hidden_dim, in_dim))
 
 

@@ -359,13 +359,20 @@ class _BNAct2d(torch.autograd.Function):
     def forward(ctx, x, weight, bias, residual, running_mean, running_var, eps: float, momentum: float, relu: bool, pool: bool,
                 sync_group, want_mean: bool = False):
         L.require_cuda(x, weight, bias, residual)
+        flat = x.dim() == 2  # (rows, C): BatchNorm1d of the heads -- the kernels see a [rows][C] matrix either way
+        if flat:
+            if pool:
+                raise ValueError("bn_act2d: the pooled variant needs a 4-D input")
+            x = _contig(x)[:, :, None, None]
+            residual = None if residual is None else _contig(residual)[:, :, None, None]
         if x.dim() != 4:
-            raise ValueError(f"bn_act2d: expected (N,C,H,W), got {tuple(x.shape)}")
+            raise ValueError(f"bn_act2d: expected (N,C,H,W) or (rows,C), got {tuple(x.shape)}")
         if pool and (residual is not None or not relu):
             raise ValueError("bn_act2d: the pooled variant is bn -> relu -> maxpool without a residual")
         if want_mean and (pool or residual is None or not relu):
             raise ValueError("bn_act2d: the spatial mean output is implemented for relu(bn(x) + residual) (a BasicBlock output)")
-        x = _nhwc(x)
+        if not flat:
+            x = _nhwc(x)
         N, Cc, H, W = x.shape
         dt, dev = x.dtype, x.device
         code = L.dtype_code(dt)
@@ -376,14 +383,17 @@ class _BNAct2d(torch.autograd.Function):
         ws_bytes = lib.msf_bn2d_workspace_bytes(rows, Cc)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         sums = torch.empty(2 * Cc + 1, dtype=torch.float64, device=dev)
-        L.check(lib.msf_bn2d_stats(L.ptr(x), rows, Cc, code, L.ptr(sums), L.ptr(ws), ws_bytes, st), "msf_bn2d_stats")
-        world = _sync_world(sync_group)
-        if world > 1:
-            dist.all_reduce(sums, group=sync_group)
         mean = torch.empty(Cc, dtype=torch.float32, device=dev)
         invstd = torch.empty(Cc, dtype=torch.float32, device=dev)
-        L.check(lib.msf_bn2d_finalize(L.ptr(sums), Cc, eps, momentum, L.ptr(mean), L.ptr(invstd), L.ptr(running_mean), L.ptr(running_var), st),
-                "msf_bn2d_finalize")
+        world = _sync_world(sync_group)
+        if world > 1:
+            L.check(lib.msf_bn2d_stats(L.ptr(x), rows, Cc, code, L.ptr(sums), L.ptr(ws), ws_bytes, st), "msf_bn2d_stats")
+            dist.all_reduce(sums, group=sync_group)  # one sum-reducible fp64 vector {sum, sum of squares, count}
+            L.check(lib.msf_bn2d_finalize(L.ptr(sums), Cc, eps, momentum, L.ptr(mean), L.ptr(invstd), L.ptr(running_mean),
+                                          L.ptr(running_var), st), "msf_bn2d_finalize")
+        else:
+            L.check(lib.msf_bn2d_stats_finalize(L.ptr(x), rows, Cc, code, eps, momentum, L.ptr(sums), L.ptr(mean), L.ptr(invstd),
+                                                L.ptr(running_mean), L.ptr(running_var), L.ptr(ws), ws_bytes, st), "msf_bn2d_stats_finalize")
         tap = x_arg = None
         if pool:
             PH, PW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
@@ -397,8 +407,8 @@ class _BNAct2d(torch.autograd.Function):
             if residual is not None:
                 if residual.shape != x.shape or residual.dtype != dt:
                     raise ValueError(f"bn_act2d: residual {tuple(residual.shape)} {residual.dtype} vs x {tuple(x.shape)} {dt}")
-                res = _nhwc(residual)
-            y = torch.empty_like(x, memory_format=torch.channels_last)
+                res = residual if flat else _nhwc(residual)
+            y = torch.empty_like(x) if flat else torch.empty_like(x, memory_format=torch.channels_last)
             L.check(lib.msf_bn2d_apply(L.ptr(x), L.ptr(res), L.ptr(y), rows, Cc, code, L.ptr(mean), L.ptr(invstd), L.ptr(gamma), L.ptr(beta),
                                        int(relu), st), "msf_bn2d_apply")
         L.launch_count += 4
@@ -406,7 +416,9 @@ class _BNAct2d(torch.autograd.Function):
         y_mask = y if ((residual is not None and relu) or pool) else None
         ctx.save_for_backward(x, gamma, beta, mean, invstd, sums, y_mask, tap, x_arg)
         ctx.meta = (N, Cc, H, W, code, relu, pool, residual is not None, sync_group, world,
-                    None if weight is None else weight.dtype, None if bias is None else bias.dtype, want_mean)
+                    None if weight is None else weight.dtype, None if bias is None else bias.dtype, want_mean, flat)
+        if flat:
+            return y[:, :, 0, 0]
         if want_mean:
             # global average pool of the block output (src/models/resnet.py:250-254); its backward is folded into the
             # batch-norm backward kernels below instead of being expanded and added to the main gradient by ATen
@@ -416,11 +428,13 @@ class _BNAct2d(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy, gmean=None):
         x, gamma, beta, mean, invstd, sums_fwd, y_mask, tap, x_arg = ctx.saved_tensors
-        N, Cc, H, W, code, relu, pool, has_res, group, world, wdt, bdt, want_mean = ctx.meta
+        N, Cc, H, W, code, relu, pool, has_res, group, world, wdt, bdt, want_mean, flat = ctx.meta
         dev = x.device
         if gy is None:  # only the pooled branch carries gradient
             gy = torch.zeros_like(x, memory_format=torch.channels_last)
-        gy = _nhwc(gy if gy.dtype == x.dtype else gy.to(x.dtype))
+        gy = gy if gy.dtype == x.dtype else gy.to(x.dtype)
+        gy = _contig(gy)[:, :, None, None] if flat else _nhwc(gy)
+        like = (lambda t: torch.empty_like(t)) if flat else (lambda t: torch.empty_like(t, memory_format=torch.channels_last))
         gp = None
         if want_mean and gmean is not None:
             gp = _contig(gmean if gmean.dtype == x.dtype else gmean.to(x.dtype))
@@ -429,7 +443,7 @@ class _BNAct2d(torch.autograd.Function):
         rows = N * H * W
         sums = torch.empty(2 * Cc, dtype=torch.float64, device=dev)
         count_ptr = sums_fwd.data_ptr() + 16 * Cc  # element 2C of the forward sums: the (global) element count
-        dx = torch.empty_like(x, memory_format=torch.channels_last)
+        dx = like(x)
         dres = None
         if pool:
             PH, PW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
@@ -453,11 +467,14 @@ class _BNAct2d(torch.autograd.Function):
                                                 L.ptr(gamma), L.ptr(sums), count_ptr, st), "msf_bn2d_pool_bwd_elemt")
         else:
             if has_res and ctx.needs_input_grad[3]:
-                dres = torch.empty_like(x, memory_format=torch.channels_last)
+                dres = like(x)
             L.check(lib.msf_bn2d_bwd_elemt(L.ptr(x), L.ptr(gy), L.ptr(y_mask), L.ptr(dx), L.ptr(dres), rows, Cc, code, L.ptr(mean),
                                            L.ptr(invstd), L.ptr(gamma), L.ptr(beta), int(relu), L.ptr(gp), hw, L.ptr(sums), count_ptr, st),
                     "msf_bn2d_bwd_elemt")
         L.launch_count += 3
+        if flat:
+            dx = dx[:, :, 0, 0]
+            dres = None if dres is None else dres[:, :, 0, 0]
         return dx, gw, gb, dres, None, None, None, None, None, None, None, None
 
 

@@ -210,3 +210,39 @@ def test_resnet18_encoder_matches_plain_torch_resnet():
     for n, p in ref.named_parameters():
         key = n.replace(".bn.", ".")
         assert _cos(ga[key], p.grad) >= 0.999, (key, _cos(ga[key], p.grad))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rows,dim,affine,act", [(48, 64, True, "relu"), (256, 576, True, "relu"), (4096, 128, False, "none"),
+                                                 (37, 4608, False, "none"), (512, 16, True, "relu")])
+def test_fused_batchnorm1d_matches_torch(dtype, rows, dim, affine, act):
+    """Heads' BatchNorm1d (+ReLU) on the [rows][C] kernels vs nn.BatchNorm1d (+F.relu) in fp64 (backbone.py:15-21,28)."""
+    from msfwsi_b200.module import FusedBatchNorm1d
+    g = torch.Generator(device=DEV).manual_seed(rows + dim)
+    x = (torch.randn(rows, dim, device=DEV, generator=g) * 1.3 + 0.2).to(dtype).requires_grad_(True)
+    mine = FusedBatchNorm1d(dim, affine=affine, act=act).to(DEV).train()
+    ref = torch.nn.BatchNorm1d(dim, affine=affine).to(DEV).double().train()
+    assert set(mine.state_dict()) == set(ref.state_dict())
+    if affine:
+        with torch.no_grad():
+            mine.weight.uniform_(-1.5, 1.5, generator=g); mine.bias.uniform_(-0.5, 0.5, generator=g)
+            ref.weight.copy_(mine.weight); ref.bias.copy_(mine.bias)
+    y = mine(x)
+    assert y.shape == (rows, dim) and y.dtype == dtype
+    xr = x.detach().double().requires_grad_(True)
+    yr = ref(xr)
+    if act == "relu":
+        yr = F.relu(yr)
+    gy = torch.randn(rows, dim, device=DEV, generator=g).to(dtype)
+    y.backward(gy)
+    yr.backward(gy.double())
+    tol = 2e-5 if dtype == torch.float32 else 2 ** -7
+    assert torch.allclose(y.double(), yr, rtol=tol, atol=tol)
+    assert torch.allclose(mine.running_mean.double(), ref.running_mean, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(mine.running_var.double(), ref.running_var, rtol=1e-5, atol=1e-6)
+    assert int(mine.num_batches_tracked) == 1
+    if dtype == torch.float32:
+        assert (x.grad.double() - xr.grad).norm() / xr.grad.norm() <= 1e-4
+    assert _cos(x.grad, xr.grad) >= 0.9999
+    if affine:
+        assert _cos(mine.weight.grad, ref.weight.grad) >= 0.9999 and _cos(mine.bias.grad, ref.bias.grad) >= 0.9999

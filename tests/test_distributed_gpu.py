@@ -57,6 +57,21 @@ def _worker(rank, world, port, q):
         assert torch.allclose(xl.grad.cpu(), x_ref.grad[rank * 6:(rank + 1) * 6], rtol=1e-3, atol=1e-4)  # cross-rank backward sums
         gw = bn.weight.grad.clone(); dist.all_reduce(gw)  # local parameter gradients sum to the full-batch gradient
         assert torch.allclose(gw.cpu(), bn_ref.weight.grad, rtol=1e-3, atol=1e-3)
+        # heads' BatchNorm1d + ReLU with cross-rank statistics == BatchNorm1d over the concatenated rows
+        from msfwsi_b200.module import FusedBatchNorm1d
+        z_all = torch.randn(world * 40, 128, generator=g)
+        bn1_ref = torch.nn.BatchNorm1d(128).train()
+        z_ref = z_all.clone().requires_grad_(True)
+        o_ref = torch.relu(bn1_ref(z_ref))
+        wz = torch.randn(z_all.shape, generator=g)
+        (o_ref * wz).sum().backward()
+        bn1 = FusedBatchNorm1d(128, act="relu").cuda().train()
+        zl = z_all[rank * 40:(rank + 1) * 40].cuda().requires_grad_(True)
+        o = bn1(zl)
+        (o * wz[rank * 40:(rank + 1) * 40].cuda()).sum().backward()
+        assert torch.allclose(o.detach().cpu(), o_ref[rank * 40:(rank + 1) * 40].detach(), rtol=1e-4, atol=1e-4)
+        assert torch.allclose(bn1.running_mean.cpu(), bn1_ref.running_mean, rtol=1e-4, atol=1e-5)
+        assert torch.allclose(zl.grad.cpu(), z_ref.grad[rank * 40:(rank + 1) * 40], rtol=1e-3, atol=1e-4)
         q.put((rank, "ok", res))
     except Exception as e:  # pragma: no cover
         import traceback

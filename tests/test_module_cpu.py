@@ -43,11 +43,14 @@ def test_survives_sync_batchnorm_conversion(model):
     import copy
     conv = torch.nn.SyncBatchNorm.convert_sync_batchnorm(copy.deepcopy(model))
     n_sync = sum(isinstance(m, torch.nn.SyncBatchNorm) for m in conv.modules())
-    # the 48 BatchNorm1d of the heads are converted; the 40 encoder BNs are FusedBatchNorm2d, which reduce their
-    # statistics across ranks themselves with SyncBatchNorm semantics (the reference converts all 88)
-    assert n_sync == 48
+    # nothing is left for torch to convert: the 48 head BNs are FusedBatchNorm1d and the 40 encoder BNs FusedBatchNorm2d,
+    # which reduce their statistics across ranks themselves with SyncBatchNorm semantics (the reference converts all 88,
+    # SURVEY 0); the call must still go through unchanged
+    assert n_sync == 0
+    from msfwsi_b200.module import FusedBatchNorm1d
     from msfwsi_b200.resnet import FusedBatchNorm2d
     assert sum(isinstance(m, FusedBatchNorm2d) for m in conv.modules()) == 40
+    assert sum(isinstance(m, FusedBatchNorm1d) for m in conv.modules()) == 48
     assert set(conv.state_dict()) == set(model.state_dict())
 
 
@@ -71,3 +74,29 @@ def test_forward_requires_cuda_library_path(model):
 def test_bad_loss_mode():
     with pytest.raises(ValueError):
         M.ssl_loss((), mode="nope")
+
+
+def test_checkpoint_layout_matches_reference_driver(model, golden_dir, tmp_path):
+    """ssl_train.py:375-387 / ssl_finetune.py:146-172: dict fields, `module.` prefix, encoder key surgery, resume."""
+    from msfwsi_b200 import checkpoint as CK
+    ref_keys = set(json.load(open(os.path.join(golden_dir, "state_dict_contract.json")))["state_dict"])
+    opt = torch.optim.Adam([p for p in model.parameters()], lr=1e-3)
+    path = str(tmp_path / "checkpoint_0000.pth.tar")
+    state = CK.save_checkpoint(path, model, opt, None, epoch=1, arch="resnet18")
+    assert set(state) == {"epoch", "arch", "state_dict", "optimizer", "scaler"}
+    assert {k[len("module."):] for k in state["state_dict"]} == ref_keys and all(k.startswith("module.") for k in state["state_dict"])
+    ctx, tgt = CK.split_encoders(torch.load(path, weights_only=False)["state_dict"])
+    plain = M.resnet18()  # torchvision-layout encoder, as the fine-tune stage builds
+    want = {k for k in plain.state_dict() if not k.startswith("fc")}
+    assert set(ctx) == want and set(tgt) == want
+    plain.load_state_dict(ctx, strict=False)
+    # resume into a fresh model: identical tensors, epoch restored, also from an un-prefixed checkpoint
+    import copy
+    fresh = copy.deepcopy(model)
+    with torch.no_grad():
+        for p in fresh.parameters():
+            p.add_(1.0)
+    assert CK.load_checkpoint(path, fresh) == 1
+    assert all(torch.equal(a, b) for a, b in zip(fresh.state_dict().values(), model.state_dict().values()))
+    torch.save({"epoch": 3, "state_dict": model.state_dict()}, path)
+    assert CK.load_checkpoint(path, fresh) == 3
