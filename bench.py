@@ -181,7 +181,7 @@ def ours(args):
                                                              gradient_as_bucket_view=True, bucket_cap_mb=128)
     lr = 1e-3 * (args.batch * world) ** 0.5 / 32 ** 0.5  # ssl_train.py:155
     groups = [{"params": [p for n, p in model.named_parameters() if n.startswith(pre)]} for pre in ("context_", "target_", "inter_")]
-    opt = torch.optim.Adam(groups, lr=lr, fused=True)
+    opt = M.FusedAdam(groups, lr=lr)  # torch.optim.Adam semantics (ssl_train.py:309), one msf_adam_multi launch per step
 
     B, K, img = args.batch, 16, args.img
     g = torch.Generator().manual_seed(3407 + rank)
@@ -305,7 +305,9 @@ def ours(args):
         t = traffic.get(top["kernel"])
         roofline = {"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"],
                     "frac": top["frac"], "traffic": None if t is None else t.get("dram_bytes_per_launch"),
-                    "traffic_source": None if t is None else t.get("source"),
+                    "traffic_note": None if t is None else (f"ncu capture at {t.get('shape')}: {t.get('dram_bytes_per_launch'):.4g} B of DRAM traffic for "
+                                                            f"{t.get('algorithmic_bytes_per_launch'):.4g} algorithmic B (ratio {t.get('ratio_to_algorithmic'):.3f}); "
+                                                            f"{t.get('source')}"),
                     "peak_source": ("MEASURED_PEAKS.json " + ("hbm_gbs" if top["bound"] == "hbm" else "bf16_tflops_sustained")) if peaks else "fallback (B200_PROFILING.md)",
                     "launches": top["launches"], "avg_us": top["avg_us"], "work_per_launch": top["work_per_launch"],
                     "share_of_step": top["share_of_step"],
@@ -332,7 +334,7 @@ def ours(args):
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic",
                 "config": {"workload": workload_name(args), "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
-                           "encoder": "resnet18 random-init (PyTorch/cuDNN, channels_last)", "optimizer": "Adam fused, 3 groups",
+                           "encoder": "resnet18 random-init (PyTorch/cuDNN, channels_last)", "optimizer": "Adam, 3 lr groups (msf_adam_multi)",
                            "l2_policy": "per-step inputs (5.2 GB) and activations exceed the 126 MB L2"},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline, "loss": last_loss,

@@ -261,6 +261,39 @@ int msf_bn2d_pool_bwd_elemt(const void* x, const void* dpool, const uint8_t* tap
                             const double* sums /*2C*/, const double* count, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * O1  multi-tensor Adam step with the GradScaler work and an optional EMA teacher update folded in.
+ * Replaces `optimizer.step()` of tools/ssl_train.py:303-309 (torch.optim.Adam over the three learning-rate groups
+ * context_/target_/inter_) and `scaler.step(optimizer)` of :472-474 (unscale, non-finite check, skipped step).
+ *   g = grad * *inv_scale (+ weight_decay * p);  m = m + (1-beta1)*(g - m);  v = beta2*v + (1-beta2)*g*g;
+ *   p -= lr[group] / (1 - beta1^t) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps);   t = *step (already incremented)
+ *   teacher = ema_momentum * teacher + (1 - ema_momentum) * p   (entries with ema != NULL, when with_ema != 0)
+ * Nothing is written when *found_inf != 0.  params / exp_avg / exp_avg_sq / ema are fp32; grads fp32, bf16 or fp16.
+ * `entries` and `chunk_prefix` are DEVICE arrays (msf_adam_plan fills a HOST prefix from HOST numels; chunks of
+ * MSF_ADAM_CHUNK elements); lr is a DEVICE array indexed by entry.group; step / inv_scale / found_inf are DEVICE scalars
+ * (inv_scale and found_inf may be NULL), so the whole optimizer step is free of host synchronisation.  The scalar
+ * hyper-parameters are doubles because torch forms 1 - beta in double before narrowing (1.f - 0.999f != float(0.001)).
+ * ---------------------------------------------------------------------------------------- */
+#define MSF_ADAM_CHUNK 4096
+typedef struct {
+  void* param;
+  const void* grad;
+  void* exp_avg;
+  void* exp_avg_sq;
+  void* ema;      /* teacher copy of this parameter or NULL */
+  int64_t numel;
+  int32_t group;  /* index into lr[] */
+  int32_t reserved;
+} msf_adam_entry;
+int msf_adam_plan(const int64_t* numels /*host*/, int n_tensors, int32_t* chunk_prefix /*host, n+1*/);
+/* *found_inf = 1 if any gradient element is NaN/Inf (never cleared here: the caller zeroes it once per step). */
+int msf_grad_check_multi(const msf_adam_entry* entries /*device*/, const int32_t* chunk_prefix /*device*/, int n_tensors,
+                         int total_chunks, int grad_dtype, float* found_inf, void* stream);
+int msf_adam_multi(const msf_adam_entry* entries /*device*/, const int32_t* chunk_prefix /*device*/, int n_tensors,
+                   int total_chunks, int grad_dtype, const float* lr, double beta1, double beta2, double eps,
+                   double weight_decay, const float* step, const float* inv_scale, const float* found_inf, int with_ema,
+                   float ema_momentum, float ema_one_minus_momentum, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Measurement hook (bench.py): when switched on, every compute entry point records a CUDA event pair on its stream
  * immediately around its main kernel(s); msf_prof_end synchronises those events and returns, per kernel id, the number
  * of calls, the summed algorithmic work (bytes for HBM-bound kernels, FLOP for tensor-bound ones, as defined in
@@ -270,7 +303,7 @@ typedef enum {
   MSF_K_GATHER_FWD = 0, MSF_K_GATHER_BWD, MSF_K_COS_FWD, MSF_K_COS_BWD, MSF_K_ROWNORM, MSF_K_NCE_FLASH, MSF_K_NCE_TWOPASS,
   MSF_K_NCE_SIMT, MSF_K_NCE_BWD, MSF_K_GEMM, MSF_K_CROP_FWD, MSF_K_CROP_BWD, MSF_K_EMA, MSF_K_BN_STATS, MSF_K_BN_APPLY,
   MSF_K_BN_APPLY_RES, MSF_K_BN_BWD_REDUCE, MSF_K_BN_BWD_ELEMT, MSF_K_BN_APPLY_POOL, MSF_K_BN_POOL_BWD_ELEMT,
-  MSF_K_ADAM, MSF_K_COUNT
+  MSF_K_ADAM, MSF_K_GRAD_CHECK, MSF_K_COUNT
 } msf_kernel_id;
 typedef struct {
   int32_t kernel;   /* msf_kernel_id */

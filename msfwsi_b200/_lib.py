@@ -47,7 +47,13 @@ class ProfRecord(C.Structure):
     _fields_ = [("kernel", C.c_int32), ("launches", C.c_int32), ("work", C.c_double), ("ms", C.c_double)]
 
 
-MSF_K_COUNT = 21
+MSF_K_COUNT = 22
+MSF_ADAM_CHUNK = 4096
+
+
+class AdamEntry(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("ema", C.c_void_p),
+                ("numel", C.c_int64), ("group", C.c_int32), ("reserved", C.c_int32)]
 
 
 class EmaEntry(C.Structure):
@@ -95,6 +101,10 @@ _SIGS = {
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "msf_bn2d_pool_bwd_elemt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "msf_adam_plan": (C.c_int, [C.POINTER(C.c_int64), C.c_int, C.POINTER(C.c_int32)]),
+    "msf_grad_check_multi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "msf_adam_multi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p]),
     "msf_prof_begin": (C.c_int, [C.c_int]),
     "msf_prof_end": (C.c_int, [C.POINTER(ProfRecord), C.POINTER(C.c_int)]),
     "msf_prof_kernel_name": (C.c_char_p, [C.c_int]),

@@ -508,8 +508,9 @@ class EmaUpdater:
         for i, (t, s) in enumerate(zip(teacher, student)):
             if t.shape != s.shape or t.dtype != self.tdt or s.dtype != self.sdt:
                 raise ValueError(f"EmaUpdater: tensor {i} shape/dtype mismatch")
-            if not (t.is_contiguous() and s.is_contiguous()):
-                raise ValueError(f"EmaUpdater: tensor {i} must be contiguous")
+            dense = t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last))
+            if not dense or t.stride() != s.stride():
+                raise ValueError(f"EmaUpdater: tensor {i} must be dense (contiguous or channels-last) with equal strides on both sides")
             numels[i] = t.numel()
         prefix = (C.c_int32 * (n + 1))()
         L.check(L.lib().msf_ema_plan(numels, n, prefix), "msf_ema_plan")
