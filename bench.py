@@ -185,17 +185,18 @@ def ours(args):
 
     B, K, img = args.batch, 16, args.img
     g = torch.Generator().manual_seed(3407 + rank)
-    host = {"c1": torch.randn(B, 3, img, img, generator=g).pin_memory(), "c2": torch.randn(B, 3, img, img, generator=g).pin_memory(),
-            "t1": torch.randn(B * K, 3, img, img, generator=g).pin_memory(), "t2": torch.randn(B * K, 3, img, img, generator=g).pin_memory(),
+    # Host side of the input pipeline: normalised views in the layout and precision the first convolution consumes under
+    # bf16 autocast (NHWC, bf16 -- autocast would round the fp32 tensor to exactly these values on the device), pinned.
+    def view(n):
+        return torch.randn(n, 3, img, img, generator=g).to(torch.bfloat16).contiguous(memory_format=torch.channels_last).pin_memory()
+
+    host = {"c1": view(B), "c2": view(B), "t1": view(B * K), "t2": view(B * K),
             "r1": torch.stack([torch.randperm(K, generator=g).argsort() for _ in range(B)]).pin_memory(),
             "r2": torch.stack([torch.randperm(K, generator=g).argsort() for _ in range(B)]).pin_memory()}
     h2d_bytes = sum(t.numel() * t.element_size() for t in host.values())
 
     def to_dev():
-        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        for k in ("c1", "c2", "t1", "t2"):
-            d[k] = d[k].contiguous(memory_format=torch.channels_last)
-        return d
+        return {k: v.to(dev, non_blocking=True) for k, v in host.items()}
 
     def step(d):
         with torch.autocast("cuda", dtype=torch.bfloat16):
@@ -228,11 +229,15 @@ def ours(args):
     launches0 = _lib.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    # process-wide start/end range (push/pop ranges are per thread and would miss the autograd thread's launches):
+    # ncu --nvtx --nvtx-include "msf_timed_steps" captures exactly the launches of the timed steps
+    nvtx_range = torch.cuda.nvtx.range_start("msf_timed_steps")
     e0.record()
     for _ in range(args.steps):
         loss = step(resident)
     e1.record()
     barrier()
+    torch.cuda.nvtx.range_end(nvtx_range)
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = _lib.launch_count - launches0
     prof, prof_dropped = _lib.prof_end()
@@ -335,7 +340,8 @@ def ours(args):
                 "data": "synthetic",
                 "config": {"workload": workload_name(args), "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
                            "encoder": "resnet18 random-init (PyTorch/cuDNN, channels_last)", "optimizer": "Adam, 3 lr groups (msf_adam_multi)",
-                           "l2_policy": "per-step inputs (5.2 GB) and activations exceed the 126 MB L2"},
+                           "l2_policy": "per-step inputs (2.6 GB bf16) and activations exceed the 126 MB L2",
+                           "host_inputs": "bf16 NHWC pinned (what the first convolution consumes under bf16 autocast)"},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline, "loss": last_loss,
                 "encoder_images_per_sec": value * 34}

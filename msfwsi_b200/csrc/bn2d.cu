@@ -152,40 +152,41 @@ __global__ void __launch_bounds__(kThreads) bn_stats_kernel(const char* __restri
   }
 }
 
-// (n, mean, M2) merge of two groups (Chan et al.), fp64
+// Moments of one channel over all row blocks of the forward partials, fp64, division-free per block:
+//   pass 1   S1 = sum_b (n_b * K_b + sd_b)                      -> mean = S1 / N
+//   pass 2   M2 = sum_b (sq_b + 2*delta_b*sd_b + n_b*delta_b^2),  delta_b = K_b - mean   (= sum over rows of (x - mean)^2,
+//            since x = K_b + d; every term is a deviation from a nearby value, so nothing cancels catastrophically)
+// One warp per channel (lane l takes the blocks l, l+32, ...; fixed butterfly => deterministic); result in every lane.
 struct Moments {
-  double n, mean, m2;
+  double n, mean, m2, s1;
 };
-__device__ __forceinline__ Moments merge(const Moments& a, const Moments& b) {
-  if (b.n == 0.0) return a;
-  if (a.n == 0.0) return b;
-  Moments r;
-  r.n = a.n + b.n;
-  const double delta = b.mean - a.mean;
-  r.mean = a.mean + delta * (b.n / r.n);
-  r.m2 = a.m2 + b.m2 + delta * delta * (a.n * b.n / r.n);
-  return r;
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
 }
-// moments of one channel over all row blocks of the forward partials; one warp per channel, result in every lane
 __device__ __forceinline__ Moments channel_moments(const float* __restrict__ partial, const float* __restrict__ cnt, int nblk, int C,
                                                    int ch, int lane) {
-  Moments acc{0.0, 0.0, 0.0};
+  double n = 0.0, s1 = 0.0;
   for (int b = lane; b < nblk; b += 32) {
-    const double n = static_cast<double>(cnt[b]);
-    if (n == 0.0) continue;
+    const double nb = static_cast<double>(cnt[b]);
+    n += nb;
+    s1 += nb * static_cast<double>(partial[(static_cast<size_t>(b) * 3 + 2) * C + ch]) +
+          static_cast<double>(partial[(static_cast<size_t>(b) * 3 + 0) * C + ch]);
+  }
+  n = warp_sum(n);
+  s1 = warp_sum(s1);
+  const double mean = s1 / n;
+  double m2 = 0.0;
+  for (int b = lane; b < nblk; b += 32) {
+    const double nb = static_cast<double>(cnt[b]);
     const double sd = static_cast<double>(partial[(static_cast<size_t>(b) * 3 + 0) * C + ch]);
     const double sq = static_cast<double>(partial[(static_cast<size_t>(b) * 3 + 1) * C + ch]);
-    const double k = static_cast<double>(partial[(static_cast<size_t>(b) * 3 + 2) * C + ch]);
-    Moments m{n, k + sd / n, fmax(sq - sd * sd / n, 0.0)};
-    acc = merge(acc, m);
+    const double delta = static_cast<double>(partial[(static_cast<size_t>(b) * 3 + 2) * C + ch]) - mean;
+    m2 += sq + delta * (2.0 * sd + nb * delta);  // blocks without rows have nb = sd = sq = 0
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    Moments other{__shfl_xor_sync(0xffffffffu, acc.n, o), __shfl_xor_sync(0xffffffffu, acc.mean, o), __shfl_xor_sync(0xffffffffu, acc.m2, o)};
-    // order the pair by lane so both partners compute the same bits
-    acc = (lane & o) ? merge(other, acc) : merge(acc, other);
-  }
-  return acc;
+  m2 = fmax(warp_sum(m2), 0.0);
+  return Moments{n, mean, m2, s1};
 }
 
 // forward partials -> the sum-reducible fp64 vector {sum x, sum x^2 per channel, count} (exact to fp64 rounding)
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(kCombineWarps * 32) bn_stats_combine_kernel(co
   if (ch >= C) return;
   const Moments m = channel_moments(partial, cnt, nblk, C, ch, lane);
   if (lane == 0) {
-    sums[ch] = m.n * m.mean;
+    sums[ch] = m.s1;
     sums[C + ch] = m.m2 + m.n * m.mean * m.mean;
   }
 }
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(kCombineWarps * 32) bn_combine_finalize_kernel
   if (ch >= C) return;
   const Moments mo = channel_moments(partial, cnt, nblk, C, ch, lane);
   if (lane != 0) return;
-  sums[ch] = mo.n * mo.mean;
+  sums[ch] = mo.s1;
   sums[C + ch] = mo.m2 + mo.n * mo.mean * mo.mean;
   const double var = mo.m2 / mo.n;
   mean[ch] = static_cast<float>(mo.mean);
@@ -611,38 +612,45 @@ __global__ void __launch_bounds__(kThreads) bn_apply_pool_kernel(const char* __r
     }
     asm volatile("" : "+r"(some_zero));
     const bool has_zero = some_zero != 0u;  // a channel with sc == 0 (gamma == 0): x_arg cannot be recovered from the key
-    for (unsigned grp = g0; grp < g1; ++grp) {
-      const unsigned w = grp * wpi + lane_w;
-      if (w >= g.windows) break;
-      const WinPos p = decode_window(w, g);
-      uint4 v[9];
-      bool ok[9];
-      // tap (dr, dc) lives (dr*W + dc)*cvec chunks after tap (0, 0); only in-range taps are dereferenced
-      const char* p0 = x + in_chunk(g, p.n, 2 * p.ph - 1, 2 * p.pw - 1, chunk) * 16;
+    // window coordinates advance incrementally (w grows by wpi per step): no division in the loop
+    unsigned w = g0 * wpi + lane_w;
+    WinPos p = decode_window(min(w, g.windows - 1), g);
+    const unsigned step_pw = wpi % static_cast<unsigned>(g.PW), step_ph = wpi / static_cast<unsigned>(g.PW);  // wpi <= 256
+    const int64_t row_chunks = static_cast<int64_t>(g.W) * g.cvec;
+    auto one_tap = [&](const uint4& v, int t, uint32_t* best, uint32_t* bi, uint32_t* bx, bool track_x) {
+      const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+      const uint32_t tc = static_cast<uint32_t>(t) * 0x00010001u;
 #pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const int r = 2 * p.ph - 1 + t / 3, c = 2 * p.pw - 1 + t % 3;
-        ok[t] = r >= 0 && r < g.H && c >= 0 && c < g.W;
-        if (ok[t]) v[t] = ldg_keep(p0 + static_cast<int64_t>(((t / 3) * g.W + (t % 3)) * g.cvec) * 16);
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t key = (wv[i] ^ flip[i]) & keep[i];
+        const uint32_t m = Pk<DT>::gt_mask(key, best[i]);
+        best[i] = (key & m) | (best[i] & ~m);
+        bi[i] = (tc & m) | (bi[i] & ~m);
+        if (track_x) bx[i] = (wv[i] & m) | (bx[i] & ~m);
       }
+    };
+    for (unsigned grp = g0; grp < g1; ++grp, w += wpi) {
+      if (w >= g.windows) break;
       uint32_t best[4], bx[4], bi[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) { best[i] = Pk<DT>::kNegInf2; bx[i] = 0u; bi[i] = 0u; }
+      // tap (dr, dc) lives (dr*W + dc)*cvec chunks after tap (0, 0); only in-range taps are dereferenced
+      const char* p0 = x + in_chunk(g, p.n, 2 * p.ph - 1, 2 * p.pw - 1, chunk) * 16;
+      const bool interior = p.ph > 0 && p.pw > 0 && 2 * p.ph + 1 < g.H && 2 * p.pw + 1 < g.W;
+      if (interior && !has_zero) {  // the common case: nine unconditional loads, three logic ops + one compare per pair
+        uint4 v[9];
 #pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        if (!ok[t]) continue;
-        const uint32_t wv[4] = {v[t].x, v[t].y, v[t].z, v[t].w};
-        const uint32_t tc = static_cast<uint32_t>(t) * 0x00010001u;
+        for (int t = 0; t < 9; ++t) v[t] = ldg_keep(p0 + ((t / 3) * row_chunks + (t % 3) * g.cvec) * 16);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t key = (wv[i] ^ flip[i]) & keep[i];
-          const uint32_t m = Pk<DT>::gt_mask(key, best[i]);
-          best[i] = (key & m) | (best[i] & ~m);
-          bi[i] = (tc & m) | (bi[i] & ~m);
-          if (has_zero) bx[i] = (wv[i] & m) | (bx[i] & ~m);
+        for (int t = 0; t < 9; ++t) one_tap(v[t], t, best, bi, bx, false);
+      } else {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int r = 2 * p.ph - 1 + t / 3, c = 2 * p.pw - 1 + t % 3;
+          if (r >= 0 && r < g.H && c >= 0 && c < g.W) one_tap(ldg_keep(p0 + ((t / 3) * row_chunks + (t % 3) * g.cvec) * 16), t, best, bi, bx, true);
         }
       }
-      if (!has_zero) {
+      if (interior && !has_zero) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) bx[i] = best[i] ^ flip[i];
       }
@@ -659,6 +667,11 @@ __global__ void __launch_bounds__(kThreads) bn_apply_pool_kernel(const char* __r
       stg_stream(y + e * 16, Elem<DT>::pack(out));
       stg_stream(xarg + e * 16, make_uint4(bx[0], bx[1], bx[2], bx[3]));
       store_taps<V>(tap, e, tb);
+      // advance (n, ph, pw) by wpi windows
+      p.pw += static_cast<int>(step_pw);
+      p.ph += static_cast<int>(step_ph);
+      if (p.pw >= g.PW) { p.pw -= g.PW; ++p.ph; }
+      while (p.ph >= g.PH) { p.ph -= g.PH; ++p.n; }
     }
   }
 }
@@ -681,10 +694,11 @@ __global__ void __launch_bounds__(kThreads, 2) bn_pool_bwd_elemt_kernel(const ch
   gc.load(chunk * V, g.cvec * V, mean, invstd, gamma, sums, static_cast<float>(1.0 / *count));
   unsigned g0, g1, wpi;
   cta_group_range(g, g0, g1, wpi);
-  for (unsigned grp = g0; grp < g1; ++grp) {
-    const unsigned w = grp * wpi + lane_w;
+  unsigned w = g0 * wpi + lane_w;
+  WinPos p = decode_window(min(w, g.windows - 1), g);  // advanced incrementally below: no division in the loop
+  const unsigned step_pw = wpi % static_cast<unsigned>(g.PW), step_ph = wpi / static_cast<unsigned>(g.PW);
+  for (unsigned grp = g0; grp < g1; ++grp, w += wpi) {
     if (w >= g.windows) break;
-    const WinPos p = decode_window(w, g);
     uint4 vx[2][2], vd[2][2];
     uint2 tb[2][2];
     bool okx[2][2];
@@ -748,6 +762,10 @@ __global__ void __launch_bounds__(kThreads, 2) bn_pool_bwd_elemt_kernel(const ch
         for (int k = 0; k < V; ++k) fx[k] = fmaf(gc.sc[k], d[k], fmaf(gc.ca[k], fx[k], gc.cb[k]));
         stg_stream(dx + (xe + (i * g.W + j) * g.cvec) * 16, Elem<DT>::pack(fx));
       }
+    p.pw += static_cast<int>(step_pw);
+    p.ph += static_cast<int>(step_ph);
+    if (p.pw >= g.PW) { p.pw -= g.PW; ++p.ph; }
+    while (p.ph >= g.PH) { p.ph -= g.PH; ++p.n; }
   }
 }
 
@@ -765,6 +783,21 @@ inline unsigned stream_grid(int64_t items_per_thread_total) {
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return static_cast<unsigned>(blocks);
+}
+
+// grid of a grid-stride streaming kernel: exactly one wave of resident CTAs (no wave-quantisation tail), never more than
+// the work needs; kept a multiple of ... nothing: the kernels keep per-thread channel constants valid for any grid size
+// as long as gridDim.x * kThreads is a multiple of cvec, which holds whenever kThreads is.
+template <typename Kern>
+inline unsigned wave_grid(Kern kern, int64_t per_thread_items, int cvec) {
+  (void)cvec;
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, 0) != cudaSuccess || occ < 1) occ = 1;
+  int64_t g = static_cast<int64_t>(kNumSMs) * occ;
+  const int64_t need = (per_thread_items + kThreads - 1) / kThreads;
+  if (g > need) g = need;
+  if (g < 1) g = 1;
+  return static_cast<unsigned>(g);
 }
 
 template <typename Kern>
@@ -862,9 +895,9 @@ extern "C" int msf_bn2d_apply(const void* x, const void* res, void* y, int64_t r
   char* yp = static_cast<char*>(y);
   ProfScope prof(stream, res ? MSF_K_BN_APPLY_RES : MSF_K_BN_APPLY, static_cast<double>(rows) * C * dtype_size(dtype) * (res ? 3 : 2));
   if (res) {
-    MSF_DISPATCH_DTYPE(dtype, (bn_apply_kernel<DT, true><<<stream_grid((chunks + 1) / 2), kThreads, 0, st>>>(xp, rp, yp, chunks, cvec, mean, invstd, gamma, beta, relu)));
+    MSF_DISPATCH_DTYPE(dtype, (bn_apply_kernel<DT, true><<<wave_grid(bn_apply_kernel<DT, true>, (chunks + 1) / 2, cvec), kThreads, 0, st>>>(xp, rp, yp, chunks, cvec, mean, invstd, gamma, beta, relu)));
   } else {
-    MSF_DISPATCH_DTYPE(dtype, (bn_apply_kernel<DT, false><<<stream_grid((chunks + 3) / 4), kThreads, 0, st>>>(xp, rp, yp, chunks, cvec, mean, invstd, gamma, beta, relu)));
+    MSF_DISPATCH_DTYPE(dtype, (bn_apply_kernel<DT, false><<<wave_grid(bn_apply_kernel<DT, false>, (chunks + 3) / 4, cvec), kThreads, 0, st>>>(xp, rp, yp, chunks, cvec, mean, invstd, gamma, beta, relu)));
   }
   MSF_LAUNCH_OK("bn_apply_kernel");
   return MSF_OK;
@@ -935,7 +968,7 @@ extern "C" int msf_bn2d_bwd_elemt(const void* x, const void* dy, const void* y_m
   const int cvec = C / vec;
   const int64_t chunks = rows * cvec;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const unsigned grid = stream_grid((chunks + 1) / 2);
+  const int64_t per_thread_total = (chunks + 1) / 2;
   const char* xp = static_cast<const char*>(x);
   const char* dp = static_cast<const char*>(dy);
   const char* mp = static_cast<const char*>(y_mask);
@@ -944,7 +977,7 @@ extern "C" int msf_bn2d_bwd_elemt(const void* x, const void* dy, const void* y_m
   ProfScope prof(stream, MSF_K_BN_BWD_ELEMT, static_cast<double>(rows) * C * dtype_size(dtype) * (3 + ((relu && y_mask) ? 1 : 0) + (dres ? 1 : 0)));
   const unsigned hwc = gpool ? static_cast<unsigned>(hw * cvec) : 1u;
 #define MSF_BWD_ELEMT(MASK, DRES, GP) \
-  MSF_DISPATCH_DTYPE(dtype, (bn_bwd_elemt_kernel<DT, MASK, DRES, GP><<<grid, kThreads, 0, st>>>(xp, dp, mp, dxp, drp, chunks, cvec, mean, invstd, gamma, beta, sums, count, gpp, hwc, gp_scale)))
+  MSF_DISPATCH_DTYPE(dtype, (bn_bwd_elemt_kernel<DT, MASK, DRES, GP><<<wave_grid(bn_bwd_elemt_kernel<DT, MASK, DRES, GP>, per_thread_total, cvec), kThreads, 0, st>>>(xp, dp, mp, dxp, drp, chunks, cvec, mean, invstd, gamma, beta, sums, count, gpp, hwc, gp_scale)))
   const int mask = !relu ? 0 : (y_mask ? 2 : 1);
   if (mask == 0 && !dres) { MSF_BWD_ELEMT(0, false, false); }
   else if (mask == 0) { MSF_BWD_ELEMT(0, true, false); }

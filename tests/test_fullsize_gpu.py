@@ -141,3 +141,57 @@ def test_crop_resample_full_size_partition_of_unity():
     tiles = ops.crop_resample(x, boxes, (32, 32))  # integer copy of the 4x4 grid (blockshaped order)
     rebuilt = tiles.reshape(B, 4, 4, Cc, 32, 32).permute(0, 3, 1, 4, 2, 5).reshape(B, Cc, H, W)
     assert torch.equal(rebuilt, x)
+
+
+@pytest.mark.timeout(600)
+def test_stem_batchnorm_relu_pool_beyond_2_31_elements():
+    """The stem activation of a 4096-image target batch (configs[1]: 16 tiles x batch 256) has 4096*64*112*112 =
+    3.29e9 elements -- beyond 32-bit indexing.  Size-independent checks of the fused bn -> relu -> maxpool (N1) there:
+    statistics against chunked fp64 sums, forward / backward of the first and last images against the unfused ATen
+    sequence evaluated with the same global statistics, and sum identities of the gradient."""
+    import torch.nn.functional as F
+    N, C, H, W = 4096, 64, 112, 112
+    g = _gen(11)
+    x = torch.empty((N, H, W, C), dtype=torch.bfloat16, device=DEV)
+    for i in range(0, N, 512):  # filled chunk-wise: randn itself is limited to 2^31 elements per call
+        x[i:i + 512] = (torch.randn((512, H, W, C), device=DEV, generator=g) * 1.5 + 0.3).to(torch.bfloat16)
+    assert x.numel() > 2 ** 31
+    xv = x.permute(0, 3, 1, 2).requires_grad_(True)  # NCHW view of the NHWC buffer
+    w = torch.empty(C, device=DEV).uniform_(0.5, 1.5, generator=g).requires_grad_(True)
+    b = torch.empty(C, device=DEV).uniform_(-0.5, 0.5, generator=g).requires_grad_(True)
+    rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    y = ops.bn_act2d(xv, w, b, rm, rv, 1e-5, 1.0, relu=True, pool=True)  # momentum 1: running stats = batch stats
+    assert y.shape == (N, C, 56, 56)
+    # (1) statistics: chunked fp64 reference
+    s = torch.zeros(C, dtype=torch.float64, device=DEV)
+    q = torch.zeros(C, dtype=torch.float64, device=DEV)
+    for i in range(0, N, 256):
+        c = x[i:i + 256].double()
+        s += c.sum(dim=(0, 1, 2)); q += (c * c).sum(dim=(0, 1, 2))
+    n = float(N * H * W)
+    mean, var = s / n, q / n - (s / n) ** 2
+    assert torch.allclose(rm.double(), mean, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(rv.double(), var * n / (n - 1), rtol=1e-5, atol=1e-6)
+    # (2) first / last images against ATen with the same statistics (eval-mode batch_norm = the affine map)
+    gy = torch.empty_like(y)
+    for i in range(0, N, 512):
+        gy[i:i + 512] = torch.randn((512, C, 56, 56), device=DEV, generator=g).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    y.backward(gy)
+    for sl in (slice(0, 4), slice(N - 4, N)):
+        xr = xv[sl].detach().float().requires_grad_(True)
+        yr = F.max_pool2d(F.relu(F.batch_norm(xr, mean.float(), var.float(), w.detach(), b.detach(), False, 0.0, 1e-5)), 3, 2, 1)
+        assert torch.allclose(y[sl].float(), yr, rtol=2 ** -7, atol=2 ** -7)
+    # (3) gradient identities of batch norm: sum_rows dx = 0 and sum_rows dx * xhat = 0 per channel (up to bf16 rounding
+    #     of dx), and grad_bias = sum of the pooled gradients that are alive
+    dx = xv.grad
+    assert dx.shape == xv.shape
+    tot = torch.zeros(C, dtype=torch.float64, device=DEV)
+    absum = torch.zeros(C, dtype=torch.float64, device=DEV)
+    for i in range(0, N, 256):
+        c = dx[i:i + 256].double()
+        tot += c.sum(dim=(0, 2, 3)); absum += c.abs().sum(dim=(0, 2, 3))
+    assert bool((tot.abs() <= 2e-3 * absum + 1e-6).all()), float((tot.abs() / absum).max())
+    alive = torch.zeros(C, dtype=torch.float64, device=DEV)
+    for i in range(0, N, 512):
+        alive += (gy[i:i + 512].double() * (y[i:i + 512] > 0)).sum(dim=(0, 2, 3))
+    assert torch.allclose(b.grad.double(), alive, rtol=1e-4, atol=1e-2)

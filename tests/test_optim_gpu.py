@@ -71,7 +71,7 @@ def test_fused_adam_under_gradscaler_skips_on_overflow_and_unscales():
         for a, b in zip(pa, pb):
             gr = torch.empty_like(a).copy_(torch.randn(a.shape, generator=g).to(DEV) * 1024.0)  # "scaled" gradients
             if it == 2:
-                gr.view(-1)[0] = float("inf")  # overflow step: both must skip and halve the scale
+                gr[(0,) * gr.dim()] = float("inf")  # overflow step: both must skip and halve the scale
             a.grad, b.grad = gr.clone(), gr.clone()
         # what scaler.scale(loss).backward() leaves behind; scaler.step / update as in ssl_train.py:473-474
         for s_, o_ in ((sa, ref), (sb, mine)):
