@@ -294,6 +294,17 @@ int msf_adam_multi(const msf_adam_entry* entries /*device*/, const int32_t* chun
                    float ema_momentum, float ema_one_minus_momentum, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * S1  space-to-depth re-layout of the encoder input for the stem convolution (src/models/resnet.py:155, 244:
+ * Conv2d(3, 64, 7, stride 2, padding 3)).  conv7x7/2(x, w) == conv4x4/1(s2d(x), w') with
+ *   s2d(x)[n, oy, ox, c*4 + dy*2 + dx] = x[n, c, 2*oy + dy - 3, 2*ox + dx - 3]   (0 outside; channels >= 4*C_in are 0)
+ * out (N, (H+6)/2, (W+6)/2, 16) NHWC in out_dtype; x addressed through ELEMENT strides (NCHW or NHWC), C_in <= 4, H and W
+ * even.  The convolution itself stays on cuDNN (3x faster in this form); w' is the 7x7 kernel zero-padded to 8x8 and
+ * rearranged the same way (a tiny differentiable torch expression on the host side, msfwsi_b200/resnet.py).
+ * ---------------------------------------------------------------------------------------- */
+int msf_stem_s2d(const void* x, int64_t N, int C_in, int H, int W, int64_t stride_n, int64_t stride_c, int64_t stride_y,
+                 int64_t stride_x, int in_dtype, void* out, int out_dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Measurement hook (bench.py): when switched on, every compute entry point records a CUDA event pair on its stream
  * immediately around its main kernel(s); msf_prof_end synchronises those events and returns, per kernel id, the number
  * of calls, the summed algorithmic work (bytes for HBM-bound kernels, FLOP for tensor-bound ones, as defined in
@@ -303,7 +314,7 @@ typedef enum {
   MSF_K_GATHER_FWD = 0, MSF_K_GATHER_BWD, MSF_K_COS_FWD, MSF_K_COS_BWD, MSF_K_ROWNORM, MSF_K_NCE_FLASH, MSF_K_NCE_TWOPASS,
   MSF_K_NCE_SIMT, MSF_K_NCE_BWD, MSF_K_GEMM, MSF_K_CROP_FWD, MSF_K_CROP_BWD, MSF_K_EMA, MSF_K_BN_STATS, MSF_K_BN_APPLY,
   MSF_K_BN_APPLY_RES, MSF_K_BN_BWD_REDUCE, MSF_K_BN_BWD_ELEMT, MSF_K_BN_APPLY_POOL, MSF_K_BN_POOL_BWD_ELEMT,
-  MSF_K_ADAM, MSF_K_GRAD_CHECK, MSF_K_COUNT
+  MSF_K_ADAM, MSF_K_GRAD_CHECK, MSF_K_STEM_S2D, MSF_K_COUNT
 } msf_kernel_id;
 typedef struct {
   int32_t kernel;   /* msf_kernel_id */

@@ -47,7 +47,7 @@ class ProfRecord(C.Structure):
     _fields_ = [("kernel", C.c_int32), ("launches", C.c_int32), ("work", C.c_double), ("ms", C.c_double)]
 
 
-MSF_K_COUNT = 22
+MSF_K_COUNT = 23
 MSF_ADAM_CHUNK = 4096
 
 
@@ -105,6 +105,8 @@ _SIGS = {
     "msf_grad_check_multi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "msf_adam_multi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p]),
+    "msf_stem_s2d": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p,
+                               C.c_int, C.c_void_p]),
     "msf_prof_begin": (C.c_int, [C.c_int]),
     "msf_prof_end": (C.c_int, [C.POINTER(ProfRecord), C.POINTER(C.c_int)]),
     "msf_prof_kernel_name": (C.c_char_p, [C.c_int]),

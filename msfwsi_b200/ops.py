@@ -491,6 +491,40 @@ def bn_act2d(x: torch.Tensor, weight: Optional[torch.Tensor], bias: Optional[tor
 
 
 # ------------------------------------------------------------------------------------------
+# S1: space-to-depth input layout for the stem convolution          (src/models/resnet.py:155, 244)
+# ------------------------------------------------------------------------------------------
+def stem_s2d(x: torch.Tensor, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """x (N, C<=4, H, W) (any strides, H and W even) -> the zero-padded (3 px), 2x2 pixel-unshuffled image as an
+    (N, 16, (H+6)/2, (W+6)/2) channels-last tensor in ``out_dtype``: channel c*4 + dy*2 + dx of pixel (oy, ox) is
+    x[n, c, 2*oy+dy-3, 2*ox+dx-3].  No gradient flows to x (the encoder input never needs one)."""
+    L.require_cuda(x)
+    if x.dim() != 4:
+        raise ValueError(f"stem_s2d: expected (N,C,H,W), got {tuple(x.shape)}")
+    N, Cin, H, W = x.shape
+    out_dtype = out_dtype or x.dtype
+    x = x.detach()
+    out = torch.empty((N, 16, (H + 6) // 2, (W + 6) // 2), dtype=out_dtype, device=x.device, memory_format=torch.channels_last)
+    sn, sc, sy, sx = x.stride()
+    L.check(L.lib().msf_stem_s2d(L.ptr(x), N, Cin, H, W, sn, sc, sy, sx, L.dtype_code(x.dtype), L.ptr(out), L.dtype_code(out_dtype),
+                                 L.stream_ptr()), "msf_stem_s2d")
+    L.launch_count += 1
+    return out
+
+
+def stem_s2d_weight(w: torch.Tensor) -> torch.Tensor:
+    """The (O, C, 7, 7) stem kernel in the layout that pairs with :func:`stem_s2d`: zero-padded to 8x8, split into
+    (ky, dy) x (kx, dx) and rearranged to (O, 16, 4, 4) with input channel c*4 + dy*2 + dx.  Plain differentiable torch
+    ops on a 9408-element tensor, so autograd turns the 4x4 kernel's gradient back into the 7x7 one."""
+    O, Cin, kh, kw = w.shape
+    if (kh, kw) != (7, 7) or Cin > 4:
+        raise ValueError(f"stem_s2d_weight: expected (O, C<=4, 7, 7), got {tuple(w.shape)}")
+    w8 = torch.nn.functional.pad(w, (0, 1, 0, 1))                       # (O, C, 8, 8), tap 7 = 0
+    w8 = w8.reshape(O, Cin, 4, 2, 4, 2).permute(0, 1, 3, 5, 2, 4)       # (O, C, dy, dx, ky, kx)
+    w16 = w8.reshape(O, Cin * 4, 4, 4)
+    return torch.nn.functional.pad(w16, (0, 0, 0, 0, 0, 16 - Cin * 4))  # channels -> 16
+
+
+# ------------------------------------------------------------------------------------------
 # E1: multi-tensor EMA (extension)
 # ------------------------------------------------------------------------------------------
 class EmaUpdater:
