@@ -296,6 +296,10 @@ def ours(args):
     for name, r in prof.items():
         if r["ms"] <= 0:
             continue
+        if r["bound"] == "l":  # latency-bound exchange (NVLink round trip): no throughput roofline, report the time
+            kernels.append({"kernel": name, "bound": "latency", "launches": r["launches"], "ms_per_step": r["ms"] / args.steps,
+                            "share_of_step": r["ms"] / ms, "avg_us": 1e3 * r["ms"] / r["launches"]})
+            continue
         if r["bound"] == "h":
             ach, peak, unit, bound = r["work"] / r["ms"] / 1e6, hbm_peak, "GB/s", "hbm"
         else:
@@ -305,8 +309,8 @@ def ours(args):
                         "work_per_launch": r["work"] / r["launches"], "avg_us": 1e3 * r["ms"] / r["launches"]})
     kernels.sort(key=lambda k: -k["ms_per_step"])
     roofline = None
-    if kernels:
-        top = kernels[0]
+    if any("frac" in k for k in kernels):
+        top = next(k for k in kernels if "frac" in k)
         t = traffic.get(top["kernel"])
         roofline = {"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"],
                     "frac": top["frac"], "traffic": None if t is None else t.get("dram_bytes_per_launch"),

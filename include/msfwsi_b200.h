@@ -305,6 +305,20 @@ int msf_stem_s2d(const void* x, int64_t N, int C_in, int H, int W, int64_t strid
                  int64_t stride_x, int in_dtype, void* out, int out_dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * C1  all-reduce (sum) of a small fp64 vector over NVLink peer memory, one single-CTA kernel per call: the cross-rank
+ * exchange of the batch-norm statistics (SyncBatchNorm, tools/ssl_train.py:160; 2C+1 doubles per layer and direction)
+ * without an NCCL launch.  `peers` is a DEVICE array of `world` pointers to the ranks' SYMMETRIC workspaces of
+ * msf_peer_workspace_bytes(capacity) bytes each, every one mapped into this process (peers[rank] is the local one), zeroed
+ * once before the first call.  All ranks must issue the same sequence of calls with seq = 1, 2, 3, ... (like any
+ * collective).  Result: vec[i] = sum over ranks, added in rank order (bit-identical on every rank).  The wait for the
+ * peers is bounded (20 s); a timeout traps, i.e. surfaces as a CUDA error instead of a hang.
+ * ---------------------------------------------------------------------------------------- */
+#define MSF_PEER_MAX_WORLD 32
+size_t msf_peer_workspace_bytes(int64_t capacity_doubles);
+int msf_peer_allreduce_f64(double* vec, int n, void* const* peers /*device*/, int world, int rank, uint64_t seq,
+                           int64_t capacity_doubles, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Measurement hook (bench.py): when switched on, every compute entry point records a CUDA event pair on its stream
  * immediately around its main kernel(s); msf_prof_end synchronises those events and returns, per kernel id, the number
  * of calls, the summed algorithmic work (bytes for HBM-bound kernels, FLOP for tensor-bound ones, as defined in
@@ -314,7 +328,7 @@ typedef enum {
   MSF_K_GATHER_FWD = 0, MSF_K_GATHER_BWD, MSF_K_COS_FWD, MSF_K_COS_BWD, MSF_K_ROWNORM, MSF_K_NCE_FLASH, MSF_K_NCE_TWOPASS,
   MSF_K_NCE_SIMT, MSF_K_NCE_BWD, MSF_K_GEMM, MSF_K_CROP_FWD, MSF_K_CROP_BWD, MSF_K_EMA, MSF_K_BN_STATS, MSF_K_BN_APPLY,
   MSF_K_BN_APPLY_RES, MSF_K_BN_BWD_REDUCE, MSF_K_BN_BWD_ELEMT, MSF_K_BN_APPLY_POOL, MSF_K_BN_POOL_BWD_ELEMT,
-  MSF_K_ADAM, MSF_K_GRAD_CHECK, MSF_K_STEM_S2D, MSF_K_COUNT
+  MSF_K_ADAM, MSF_K_GRAD_CHECK, MSF_K_STEM_S2D, MSF_K_PEER_ALLREDUCE, MSF_K_COUNT
 } msf_kernel_id;
 typedef struct {
   int32_t kernel;   /* msf_kernel_id */
@@ -325,7 +339,7 @@ typedef struct {
 int msf_prof_begin(int capacity /* event pairs to pre-create; calls beyond it are dropped and counted */);
 int msf_prof_end(msf_prof_record* out /* host, MSF_K_COUNT entries */, int* dropped /* host, may be NULL */);
 const char* msf_prof_kernel_name(int kernel);
-int msf_prof_kernel_bound(int kernel); /* 'h' HBM, 't' tensor pipe, 'f' fp32 FMA */
+int msf_prof_kernel_bound(int kernel); /* 'h' HBM, 't' tensor pipe, 'f' fp32 FMA, 'l' latency (NVLink round trip) */
 
 #ifdef __cplusplus
 }

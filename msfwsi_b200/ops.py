@@ -351,6 +351,67 @@ def _sync_world(group) -> int:
     return dist.get_world_size(group)
 
 
+class PeerReducer:
+    """Sum-all-reduce of small fp64 vectors over NVLink peer memory (``msf_peer_allreduce_f64``): one single-CTA kernel
+    on the current stream per call instead of an NCCL launch.  The symmetric workspace (every rank's copy mapped into
+    every process) comes from ``torch.distributed._symmetric_memory``; creating a reducer is a collective."""
+
+    CAPACITY = 16384  # doubles per slot: 2 * 4608 + 1 (the widest head BatchNorm) fits with room to spare
+    _cache = {}
+
+    def __init__(self, group, device: torch.device):
+        import torch.distributed._symmetric_memory as symm
+        nbytes = L.lib().msf_peer_workspace_bytes(self.CAPACITY)
+        self.buf = symm.empty(nbytes, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, group)
+        self.world, self.rank = int(self.hdl.world_size), int(self.hdl.rank)
+        if self.world > L.MSF_PEER_MAX_WORLD:
+            raise RuntimeError(f"PeerReducer supports up to {L.MSF_PEER_MAX_WORLD} ranks")
+        self.peers = torch.tensor([int(p) for p in self.hdl.buffer_ptrs], dtype=torch.int64, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)  # every workspace is zeroed before anybody publishes a flag
+        self.seq = 0
+
+    def all_reduce_(self, vec: torch.Tensor) -> torch.Tensor:
+        if vec.dtype != torch.float64 or not vec.is_contiguous() or vec.numel() > self.CAPACITY:
+            raise ValueError("PeerReducer.all_reduce_: contiguous float64 vector of at most CAPACITY elements expected")
+        self.seq += 1
+        L.check(L.lib().msf_peer_allreduce_f64(L.ptr(vec), vec.numel(), L.ptr(self.peers), self.world, self.rank, self.seq, self.CAPACITY,
+                                               L.stream_ptr()), "msf_peer_allreduce_f64")
+        L.launch_count += 1
+        return vec
+
+    @classmethod
+    def get(cls, group, device: torch.device):
+        """The reducer of (group, device), created on first use (collectively).  If symmetric memory cannot be set up
+        on ANY rank, all ranks agree to use NCCL instead (returns None)."""
+        key = (id(group), device.index)
+        if key not in cls._cache:
+            red, ok = None, 1
+            try:
+                red = cls(group, device)
+            except Exception as e:  # noqa: BLE001 -- any failure means "no peer memory here"
+                import warnings
+                warnings.warn(f"msfwsi_b200: NVLink peer-memory all-reduce unavailable ({e!r:.200}); batch-norm statistics use NCCL", stacklevel=2)
+                ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            cls._cache[key] = red if int(flag.item()) == 1 else None
+        return cls._cache[key]
+
+
+USE_PEER_ALLREDUCE = True  # batch-norm statistics over NVLink peer memory when available (else NCCL)
+
+
+def _all_reduce_stats(sums: torch.Tensor, group) -> None:
+    red = PeerReducer.get(group, sums.device) if USE_PEER_ALLREDUCE else None
+    if red is not None:
+        red.all_reduce_(sums)
+    else:
+        dist.all_reduce(sums, group=group)
+
+
 class _BNAct2d(torch.autograd.Function):
     """act(batch_norm(x) (+ residual)) with batch statistics (train mode), optionally followed by the stem's
     3x3/2 max-pool.  ``sync_group`` = process group the statistics are reduced over (SyncBatchNorm semantics), or None."""
@@ -388,7 +449,7 @@ class _BNAct2d(torch.autograd.Function):
         world = _sync_world(sync_group)
         if world > 1:
             L.check(lib.msf_bn2d_stats(L.ptr(x), rows, Cc, code, L.ptr(sums), L.ptr(ws), ws_bytes, st), "msf_bn2d_stats")
-            dist.all_reduce(sums, group=sync_group)  # one sum-reducible fp64 vector {sum, sum of squares, count}
+            _all_reduce_stats(sums, sync_group)  # one sum-reducible fp64 vector {sum, sum of squares, count}
             L.check(lib.msf_bn2d_finalize(L.ptr(sums), Cc, eps, momentum, L.ptr(mean), L.ptr(invstd), L.ptr(running_mean),
                                           L.ptr(running_var), st), "msf_bn2d_finalize")
         else:
@@ -461,7 +522,7 @@ class _BNAct2d(torch.autograd.Function):
         gw = None if wdt is None else sums[Cc:].to(wdt)
         gb = None if bdt is None else sums[:Cc].to(bdt)
         if world > 1:
-            dist.all_reduce(sums, group=group)
+            _all_reduce_stats(sums, group)
         if pool:
             L.check(lib.msf_bn2d_pool_bwd_elemt(L.ptr(x), L.ptr(gy), L.ptr(tap), L.ptr(dx), N, H, W, Cc, code, L.ptr(mean), L.ptr(invstd),
                                                 L.ptr(gamma), L.ptr(sums), count_ptr, st), "msf_bn2d_pool_bwd_elemt")

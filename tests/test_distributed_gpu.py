@@ -57,6 +57,18 @@ def _worker(rank, world, port, q):
         assert torch.allclose(xl.grad.cpu(), x_ref.grad[rank * 6:(rank + 1) * 6], rtol=1e-3, atol=1e-4)  # cross-rank backward sums
         gw = bn.weight.grad.clone(); dist.all_reduce(gw)  # local parameter gradients sum to the full-batch gradient
         assert torch.allclose(gw.cpu(), bn_ref.weight.grad, rtol=1e-3, atol=1e-3)
+        # C1: the NVLink peer-memory all-reduce the batch norms use == a plain sum over ranks, bit-identical on all ranks
+        from msfwsi_b200 import ops as _ops
+        red = _ops.PeerReducer.get(dist.group.WORLD, torch.device("cuda", torch.cuda.current_device()))
+        assert red is not None, "symmetric memory unavailable on this box"
+        for n in (1, 129, 1025, 9217):
+            v = (torch.arange(n, dtype=torch.float64, device="cuda") + 1.0) * (rank + 1) * 1e-3
+            want = (torch.arange(n, dtype=torch.float64, device="cuda") + 1.0) * 1e-3 * sum(range(1, world + 1))
+            red.all_reduce_(v)
+            assert torch.allclose(v, want, rtol=1e-15, atol=0)
+            gathered = [torch.empty_like(v) for _ in range(world)]
+            dist.all_gather(gathered, v)
+            assert all(torch.equal(gathered[0], t) for t in gathered)
         # heads' BatchNorm1d + ReLU with cross-rank statistics == BatchNorm1d over the concatenated rows
         from msfwsi_b200.module import FusedBatchNorm1d
         z_all = torch.randn(world * 40, 128, generator=g)

@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT)
 import msfwsi_b200 as M
 
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
-torch.cuda.set_device(local); dev = torch.device("cuda", local)
+torch.cuda.set_device(local); dev = torch.device("cuda", local); torch.backends.cudnn.benchmark = True  # like bench.py
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 B = int(os.environ.get("B", "256"))
