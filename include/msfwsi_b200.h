@@ -311,12 +311,12 @@ int msf_stem_s2d(const void* x, int64_t N, int C_in, int H, int W, int64_t strid
  * msf_peer_workspace_bytes(capacity) bytes each, every one mapped into this process (peers[rank] is the local one), zeroed
  * once before the first call.  All ranks must issue the same sequence of calls with seq = 1, 2, 3, ... (like any
  * collective).  Result: vec[i] = sum over ranks, added in rank order (bit-identical on every rank).  The wait for the
- * peers is bounded (20 s); a timeout traps, i.e. surfaces as a CUDA error instead of a hang.
+ * peers is bounded by timeout_ms; a timeout traps, i.e. surfaces as a CUDA error instead of a hang.
  * ---------------------------------------------------------------------------------------- */
 #define MSF_PEER_MAX_WORLD 32
 size_t msf_peer_workspace_bytes(int64_t capacity_doubles);
 int msf_peer_allreduce_f64(double* vec, int n, void* const* peers /*device*/, int world, int rank, uint64_t seq,
-                           int64_t capacity_doubles, void* stream);
+                           int64_t capacity_doubles, int timeout_ms, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Measurement hook (bench.py): when switched on, every compute entry point records a CUDA event pair on its stream

@@ -109,7 +109,7 @@ _SIGS = {
     "msf_stem_s2d": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p,
                                C.c_int, C.c_void_p]),
     "msf_peer_workspace_bytes": (C.c_size_t, [C.c_int64]),
-    "msf_peer_allreduce_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_int64, C.c_void_p]),
+    "msf_peer_allreduce_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_int64, C.c_int, C.c_void_p]),
     "msf_prof_begin": (C.c_int, [C.c_int]),
     "msf_prof_end": (C.c_int, [C.POINTER(ProfRecord), C.POINTER(C.c_int)]),
     "msf_prof_kernel_name": (C.c_char_p, [C.c_int]),

@@ -6,7 +6,7 @@
 // every process: torch.distributed._symmetric_memory) and one single-CTA kernel does the whole exchange:
 //   1. copy the local vector into my workspace slot (two slots, alternating with the call sequence number),
 //   2. __threadfence_system(), then store `seq` into flags[my_rank] of EVERY rank's workspace (NVLink stores),
-//   3. spin (bounded, ld.acquire.sys) until my flags[r] >= seq for all r,
+//   3. spin (bounded by the caller's timeout, ld.acquire.sys) until my flags[r] >= seq for all r,
 //   4. sum the peers' slots in rank order (NVLink loads) -- fixed order, so all ranks get bit-identical results.
 // Two slots suffice: a rank enters call k+2 only after passing the wait of call k+1, which needs every peer's flag
 // k+1, which a peer publishes only after it has finished reading the slots of call k.
@@ -79,15 +79,16 @@ extern "C" size_t msf_peer_workspace_bytes(int64_t capacity_doubles) {
 }
 
 extern "C" int msf_peer_allreduce_f64(double* vec, int n, void* const* peers, int world, int rank, uint64_t seq, int64_t capacity_doubles,
-                                      void* stream) {
+                                      int timeout_ms, void* stream) {
   MSF_REQUIRE(vec && peers && n > 0, MSF_ERR_INVALID, "bad arguments");
   MSF_REQUIRE(world >= 1 && world <= MSF_PEER_MAX_WORLD && rank >= 0 && rank < world, MSF_ERR_INVALID, "world=%d rank=%d out of range", world, rank);
   MSF_REQUIRE(n <= capacity_doubles, MSF_ERR_WORKSPACE, "vector of %d doubles exceeds the workspace capacity %lld", n,
               static_cast<long long>(capacity_doubles));
   MSF_REQUIRE(seq > 0, MSF_ERR_INVALID, "sequence numbers start at 1");
+  MSF_REQUIRE(timeout_ms > 0, MSF_ERR_INVALID, "timeout_ms must be positive");
   ProfScope prof(stream, MSF_K_PEER_ALLREDUCE, static_cast<double>(n) * 8.0 * (world + 1));
   peer_allreduce_kernel<<<1, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(vec, n, reinterpret_cast<char* const*>(peers), world, rank, seq,
-                                                                               static_cast<size_t>(capacity_doubles), 20ull * 1000 * 1000 * 1000);
+                                                                               static_cast<size_t>(capacity_doubles), static_cast<uint64_t>(timeout_ms) * 1000000ull);
   MSF_LAUNCH_OK("peer_allreduce_kernel");
   return MSF_OK;
 }

@@ -160,9 +160,13 @@ class MSFWSI(nn.Module):
 
         from torch.distributed.algorithms._checkpoint.checkpoint_wrapper import (CheckpointImpl, apply_activation_checkpointing,
                                                                                   checkpoint_wrapper)
-        wrap = partial(checkpoint_wrapper, offload_to_cpu=False, checkpoint_impl=CheckpointImpl.NO_REENTRANT)
+        # backbone.py:106-119 (its `offload_to_cpu=False` keyword no longer exists in current torch and would be forwarded
+        # to Conv2d.forward; omitted here).  The reference then replaces both stem convolutions by fresh, unwrapped
+        # layers (backbone.py:121-127) -- here conv1 is simply left unwrapped, keeping its weights.
+        wrap = partial(checkpoint_wrapper, checkpoint_impl=CheckpointImpl.NO_REENTRANT)
+        stems = {id(self.context_encoder.conv1), id(self.target_encoder.conv1)} if hasattr(self.context_encoder, "conv1") else set()
         apply_activation_checkpointing(self, checkpoint_wrapper_fn=wrap,
-                                       check_fn=lambda m: isinstance(m, (nn.Conv2d, nn.Linear)))
+                                       check_fn=lambda m: isinstance(m, (nn.Conv2d, nn.Linear)) and id(m) not in stems)
 
     # ---- hot path ----------------------------------------------------------------------------
     def heads(self, context_f1, context_f2, target_f1, target_f2, jigsaw_idx):

@@ -357,6 +357,9 @@ class PeerReducer:
     every process) comes from ``torch.distributed._symmetric_memory``; creating a reducer is a collective."""
 
     CAPACITY = 16384  # doubles per slot: 2 * 4608 + 1 (the widest head BatchNorm) fits with room to spare
+    # how long a rank waits for its peers inside the kernel before trapping (first steps can be seconds apart while
+    # cuDNN autotunes); MSFWSI_PEER_TIMEOUT_S overrides
+    TIMEOUT_MS = int(float(__import__("os").environ.get("MSFWSI_PEER_TIMEOUT_S", "120")) * 1000)
     _cache = {}
 
     def __init__(self, group, device: torch.device):
@@ -378,7 +381,7 @@ class PeerReducer:
             raise ValueError("PeerReducer.all_reduce_: contiguous float64 vector of at most CAPACITY elements expected")
         self.seq += 1
         L.check(L.lib().msf_peer_allreduce_f64(L.ptr(vec), vec.numel(), L.ptr(self.peers), self.world, self.rank, self.seq, self.CAPACITY,
-                                               L.stream_ptr()), "msf_peer_allreduce_f64")
+                                               self.TIMEOUT_MS, L.stream_ptr()), "msf_peer_allreduce_f64")
         L.launch_count += 1
         return vec
 

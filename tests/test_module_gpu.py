@@ -201,3 +201,35 @@ def test_tc_linear_matches_cublas_autocast(rows, fin, fout, bias):
     assert _cos(gx1, gx0) >= 0.9999 and _cos(gw1, gw0) >= 0.9999
     if bias:
         assert _cos(gb1, gb0) >= 0.9999
+
+
+def test_activation_checkpointing_variant_matches_plain_model():
+    """use_checkpoint=True (backbone.py:103-127: checkpoint_wrapper over every Conv2d / Linear except the stem) gives the
+    same loss and gradients as the plain model with identical weights."""
+    import copy
+    import warnings
+    torch.manual_seed(3)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        plain = M.MSFWSI(M.resnet18, 2, 2048, 512, 0.5, False).to(DEV).to(memory_format=torch.channels_last).train()
+        ckpt = M.MSFWSI(M.resnet18, 2, 2048, 512, 0.5, True).to(DEV).to(memory_format=torch.channels_last).train()
+    sd = {k.replace("_checkpoint_wrapped_module.", ""): v for k, v in ckpt.state_dict().items()}
+    assert set(sd) == set(plain.state_dict())
+    ckpt.load_state_dict({k: plain.state_dict()[k.replace("_checkpoint_wrapped_module.", "")] for k in ckpt.state_dict()})
+    B, K = 4, 4
+    g = torch.Generator().manual_seed(4)
+    mk = lambda n: torch.randn(n, 3, 64, 64, generator=g).to(DEV).contiguous(memory_format=torch.channels_last)
+    x1, x2 = (mk(B), mk(B * K)), (mk(B), mk(B * K))
+    rev = [torch.stack([torch.randperm(K, generator=g).argsort() for _ in range(B)]).to(DEV) for _ in range(2)]
+    losses = []
+    for m in (plain, ckpt):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = m.forward_loss(x1, x2, rev, W, mode="cosine")
+        loss.backward()
+        losses.append(float(loss))
+    assert abs(losses[0] - losses[1]) <= 2e-3 * max(1.0, abs(losses[0]))
+    gp = dict(plain.named_parameters())
+    for n, p in ckpt.named_parameters():
+        q = gp[n.replace("_checkpoint_wrapped_module.", "")]
+        assert p.grad is not None and q.grad is not None, n
+    assert _cos(ckpt.context_encoder.conv1.weight.grad, plain.context_encoder.conv1.weight.grad) >= 0.99
