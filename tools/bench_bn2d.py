@@ -139,6 +139,23 @@ def main():
                 if tag == "stem":
                     rec("ATen max_pool2d fwd", nb + nb // 4 * 5, timeit(lambda: F.max_pool2d(xa, 3, 2, 1)), shape + " (+int64 indices)")
         del x, dy, y, dx
+    if not args.only or "extra" in args.only.split(","):
+        # S1: space-to-depth layout of a 4096-image (or --stem-n) bf16 NHWC batch of 224^2 views
+        from msfwsi_b200 import FusedAdam, ops
+        n_img = args.stem_n
+        img = torch.randn(n_img, 3, 224, 224, device=dev).to(dt).contiguous(memory_format=torch.channels_last)
+        out_bytes = n_img * 115 * 115 * 16 * e
+        rec("stem_s2d", img.numel() * e + out_bytes, timeit(lambda: ops.stem_s2d(img, dt)), f"({n_img},3,224,224) bf16 NHWC -> ({n_img},16,115,115)")
+        del img
+        # O1: Adam over the reference model's 123.6 M fp32 parameters (two ResNet-18 encoders + heads), three lr groups
+        sizes = [64 * 3 * 49, 64, 64] + [64 * 64 * 9] * 4 + [128 * 64 * 9, 128 * 128 * 9 * 3] + [256 * 256 * 9] * 3 + [512 * 512 * 9] * 3 + \
+                [4608 * 4608] * 3 + [2304 * 2304] * 3 + [1152 * 1152] * 3 + [576 * 576] * 3 + [512, 256, 128, 64] * 8
+        ps = [torch.randn(n, device=dev).requires_grad_(True) for n in sizes]
+        for p in ps:
+            p.grad = torch.randn_like(p)
+        third = len(ps) // 3
+        opt = FusedAdam([{"params": ps[:third]}, {"params": ps[third:2 * third], "lr": 3e-3}, {"params": ps[2 * third:]}], lr=1e-3)
+        rec("adam_multi", 28 * sum(sizes), timeit(opt.step), f"{len(sizes)} fp32 tensors, {sum(sizes) / 1e6:.1f} M parameters, 3 lr groups")
     if args.out:
         json.dump({"peak_GBps": peak, "rows": rows}, open(args.out, "w"), indent=1)
 
