@@ -231,28 +231,32 @@ int msf_bn2d_stats_finalize(const void* x, int64_t rows, int C, int dtype, float
  * the unbiased variance, like torch.nn.BatchNorm2d. */
 int msf_bn2d_finalize(const double* sums /*2C+1*/, int C, float eps, float momentum, float* mean, float* invstd,
                       float* running_mean, float* running_var, void* stream);
-/* y = act(gamma * (x - mean) * invstd + beta (+ res)); res may be NULL; relu != 0 applies max(., 0). */
-int msf_bn2d_apply(const void* x, const void* res, void* y, int64_t rows, int C, int dtype, const float* mean,
-                   const float* invstd, const float* gamma, const float* beta, int relu, void* stream);
+/* y = act(gamma * (x - mean) * invstd + beta (+ res)); res may be NULL; relu != 0 applies max(., 0).
+ * relu_bits (may be NULL): rows*C/vec bytes, one per 16-byte chunk (vec = 8 elements for 16-bit dtypes, 4 for fp32), bit i
+ * = (pre-ReLU value of element i > 0): the ReLU mask for the backward of the residual form, 16x smaller than the output. */
+int msf_bn2d_apply(const void* x, const void* res, void* y, uint8_t* relu_bits, int64_t rows, int C, int dtype,
+                   const float* mean, const float* invstd, const float* gamma, const float* beta, int relu, void* stream);
 /* gpool (may be NULL): gradient of the global average pool of the same output y (src/models/resnet.py:250-254 pools the
  * layer outputs), (N, C) in the activation dtype with hw = H*W rows per image: dy of every row of image n is taken as
  * dy + gpool[n, :] / hw, i.e. the pooled branch's gradient is folded in instead of being expanded and added by ATen.
  * Only with relu != 0 and y_mask given (the BasicBlock output); rows*C/vec must be < 2^32. */
-int msf_bn2d_bwd_reduce(const void* x, const void* dy, const void* y_mask, int64_t rows, int C, int dtype,
+/* y_mask: NULL (mask recomputed from x), the saved output y (mask_is_bits = 0), or the relu_bits of msf_bn2d_apply
+ * (mask_is_bits = 1). */
+int msf_bn2d_bwd_reduce(const void* x, const void* dy, const void* y_mask, int mask_is_bits, int64_t rows, int C, int dtype,
                         const float* mean, const float* invstd, const float* gamma, const float* beta, int relu,
                         const void* gpool, int64_t hw, double* sums_out /*2C*/, void* workspace, size_t workspace_bytes,
                         void* stream);
 /* dx = gamma*invstd * (dy' - sums[c]/count - xhat * sums[C+c]/count); dres (may be NULL) = dy'.
  * `count` is a DEVICE double (element 2C of the forward sums). */
-int msf_bn2d_bwd_elemt(const void* x, const void* dy, const void* y_mask, void* dx, void* dres, int64_t rows, int C,
-                       int dtype, const float* mean, const float* invstd, const float* gamma, const float* beta,
+int msf_bn2d_bwd_elemt(const void* x, const void* dy, const void* y_mask, int mask_is_bits, void* dx, void* dres, int64_t rows,
+                       int C, int dtype, const float* mean, const float* invstd, const float* gamma, const float* beta,
                        int relu, const void* gpool, int64_t hw, const double* sums /*2C*/, const double* count,
                        void* stream);
 /* Stem: y (N,PH,PW,C) = maxpool3x3/stride2/pad1(relu(bn(x))), x (N,H,W,C), PH = (H-1)/2+1, PW = (W-1)/2+1, N*PH*PW < 2^31.
  * tap (N,PH,PW,C) uint8 = arg-max tap dr*3+dc of each output (first maximum in scan order, ATen's max_pool2d rule),
  * 255 where the output is 0 (no gradient); x_arg (N,PH,PW,C) = the x value at the arg-max.
- * Backward: dy' lives on the pooled grid, so the reduction is msf_bn2d_bwd_reduce(x_arg, dpool, y_mask = y, rows = N*PH*PW,
- * relu = 1) -- a streaming pass over pooled-size tensors -- followed by msf_bn2d_pool_bwd_elemt, which scatters the pooled
+ * Backward: dy' lives on the pooled grid, so the reduction is msf_bn2d_bwd_reduce(x_arg, dpool, y_mask = y, mask_is_bits = 0,
+ * rows = N*PH*PW, relu = 1) -- a streaming pass over pooled-size tensors -- followed by msf_bn2d_pool_bwd_elemt, which scatters the pooled
  * gradient to the arg-max positions and applies the batch-norm input gradient in one pass over x. */
 int msf_bn2d_apply_pool(const void* x, void* y, uint8_t* tap, void* x_arg, int64_t N, int H, int W, int C, int dtype,
                         const float* mean, const float* invstd, const float* gamma, const float* beta, void* stream);

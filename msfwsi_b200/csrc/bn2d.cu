@@ -30,6 +30,7 @@ constexpr int kThreads = 256;
 // (a "column group"), kThreads/ct row lanes walk the rows.  CTA b handles the row groups b, b+G, b+2G, ... (G = grid
 // size = SMs x resident CTAs, so there is exactly one wave and all CTAs sweep memory together).
 constexpr int kMaxRowBlocks = kNumSMs * 8;
+constexpr int kStatsMaxBlocks = 640;  // row blocks of the forward statistics kernel (one wave at 4 CTAs/SM is 592)
 struct Layout {
   int cvec;     // 16-byte chunks per row
   int ct;       // chunks per column group handled by one CTA (power of two <= 32)
@@ -167,23 +168,33 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 __device__ __forceinline__ Moments channel_moments(const float* __restrict__ partial, const float* __restrict__ cnt, int nblk, int C,
                                                    int ch, int lane) {
+  // the partials are few (<= 1184 blocks) but sit in L2: the loads of four blocks are issued together and the values kept
+  // in registers for the second pass (the statistics kernel runs at most kStatsMaxBlocks = 640 row blocks: 20 per lane)
+  constexpr int kMine = kStatsMaxBlocks / 32;
+  float nb[kMine], sd[kMine], sq[kMine], kk[kMine];
+#pragma unroll
+  for (int j = 0; j < kMine; ++j) {
+    const int b = lane + 32 * j;
+    const bool in = b < nblk;
+    nb[j] = in ? __ldg(cnt + b) : 0.f;
+    sd[j] = in ? __ldg(partial + (static_cast<size_t>(b) * 3 + 0) * C + ch) : 0.f;
+    sq[j] = in ? __ldg(partial + (static_cast<size_t>(b) * 3 + 1) * C + ch) : 0.f;
+    kk[j] = in ? __ldg(partial + (static_cast<size_t>(b) * 3 + 2) * C + ch) : 0.f;
+  }
   double n = 0.0, s1 = 0.0;
-  for (int b = lane; b < nblk; b += 32) {
-    const double nb = static_cast<double>(cnt[b]);
-    n += nb;
-    s1 += nb * static_cast<double>(partial[(static_cast<size_t>(b) * 3 + 2) * C + ch]) +
-          static_cast<double>(partial[(static_cast<size_t>(b) * 3 + 0) * C + ch]);
+#pragma unroll
+  for (int j = 0; j < kMine; ++j) {
+    n += static_cast<double>(nb[j]);
+    s1 += static_cast<double>(nb[j]) * static_cast<double>(kk[j]) + static_cast<double>(sd[j]);
   }
   n = warp_sum(n);
   s1 = warp_sum(s1);
   const double mean = s1 / n;
   double m2 = 0.0;
-  for (int b = lane; b < nblk; b += 32) {
-    const double nb = static_cast<double>(cnt[b]);
-    const double sd = static_cast<double>(partial[(static_cast<size_t>(b) * 3 + 0) * C + ch]);
-    const double sq = static_cast<double>(partial[(static_cast<size_t>(b) * 3 + 1) * C + ch]);
-    const double delta = static_cast<double>(partial[(static_cast<size_t>(b) * 3 + 2) * C + ch]) - mean;
-    m2 += sq + delta * (2.0 * sd + nb * delta);  // blocks without rows have nb = sd = sq = 0
+#pragma unroll
+  for (int j = 0; j < kMine; ++j) {
+    const double delta = static_cast<double>(kk[j]) - mean;
+    m2 += static_cast<double>(sq[j]) + delta * (2.0 * static_cast<double>(sd[j]) + static_cast<double>(nb[j]) * delta);  // empty blocks: all zero
   }
   m2 = fmax(warp_sum(m2), 0.0);
   return Moments{n, mean, m2, s1};
@@ -212,8 +223,13 @@ __global__ void __launch_bounds__(kCombineWarps * 32) bn_combine_kernel(const fl
   const int e = blockIdx.x * kCombineWarps + (threadIdx.x >> 5);
   if (blockIdx.x == 0 && threadIdx.x == 0 && count >= 0.0) sums[2 * C] = count;
   if (e >= 2 * C) return;
+  constexpr int kMine = (kMaxRowBlocks + 31) / 32;
+  float v[kMine];
+#pragma unroll
+  for (int j = 0; j < kMine; ++j) v[j] = (lane + 32 * j < nblk) ? __ldg(partial + static_cast<size_t>(lane + 32 * j) * 2 * C + e) : 0.f;  // loads in flight together
   double t = 0.0;
-  for (int b = lane; b < nblk; b += 32) t += static_cast<double>(partial[static_cast<size_t>(b) * 2 * C + e]);
+#pragma unroll
+  for (int j = 0; j < kMine; ++j) t += static_cast<double>(v[j]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
   if (lane == 0) sums[e] = t;
@@ -275,9 +291,11 @@ struct ChanConst {
   }
 };
 
+// `bits` (may be NULL): one byte per 16-byte chunk, bit i = (pre-ReLU value of element i > 0) -- the ReLU mask the
+// backward needs when a residual was added, 16x smaller than re-reading the bf16 output.
 template <int DT, bool RES>
 __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const char* __restrict__ x, const char* __restrict__ res,
-                                                            char* __restrict__ y, int64_t chunks, int cvec,
+                                                            char* __restrict__ y, unsigned char* __restrict__ bits, int64_t chunks, int cvec,
                                                             const float* __restrict__ mean, const float* __restrict__ invstd,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta, int relu) {
   constexpr int V = Elem<DT>::VEC;
@@ -302,19 +320,22 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const char* __restri
       float f[V], g[V];
       Elem<DT>::unpack(v[u], f);
       if (RES) Elem<DT>::unpack(w[u], g);
+      uint32_t alive = 0;
 #pragma unroll
       for (int i = 0; i < V; ++i) {
         float o = fmaf(f[i], k.sc[i], k.sh[i]);
         if (RES) o += g[i];
+        alive |= (o > 0.f ? 1u : 0u) << i;
         if (relu) o = fmaxf(o, 0.f);
         f[i] = o;
       }
       stg_stream(y + idx * 16, Elem<DT>::pack(f));
+      if (bits) bits[idx] = static_cast<unsigned char>(alive);
     }
   }
 }
 
-// MASK: 0 none, 1 relu mask recomputed from x, 2 relu mask from the saved output y
+// MASK: 0 none, 1 relu mask recomputed from x, 2 relu mask from the saved output y, 3 relu mask from one bit per element
 constexpr int kReduceRows = 4;  // rows in flight per thread (x 2 or 3 tensors)
 // GP: a per-(image, channel) gradient gp[n][c] * gp_scale is added to every dy of that image before the mask (the
 // backward of a global average pool over the same output, folded in instead of being materialised and added).
@@ -351,6 +372,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const char* __r
         a[u] = ldg_stream(x + (rr * cvec + chunk) * 16);
         b[u] = ldg_stream(dy + (rr * cvec + chunk) * 16);
         if (MASK == 2) m[u] = ldg_stream(ymask + (rr * cvec + chunk) * 16);
+        if (MASK == 3) m[u].x = __ldg(reinterpret_cast<const unsigned char*>(ymask) + rr * cvec + chunk);
         if (GP) p[u] = ldg_keep(gp + (static_cast<int64_t>(static_cast<unsigned>(rr) / hw) * cvec + chunk) * 16);
       }
     }
@@ -366,6 +388,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const char* __r
         float d = GP ? fmaf(fp[i], gp_scale, fd[i]) : fd[i];
         if (MASK == 1 && fmaf(fx[i], k.sc[i], k.sh[i]) <= 0.f) d = 0.f;
         if (MASK == 2 && fm[i] <= 0.f) d = 0.f;
+        if (MASK == 3 && !((m[u].x >> i) & 1u)) d = 0.f;
         s[i] += d;
         q[i] = fmaf(d, (fx[i] - mu[i]) * is[i], q[i]);
       }
@@ -426,6 +449,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_elemt_kernel(const char* __re
         vx[u] = ldg_stream(x + idx * 16);
         vd[u] = ldg_stream(dy + idx * 16);
         if (MASK == 2) vm[u] = ldg_stream(ymask + idx * 16);
+        if (MASK == 3) vm[u].x = __ldg(reinterpret_cast<const unsigned char*>(ymask) + idx);
         if (GP) {  // chunk (n, c) of the pooled gradient; 32-bit index math (the ABI requires rows*cvec < 2^32 here)
           const unsigned i32 = static_cast<unsigned>(idx);
           vp[u] = ldg_keep(gp + (static_cast<int64_t>(i32 / hw_chunks) * cvec + i32 % static_cast<unsigned>(cvec)) * 16);
@@ -446,6 +470,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_elemt_kernel(const char* __re
         float d = GP ? fmaf(fp[i], gp_scale, fd[i]) : fd[i];
         if (MASK == 1 && fmaf(fx[i], g.sc[i], sh[i]) <= 0.f) d = 0.f;
         if (MASK == 2 && fm[i] <= 0.f) d = 0.f;
+        if (MASK == 3 && !((vm[u].x >> i) & 1u)) d = 0.f;
         fd[i] = d;
         fx[i] = fmaf(g.sc[i], d, fmaf(g.ca[i], fx[i], g.cb[i]));
       }
@@ -856,6 +881,7 @@ int bn_stats_impl(const void* x, int64_t rows, int C, int dtype, double* sums_ou
   ProfScope prof(stream, MSF_K_BN_STATS, static_cast<double>(rows) * C * dtype_size(dtype));
   MSF_DISPATCH_DTYPE(dtype, {
     nblk = reduce_grid(bn_stats_kernel<DT>, smem, l, rows, l.rlanes);
+    if (nblk > kStatsMaxBlocks) nblk = kStatsMaxBlocks;
     dim3 grid(static_cast<unsigned>(nblk), static_cast<unsigned>(l.cgroups));
     bn_stats_kernel<DT><<<grid, kThreads, smem, st>>>(static_cast<const char*>(x), rows, l.cvec, l.ct, partial, cnt);
   });
@@ -882,8 +908,8 @@ extern "C" int msf_bn2d_finalize(const double* sums, int C, float eps, float mom
   return MSF_OK;
 }
 
-extern "C" int msf_bn2d_apply(const void* x, const void* res, void* y, int64_t rows, int C, int dtype, const float* mean,
-                              const float* invstd, const float* gamma, const float* beta, int relu, void* stream) {
+extern "C" int msf_bn2d_apply(const void* x, const void* res, void* y, uint8_t* relu_bits, int64_t rows, int C, int dtype,
+                              const float* mean, const float* invstd, const float* gamma, const float* beta, int relu, void* stream) {
   if (int rc = check_bn(x, rows, C, dtype)) return rc;
   MSF_REQUIRE(y && aligned16(y) && aligned16(res) && mean && invstd, MSF_ERR_INVALID, "bad arguments");
   const int vec = 16 / static_cast<int>(dtype_size(dtype));
@@ -893,11 +919,11 @@ extern "C" int msf_bn2d_apply(const void* x, const void* res, void* y, int64_t r
   const char* xp = static_cast<const char*>(x);
   const char* rp = static_cast<const char*>(res);
   char* yp = static_cast<char*>(y);
-  ProfScope prof(stream, res ? MSF_K_BN_APPLY_RES : MSF_K_BN_APPLY, static_cast<double>(rows) * C * dtype_size(dtype) * (res ? 3 : 2));
+  ProfScope prof(stream, res ? MSF_K_BN_APPLY_RES : MSF_K_BN_APPLY, static_cast<double>(rows) * C * dtype_size(dtype) * (res ? 3 : 2) + (relu_bits ? static_cast<double>(chunks) : 0.0));
   if (res) {
-    MSF_DISPATCH_DTYPE(dtype, (bn_apply_kernel<DT, true><<<wave_grid(bn_apply_kernel<DT, true>, (chunks + 1) / 2, cvec), kThreads, 0, st>>>(xp, rp, yp, chunks, cvec, mean, invstd, gamma, beta, relu)));
+    MSF_DISPATCH_DTYPE(dtype, (bn_apply_kernel<DT, true><<<wave_grid(bn_apply_kernel<DT, true>, (chunks + 1) / 2, cvec), kThreads, 0, st>>>(xp, rp, yp, relu_bits, chunks, cvec, mean, invstd, gamma, beta, relu)));
   } else {
-    MSF_DISPATCH_DTYPE(dtype, (bn_apply_kernel<DT, false><<<wave_grid(bn_apply_kernel<DT, false>, (chunks + 3) / 4, cvec), kThreads, 0, st>>>(xp, rp, yp, chunks, cvec, mean, invstd, gamma, beta, relu)));
+    MSF_DISPATCH_DTYPE(dtype, (bn_apply_kernel<DT, false><<<wave_grid(bn_apply_kernel<DT, false>, (chunks + 3) / 4, cvec), kThreads, 0, st>>>(xp, rp, yp, relu_bits, chunks, cvec, mean, invstd, gamma, beta, relu)));
   }
   MSF_LAUNCH_OK("bn_apply_kernel");
   return MSF_OK;
@@ -916,12 +942,13 @@ int check_gp(const void* gp, int64_t hw, int64_t rows, int C, int dtype, const v
 }
 }  // namespace
 
-extern "C" int msf_bn2d_bwd_reduce(const void* x, const void* dy, const void* y_mask, int64_t rows, int C, int dtype,
+extern "C" int msf_bn2d_bwd_reduce(const void* x, const void* dy, const void* y_mask, int mask_is_bits, int64_t rows, int C, int dtype,
                                    const float* mean, const float* invstd, const float* gamma, const float* beta, int relu,
                                    const void* gpool, int64_t hw, double* sums_out, void* workspace, size_t workspace_bytes,
                                    void* stream) {
   if (int rc = check_bn(x, rows, C, dtype)) return rc;
-  MSF_REQUIRE(dy && aligned16(dy) && aligned16(y_mask) && mean && invstd && sums_out, MSF_ERR_INVALID, "bad arguments");
+  MSF_REQUIRE(dy && aligned16(dy) && (mask_is_bits || aligned16(y_mask)) && mean && invstd && sums_out, MSF_ERR_INVALID, "bad arguments");
+  MSF_REQUIRE(!mask_is_bits || (y_mask && relu), MSF_ERR_INVALID, "mask_is_bits needs relu and a mask pointer");
   if (int rc = check_gp(gpool, hw, rows, C, dtype, y_mask, relu)) return rc;
   const char* gpp = static_cast<const char*>(gpool);
   const unsigned hw32 = gpool ? static_cast<unsigned>(hw) : 1u;
@@ -936,7 +963,8 @@ extern "C" int msf_bn2d_bwd_reduce(const void* x, const void* dy, const void* y_
   const char* dp = static_cast<const char*>(dy);
   const char* mp = static_cast<const char*>(y_mask);
   int nblk = 1;
-  ProfScope prof(stream, MSF_K_BN_BWD_REDUCE, static_cast<double>(rows) * C * dtype_size(dtype) * ((relu && y_mask) ? 3 : 2));
+  ProfScope prof(stream, MSF_K_BN_BWD_REDUCE, static_cast<double>(rows) * C * (dtype_size(dtype) * ((relu && y_mask && !mask_is_bits) ? 3 : 2) +
+                                                                             (mask_is_bits ? 1.0 / vec : 0.0)));
 #define MSF_BWD_REDUCE(MASK, GP)                                                                                      \
   MSF_DISPATCH_DTYPE(dtype, {                                                                                         \
     nblk = reduce_grid(bn_bwd_reduce_kernel<DT, MASK, GP>, smem, l, rows, kReduceRows * l.rlanes);                    \
@@ -946,8 +974,10 @@ extern "C" int msf_bn2d_bwd_reduce(const void* x, const void* dy, const void* y_
   })
   if (!relu) { MSF_BWD_REDUCE(0, false); }
   else if (!y_mask) { MSF_BWD_REDUCE(1, false); }
-  else if (!gpool) { MSF_BWD_REDUCE(2, false); }
-  else { MSF_BWD_REDUCE(2, true); }
+  else if (!mask_is_bits && !gpool) { MSF_BWD_REDUCE(2, false); }
+  else if (!mask_is_bits) { MSF_BWD_REDUCE(2, true); }
+  else if (!gpool) { MSF_BWD_REDUCE(3, false); }
+  else { MSF_BWD_REDUCE(3, true); }
 #undef MSF_BWD_REDUCE
   MSF_LAUNCH_OK("bn_bwd_reduce_kernel");
   bn_combine_kernel<<<(2 * C + kCombineWarps - 1) / kCombineWarps, kCombineWarps * 32, 0, st>>>(partial, nblk, C, sums_out, -1.0);
@@ -955,15 +985,16 @@ extern "C" int msf_bn2d_bwd_reduce(const void* x, const void* dy, const void* y_
   return MSF_OK;
 }
 
-extern "C" int msf_bn2d_bwd_elemt(const void* x, const void* dy, const void* y_mask, void* dx, void* dres, int64_t rows, int C,
-                                  int dtype, const float* mean, const float* invstd, const float* gamma, const float* beta,
+extern "C" int msf_bn2d_bwd_elemt(const void* x, const void* dy, const void* y_mask, int mask_is_bits, void* dx, void* dres, int64_t rows,
+                                  int C, int dtype, const float* mean, const float* invstd, const float* gamma, const float* beta,
                                   int relu, const void* gpool, int64_t hw, const double* sums, const double* count, void* stream) {
   if (int rc = check_bn(x, rows, C, dtype)) return rc;
   if (int rc = check_gp(gpool, hw, rows, C, dtype, y_mask, relu)) return rc;
   const char* gpp = static_cast<const char*>(gpool);
   const float gp_scale = gpool ? 1.f / static_cast<float>(hw) : 0.f;
-  MSF_REQUIRE(dy && dx && aligned16(dy) && aligned16(dx) && aligned16(y_mask) && aligned16(dres) && mean && invstd && sums && count,
+  MSF_REQUIRE(dy && dx && aligned16(dy) && aligned16(dx) && (mask_is_bits || aligned16(y_mask)) && aligned16(dres) && mean && invstd && sums && count,
               MSF_ERR_INVALID, "bad arguments");
+  MSF_REQUIRE(!mask_is_bits || (y_mask && relu), MSF_ERR_INVALID, "mask_is_bits needs relu and a mask pointer");
   const int vec = 16 / static_cast<int>(dtype_size(dtype));
   const int cvec = C / vec;
   const int64_t chunks = rows * cvec;
@@ -974,19 +1005,24 @@ extern "C" int msf_bn2d_bwd_elemt(const void* x, const void* dy, const void* y_m
   const char* mp = static_cast<const char*>(y_mask);
   char* dxp = static_cast<char*>(dx);
   char* drp = static_cast<char*>(dres);
-  ProfScope prof(stream, MSF_K_BN_BWD_ELEMT, static_cast<double>(rows) * C * dtype_size(dtype) * (3 + ((relu && y_mask) ? 1 : 0) + (dres ? 1 : 0)));
+  ProfScope prof(stream, MSF_K_BN_BWD_ELEMT, static_cast<double>(rows) * C * (dtype_size(dtype) * (3 + ((relu && y_mask && !mask_is_bits) ? 1 : 0) + (dres ? 1 : 0)) +
+                                                                            (mask_is_bits ? 1.0 / vec : 0.0)));
   const unsigned hwc = gpool ? static_cast<unsigned>(hw * cvec) : 1u;
 #define MSF_BWD_ELEMT(MASK, DRES, GP) \
   MSF_DISPATCH_DTYPE(dtype, (bn_bwd_elemt_kernel<DT, MASK, DRES, GP><<<wave_grid(bn_bwd_elemt_kernel<DT, MASK, DRES, GP>, per_thread_total, cvec), kThreads, 0, st>>>(xp, dp, mp, dxp, drp, chunks, cvec, mean, invstd, gamma, beta, sums, count, gpp, hwc, gp_scale)))
-  const int mask = !relu ? 0 : (y_mask ? 2 : 1);
+  const int mask = !relu ? 0 : (y_mask ? (mask_is_bits ? 3 : 2) : 1);
   if (mask == 0 && !dres) { MSF_BWD_ELEMT(0, false, false); }
   else if (mask == 0) { MSF_BWD_ELEMT(0, true, false); }
   else if (mask == 1 && !dres) { MSF_BWD_ELEMT(1, false, false); }
   else if (mask == 1) { MSF_BWD_ELEMT(1, true, false); }
-  else if (!dres && !gpool) { MSF_BWD_ELEMT(2, false, false); }
-  else if (!gpool) { MSF_BWD_ELEMT(2, true, false); }
-  else if (!dres) { MSF_BWD_ELEMT(2, false, true); }
-  else { MSF_BWD_ELEMT(2, true, true); }
+  else if (mask == 2 && !dres && !gpool) { MSF_BWD_ELEMT(2, false, false); }
+  else if (mask == 2 && !gpool) { MSF_BWD_ELEMT(2, true, false); }
+  else if (mask == 2 && !dres) { MSF_BWD_ELEMT(2, false, true); }
+  else if (mask == 2) { MSF_BWD_ELEMT(2, true, true); }
+  else if (!dres && !gpool) { MSF_BWD_ELEMT(3, false, false); }
+  else if (!gpool) { MSF_BWD_ELEMT(3, true, false); }
+  else if (!dres) { MSF_BWD_ELEMT(3, false, true); }
+  else { MSF_BWD_ELEMT(3, true, true); }
 #undef MSF_BWD_ELEMT
   MSF_LAUNCH_OK("bn_bwd_elemt_kernel");
   return MSF_OK;

@@ -19,35 +19,38 @@ __device__ __forceinline__ float ld_elem(const void* p, int64_t i) {
   else return __half2float(__ldg(static_cast<const __half*>(p) + i));
 }
 
+// One CTA per output row (n, oy): a single division per CTA, threads walk the row's pixels.
 template <int IDT, int ODT>
-__global__ void __launch_bounds__(256) stem_s2d_kernel(const void* __restrict__ x, char* __restrict__ out, int64_t total /*N*OH*OW*/,
-                                                       int cin, int H, int W, int OH, int OW, int64_t sn, int64_t sc, int64_t sy,
-                                                       int64_t sx) {
+__global__ void __launch_bounds__(128) stem_s2d_kernel(const void* __restrict__ x, char* __restrict__ out, int cin, int H, int W, int OH,
+                                                       int OW, int64_t sn, int64_t sc, int64_t sy, int64_t sx) {
   constexpr int OV = Elem<ODT>::VEC;      // output elements per 16-byte chunk
   constexpr int CHUNKS = 16 / OV;         // 16 channels = 2 chunks (16-bit) or 4 chunks (fp32)
-  for (int64_t e = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; e < total; e += static_cast<int64_t>(gridDim.x) * 256) {
-    const int ox = static_cast<int>(e % OW);
-    const int64_t t = e / OW;
-    const int oy = static_cast<int>(t % OH);
-    const int64_t n = t / OH;
+  const int64_t row = blockIdx.x;         // n * OH + oy
+  const int oy = static_cast<int>(row % OH);
+  const int64_t n = row / OH;
+  const int y0 = 2 * oy - 3;
+  const bool oky[2] = {y0 >= 0 && y0 < H, y0 + 1 >= 0 && y0 + 1 < H};
+  const int64_t base_row = n * sn + y0 * sy;
+  char* orow = out + row * OW * (16 * (16 / OV));
+  for (int ox = threadIdx.x; ox < OW; ox += 128) {
     float v[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) v[k] = 0.f;
+    const int x0 = 2 * ox - 3;
 #pragma unroll
     for (int dy = 0; dy < 2; ++dy) {
-      const int y = 2 * oy + dy - 3;
-      if (y < 0 || y >= H) continue;
+      if (!oky[dy]) continue;
 #pragma unroll
       for (int dx = 0; dx < 2; ++dx) {
-        const int xx = 2 * ox + dx - 3;
+        const int xx = x0 + dx;
         if (xx < 0 || xx >= W) continue;
-        const int64_t base = n * sn + y * sy + xx * sx;
+        const int64_t base = base_row + dy * sy + xx * sx;
 #pragma unroll
         for (int c = 0; c < 4; ++c)
           if (c < cin) v[c * 4 + dy * 2 + dx] = ld_elem<IDT>(x, base + c * sc);
       }
     }
-    char* o = out + e * (16 * (16 / OV));  // 16 channels * element size
+    char* o = orow + static_cast<int64_t>(ox) * (16 * (16 / OV));
 #pragma unroll
     for (int k = 0; k < CHUNKS; ++k) stg_stream(o + k * 16, Elem<ODT>::pack(v + k * OV));
   }
@@ -67,14 +70,13 @@ extern "C" int msf_stem_s2d(const void* x, int64_t N, int C_in, int H, int W, in
   MSF_REQUIRE(x && out && aligned16(out), MSF_ERR_INVALID, "NULL or misaligned pointer");
   const int OH = (H + 6) / 2, OW = (W + 6) / 2;
   const int64_t total = N * OH * OW;
-  int64_t blocks = (total + 255) / 256;
-  const int64_t cap = static_cast<int64_t>(kNumSMs) * 16;
-  if (blocks > cap) blocks = cap;
+  const int64_t blocks = N * OH;  // one CTA per output row
+  MSF_REQUIRE(blocks < (int64_t{1} << 31), MSF_ERR_UNSUPPORTED, "N*(H+6)/2 = %lld must be < 2^31", static_cast<long long>(blocks));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ProfScope prof(stream, MSF_K_STEM_S2D, static_cast<double>(N) * C_in * H * W * dtype_size(in_dtype) + static_cast<double>(total) * 16 * dtype_size(out_dtype));
 #define MSF_S2D(I, O)                                                                                                               \
   if (in_dtype == I && out_dtype == O) {                                                                                            \
-    stem_s2d_kernel<I, O><<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, static_cast<char*>(out), total, C_in, H, W, OH, OW,     \
+    stem_s2d_kernel<I, O><<<static_cast<unsigned>(blocks), 128, 0, st>>>(x, static_cast<char*>(out), C_in, H, W, OH, OW,            \
                                                                          stride_n, stride_c, stride_y, stride_x);                 \
     MSF_LAUNCH_OK("stem_s2d_kernel");                                                                                               \
     return MSF_OK;                                                                                                                  \

@@ -389,7 +389,7 @@ class PeerReducer:
     def get(cls, group, device: torch.device):
         """The reducer of (group, device), created on first use (collectively).  If symmetric memory cannot be set up
         on ANY rank, all ranks agree to use NCCL instead (returns None)."""
-        key = (id(group), device.index)
+        key = (getattr(group, "group_name", None) or id(group), device.index)
         if key not in cls._cache:
             red, ok = None, 1
             try:
@@ -458,7 +458,7 @@ class _BNAct2d(torch.autograd.Function):
         else:
             L.check(lib.msf_bn2d_stats_finalize(L.ptr(x), rows, Cc, code, eps, momentum, L.ptr(sums), L.ptr(mean), L.ptr(invstd),
                                                 L.ptr(running_mean), L.ptr(running_var), L.ptr(ws), ws_bytes, st), "msf_bn2d_stats_finalize")
-        tap = x_arg = None
+        tap = x_arg = bits = None
         if pool:
             PH, PW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
             y = torch.empty((N, Cc, PH, PW), dtype=dt, device=dev, memory_format=torch.channels_last)
@@ -473,11 +473,14 @@ class _BNAct2d(torch.autograd.Function):
                     raise ValueError(f"bn_act2d: residual {tuple(residual.shape)} {residual.dtype} vs x {tuple(x.shape)} {dt}")
                 res = residual if flat else _nhwc(residual)
             y = torch.empty_like(x) if flat else torch.empty_like(x, memory_format=torch.channels_last)
-            L.check(lib.msf_bn2d_apply(L.ptr(x), L.ptr(res), L.ptr(y), rows, Cc, code, L.ptr(mean), L.ptr(invstd), L.ptr(gamma), L.ptr(beta),
-                                       int(relu), st), "msf_bn2d_apply")
+            # with a residual the ReLU mask cannot be recomputed from x alone: one bit per element is written here
+            # (16x less backward traffic than re-reading the bf16 output in both backward passes)
+            if residual is not None and relu:
+                bits = torch.empty(rows * Cc // (16 // x.element_size()), dtype=torch.uint8, device=dev)
+            L.check(lib.msf_bn2d_apply(L.ptr(x), L.ptr(res), L.ptr(y), L.ptr(bits), rows, Cc, code, L.ptr(mean), L.ptr(invstd), L.ptr(gamma),
+                                       L.ptr(beta), int(relu), st), "msf_bn2d_apply")
         L.launch_count += 4
-        # with a residual the ReLU mask of the backward comes from the output (no extra memory: the next layer keeps it anyway)
-        y_mask = y if ((residual is not None and relu) or pool) else None
+        y_mask = y if pool else bits  # stem: the pooled output is the mask of the pooled-grid reduction
         ctx.save_for_backward(x, gamma, beta, mean, invstd, sums, y_mask, tap, x_arg)
         ctx.meta = (N, Cc, H, W, code, relu, pool, residual is not None, sync_group, world,
                     None if weight is None else weight.dtype, None if bias is None else bias.dtype, want_mean, flat)
@@ -514,12 +517,12 @@ class _BNAct2d(torch.autograd.Function):
             ws_bytes = lib.msf_bn2d_workspace_bytes(N * PH * PW, Cc)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             # dy' lives on the pooled grid: reduce over (x at the arg-max, pooled gradient, pooled output as ReLU mask)
-            L.check(lib.msf_bn2d_bwd_reduce(L.ptr(x_arg), L.ptr(gy), L.ptr(y_mask), N * PH * PW, Cc, code, L.ptr(mean), L.ptr(invstd),
+            L.check(lib.msf_bn2d_bwd_reduce(L.ptr(x_arg), L.ptr(gy), L.ptr(y_mask), 0, N * PH * PW, Cc, code, L.ptr(mean), L.ptr(invstd),
                                             L.ptr(gamma), L.ptr(beta), 1, None, 0, L.ptr(sums), L.ptr(ws), ws_bytes, st), "msf_bn2d_bwd_reduce")
         else:
             ws_bytes = lib.msf_bn2d_workspace_bytes(rows, Cc)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            L.check(lib.msf_bn2d_bwd_reduce(L.ptr(x), L.ptr(gy), L.ptr(y_mask), rows, Cc, code, L.ptr(mean), L.ptr(invstd), L.ptr(gamma),
+            L.check(lib.msf_bn2d_bwd_reduce(L.ptr(x), L.ptr(gy), L.ptr(y_mask), int(y_mask is not None), rows, Cc, code, L.ptr(mean), L.ptr(invstd), L.ptr(gamma),
                                             L.ptr(beta), int(relu), L.ptr(gp), hw, L.ptr(sums), L.ptr(ws), ws_bytes, st), "msf_bn2d_bwd_reduce")
         # parameter gradients are the LOCAL sums (DDP averages them over ranks, as with SyncBatchNorm)
         gw = None if wdt is None else sums[Cc:].to(wdt)
@@ -532,7 +535,7 @@ class _BNAct2d(torch.autograd.Function):
         else:
             if has_res and ctx.needs_input_grad[3]:
                 dres = like(x)
-            L.check(lib.msf_bn2d_bwd_elemt(L.ptr(x), L.ptr(gy), L.ptr(y_mask), L.ptr(dx), L.ptr(dres), rows, Cc, code, L.ptr(mean),
+            L.check(lib.msf_bn2d_bwd_elemt(L.ptr(x), L.ptr(gy), L.ptr(y_mask), int(y_mask is not None), L.ptr(dx), L.ptr(dres), rows, Cc, code, L.ptr(mean),
                                            L.ptr(invstd), L.ptr(gamma), L.ptr(beta), int(relu), L.ptr(gp), hw, L.ptr(sums), count_ptr, st),
                     "msf_bn2d_bwd_elemt")
         L.launch_count += 3

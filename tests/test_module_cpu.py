@@ -100,3 +100,36 @@ def test_checkpoint_layout_matches_reference_driver(model, golden_dir, tmp_path)
     assert all(torch.equal(a, b) for a, b in zip(fresh.state_dict().values(), model.state_dict().values()))
     torch.save({"epoch": 3, "state_dict": model.state_dict()}, path)
     assert CK.load_checkpoint(path, fresh) == 3
+
+
+def test_stem_space_to_depth_weight_identity_on_cpu():
+    """S1 host logic: conv7x7/2(x, w) == conv4x4/1(pad + pixel_unshuffle(x), stem_s2d_weight(w)) (resnet.py:155), and the
+    rearrangement is differentiable back to the (O, 3, 7, 7) parameter."""
+    import torch.nn.functional as F
+    from msfwsi_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 3, 16, 20, dtype=torch.float64, generator=g)
+    w = torch.randn(5, 3, 7, 7, dtype=torch.float64, generator=g, requires_grad=True)
+    xs = F.pad(F.pixel_unshuffle(F.pad(x, (3, 3, 3, 3)), 2), (0, 0, 0, 0, 0, 4))  # what msf_stem_s2d produces on the device
+    y = F.conv2d(xs, ops.stem_s2d_weight(w))
+    y_ref = F.conv2d(x, w, None, 2, 3)
+    assert torch.allclose(y, y_ref, rtol=1e-12, atol=1e-12)
+    gy = torch.randn(y.shape, dtype=torch.float64, generator=g)
+    (gw,) = torch.autograd.grad(y, w, gy, retain_graph=True)
+    (gw_ref,) = torch.autograd.grad(y_ref, w, gy)
+    assert gw.shape == (5, 3, 7, 7) and torch.allclose(gw, gw_ref, rtol=1e-12, atol=1e-12)
+    with pytest.raises(ValueError):
+        ops.stem_s2d_weight(torch.zeros(4, 3, 3, 3))
+
+
+def test_product_ops_refuse_cpu_tensors():
+    """No CPU fallback anywhere in the product path: the operators and the optimizer raise on CPU tensors."""
+    from msfwsi_b200 import FusedAdam, ops
+    with pytest.raises(RuntimeError):
+        ops.bn_act2d(torch.zeros(2, 8, 2, 2), None, None, None, None)
+    with pytest.raises(RuntimeError):
+        ops.stem_s2d(torch.zeros(1, 3, 4, 4))
+    p = torch.nn.Parameter(torch.zeros(4))
+    p.grad = torch.ones(4)
+    with pytest.raises(RuntimeError):
+        FusedAdam([p], lr=1e-3).step()

@@ -82,29 +82,30 @@ def main():
         f_stats = lambda: L.check(lib.msf_bn2d_stats(x.data_ptr(), rows_, C, code, sums.data_ptr(), ws.data_ptr(), wsb, st), "stats")
         rec("bn_stats", nb, timeit(f_stats), shape)
         L.check(lib.msf_bn2d_finalize(sums.data_ptr(), C, 1e-5, 0.1, mean.data_ptr(), invstd.data_ptr(), None, None, st), "fin")
-        f_apply = lambda: L.check(lib.msf_bn2d_apply(x.data_ptr(), None, y.data_ptr(), rows_, C, code, mean.data_ptr(), invstd.data_ptr(),
+        f_apply = lambda: L.check(lib.msf_bn2d_apply(x.data_ptr(), None, y.data_ptr(), None, rows_, C, code, mean.data_ptr(), invstd.data_ptr(),
                                                      gamma.data_ptr(), beta.data_ptr(), 1, st), "apply")
         rec("bn_apply+relu", 2 * nb, timeit(f_apply), shape)
-        f_red = lambda: L.check(lib.msf_bn2d_bwd_reduce(x.data_ptr(), dy.data_ptr(), None, rows_, C, code, mean.data_ptr(), invstd.data_ptr(),
+        f_red = lambda: L.check(lib.msf_bn2d_bwd_reduce(x.data_ptr(), dy.data_ptr(), None, 0, rows_, C, code, mean.data_ptr(), invstd.data_ptr(),
                                                         gamma.data_ptr(), beta.data_ptr(), 1, None, 0, sums2.data_ptr(), ws.data_ptr(), wsb, st), "red")
         rec("bn_bwd_reduce (relu mask recomputed)", 2 * nb, timeit(f_red), shape)
-        f_el = lambda: L.check(lib.msf_bn2d_bwd_elemt(x.data_ptr(), dy.data_ptr(), None, dx.data_ptr(), None, rows_, C, code, mean.data_ptr(),
+        f_el = lambda: L.check(lib.msf_bn2d_bwd_elemt(x.data_ptr(), dy.data_ptr(), None, 0, dx.data_ptr(), None, rows_, C, code, mean.data_ptr(),
                                                       invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1, None, 0, sums2.data_ptr(), cnt, st), "el")
         rec("bn_bwd_elemt (relu mask recomputed)", 3 * nb, timeit(f_el), shape)
         if tag != "stem":
             res, dres = torch.randn_like(x), torch.empty_like(x)
-            f_apply_r = lambda: L.check(lib.msf_bn2d_apply(x.data_ptr(), res.data_ptr(), y.data_ptr(), rows_, C, code, mean.data_ptr(),
+            bits = torch.empty(x.numel() // 8, dtype=torch.uint8, device=dev)
+            f_apply_r = lambda: L.check(lib.msf_bn2d_apply(x.data_ptr(), res.data_ptr(), y.data_ptr(), bits.data_ptr(), rows_, C, code, mean.data_ptr(),
                                                            invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1, st), "apply")
-            rec("bn_apply+residual+relu", 3 * nb, timeit(f_apply_r), shape)
-            f_red_r = lambda: L.check(lib.msf_bn2d_bwd_reduce(x.data_ptr(), dy.data_ptr(), y.data_ptr(), rows_, C, code, mean.data_ptr(),
+            rec("bn_apply+residual+relu (+mask bits)", 3 * nb + nb // 16, timeit(f_apply_r), shape)
+            f_red_r = lambda: L.check(lib.msf_bn2d_bwd_reduce(x.data_ptr(), dy.data_ptr(), bits.data_ptr(), 1, rows_, C, code, mean.data_ptr(),
                                                               invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1, None, 0, sums2.data_ptr(), ws.data_ptr(),
                                                               wsb, st), "red")
-            rec("bn_bwd_reduce (mask from y)", 3 * nb, timeit(f_red_r), shape)
-            f_el_r = lambda: L.check(lib.msf_bn2d_bwd_elemt(x.data_ptr(), dy.data_ptr(), y.data_ptr(), dx.data_ptr(), dres.data_ptr(), rows_, C, code,
+            rec("bn_bwd_reduce (mask bits)", 2 * nb + nb // 16, timeit(f_red_r), shape)
+            f_el_r = lambda: L.check(lib.msf_bn2d_bwd_elemt(x.data_ptr(), dy.data_ptr(), bits.data_ptr(), 1, dx.data_ptr(), dres.data_ptr(), rows_, C, code,
                                                             mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1, None, 0, sums2.data_ptr(),
                                                             cnt, st), "el")
-            rec("bn_bwd_elemt (mask from y, + dres)", 5 * nb, timeit(f_el_r), shape)
-            del res, dres
+            rec("bn_bwd_elemt (mask bits, + dres)", 4 * nb + nb // 16, timeit(f_el_r), shape)
+            del res, dres, bits
         else:
             PH, PW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
             yp = torch.empty(N, PH, PW, C, device=dev, dtype=dt)
@@ -117,7 +118,7 @@ def main():
             f_ap = lambda: L.check(lib.msf_bn2d_apply_pool(x.data_ptr(), yp.data_ptr(), tap.data_ptr(), xarg.data_ptr(), N, H, W, C, code,
                                                            mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), st), "apply_pool")
             rec("bn_apply+relu+maxpool", nb + npool * (2 * e + 1), timeit(f_ap), shape)
-            f_pr = lambda: L.check(lib.msf_bn2d_bwd_reduce(xarg.data_ptr(), dp.data_ptr(), yp.data_ptr(), N * PH * PW, C, code, mean.data_ptr(),
+            f_pr = lambda: L.check(lib.msf_bn2d_bwd_reduce(xarg.data_ptr(), dp.data_ptr(), yp.data_ptr(), 0, N * PH * PW, C, code, mean.data_ptr(),
                                                            invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1, None, 0, sums2.data_ptr(), ws2.data_ptr(),
                                                            wsb2, st), "pool_red")
             rec("bn_bwd_reduce on the pooled grid (x_arg, dpool, y)", 3 * npool * e, timeit(f_pr), shape)
