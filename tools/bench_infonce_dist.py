@@ -1,0 +1,102 @@
+"""c5 microbench at G GPUs (BASELINE.json configs[4]): fused InfoNCE fwd+bwd with the queries sharded N/G per rank and
+the keys global (NCCL all-gather of the normalised bf16 keys, rank-major, positives at rank*N/G + i -- SURVEY 8e).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 tools/bench_infonce_dist.py [--n 65536] [--d 128 256]
+
+One timed iteration per rank = row-normalise local q and k, all-gather the keys, forward (loss + O partials), backward
+(grad_q).  CUDA events on the launching stream, L2 flushed between iterations, MAX over ranks; whole-job TFLOP/s =
+4*N*N*D / time (algorithmic FLOPs of all ranks together); peak = G x MEASURED_PEAKS.json bf16_tflops."""
+import argparse
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from msfwsi_b200 import _lib as L  # noqa: E402
+from msfwsi_b200 import ops  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, nargs="+", default=[16384, 65536])
+    ap.add_argument("--d", type=int, nargs="+", default=[128, 256])
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--tau", type=float, default=0.07)
+    ap.add_argument("--out", default=None)
+    args = ap.parse_args()
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    try:
+        peak1 = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]
+    except Exception:
+        peak1 = 1590.0
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    rows = []
+    for d in args.d:
+        for n in args.n:
+            nq = n // world
+            g = torch.Generator(device=dev).manual_seed(3407)  # same stream on every rank: rank r takes rows [r*nq, (r+1)*nq)
+            k_all = torch.randn(n, d, device=dev, generator=g)
+            q_all = 0.3 * k_all + torch.randn(n, d, device=dev, generator=g)
+            q = q_all[rank * nq:(rank + 1) * nq].to(torch.bfloat16).contiguous()
+            k = k_all[rank * nq:(rank + 1) * nq].to(torch.bfloat16).contiguous()
+            del k_all, q_all
+            ws_bytes = L.lib().msf_infonce_workspace_bytes(nq, n, d, L.MSF_BF16)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            gout = torch.ones((), device=dev)
+            gq = torch.empty_like(q)
+            st = L.stream_ptr()
+
+            def step():
+                qh, qi = ops.rownorm(q, torch.bfloat16)
+                kh, _ = ops.rownorm(k, torch.bfloat16)
+                ka, off = ops.all_gather_keys(kh)
+                L.check(L.lib().msf_infonce_fwd(qh.data_ptr(), ka.data_ptr(), nq, n, d, off, args.tau, L.MSF_BF16, loss.data_ptr(), 0,
+                                                ws.data_ptr(), ws_bytes, st), "fwd")
+                L.check(L.lib().msf_infonce_bwd(qh.data_ptr(), ka.data_ptr(), qi.data_ptr(), nq, n, d, off, args.tau, L.MSF_BF16, gout.data_ptr(),
+                                                1.0 / n, ws.data_ptr(), ws_bytes, gq.data_ptr(), L.MSF_BF16, st), "bwd")
+
+            for _ in range(3):
+                step()
+            ts = []
+            for _ in range(args.iters):
+                flush.zero_()
+                if world > 1:
+                    dist.barrier()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                step()
+                e1.record()
+                torch.cuda.synchronize()
+                t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+                if world > 1:
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ts.append(float(t.item()))
+            ts.sort()
+            ms = ts[len(ts) // 2]
+            total = loss.detach().clone()
+            if world > 1:
+                dist.all_reduce(total)
+            flops = 4.0 * n * n * d
+            row = {"gpus": world, "N": n, "Nq_per_gpu": nq, "D": d, "mean_loss": float(total.item()) / n, "ms_fwd_bwd": ms,
+                   "tflops_whole_job": flops / ms / 1e9, "frac_of_peak": flops / ms / 1e9 / (peak1 * world), "peak_tflops_per_gpu": peak1}
+            rows.append(row)
+            if rank == 0:
+                print(json.dumps(row), flush=True)
+    if rank == 0 and args.out:
+        json.dump(rows, open(args.out, "w"), indent=1)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
