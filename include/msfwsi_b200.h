@@ -323,6 +323,20 @@ int msf_peer_allreduce_f64(double* vec, int n, void* const* peers /*device*/, in
                            int64_t capacity_doubles, int timeout_ms, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * D1  on-device data path of the views: blockshaped tiling + jigsaw shuffle + resize + normalise from the uint8 source
+ * image in one kernel.  Replaces, per sample, src/utils/data/bcss.py:171-177 `blockshaped(img, 256, 256)[jigsaw_idx]`
+ * and the per-tile Resize / Normalize / ToTensor of transforms[2] (the random augmentations are not reproduced).
+ *   src (B, H, W, 3) uint8 HWC; perm (B, grid*grid) int64 = jigsaw_idx (the FORWARD shuffle; NULL = identity);
+ *   out (B*grid*grid, oh, ow, 3) NHWC in out_dtype: tile j of sample b = source tile perm[b, j] (raster order of
+ *   blockshaped), bilinearly resampled to oh x ow (align_corners = False on the cropped tile) and normalised with
+ *   (v - 255*mean[c]) / (255*std[c]).  mean3 / std3 are HOST arrays.  grid = 1 yields the context view.
+ * perm values outside [-K, K) set bit 0 of *status_flag (device, may be NULL) and are clamped.
+ * ---------------------------------------------------------------------------------------- */
+int msf_jigsaw_tiles(const uint8_t* src, int64_t B, int H, int W, int grid, const int64_t* perm, int oh, int ow,
+                     const float* mean3 /*host*/, const float* std3 /*host*/, void* out, int out_dtype,
+                     int32_t* status_flag, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Measurement hook (bench.py): when switched on, every compute entry point records a CUDA event pair on its stream
  * immediately around its main kernel(s); msf_prof_end synchronises those events and returns, per kernel id, the number
  * of calls, the summed algorithmic work (bytes for HBM-bound kernels, FLOP for tensor-bound ones, as defined in
@@ -332,7 +346,7 @@ typedef enum {
   MSF_K_GATHER_FWD = 0, MSF_K_GATHER_BWD, MSF_K_COS_FWD, MSF_K_COS_BWD, MSF_K_ROWNORM, MSF_K_NCE_FLASH, MSF_K_NCE_TWOPASS,
   MSF_K_NCE_SIMT, MSF_K_NCE_BWD, MSF_K_GEMM, MSF_K_CROP_FWD, MSF_K_CROP_BWD, MSF_K_EMA, MSF_K_BN_STATS, MSF_K_BN_APPLY,
   MSF_K_BN_APPLY_RES, MSF_K_BN_BWD_REDUCE, MSF_K_BN_BWD_ELEMT, MSF_K_BN_APPLY_POOL, MSF_K_BN_POOL_BWD_ELEMT,
-  MSF_K_ADAM, MSF_K_GRAD_CHECK, MSF_K_STEM_S2D, MSF_K_PEER_ALLREDUCE, MSF_K_COUNT
+  MSF_K_ADAM, MSF_K_GRAD_CHECK, MSF_K_STEM_S2D, MSF_K_PEER_ALLREDUCE, MSF_K_JIGSAW_TILES, MSF_K_COUNT
 } msf_kernel_id;
 typedef struct {
   int32_t kernel;   /* msf_kernel_id */

@@ -47,7 +47,7 @@ class ProfRecord(C.Structure):
     _fields_ = [("kernel", C.c_int32), ("launches", C.c_int32), ("work", C.c_double), ("ms", C.c_double)]
 
 
-MSF_K_COUNT = 24
+MSF_K_COUNT = 25
 MSF_ADAM_CHUNK = 4096
 MSF_PEER_MAX_WORLD = 32
 
@@ -110,6 +110,8 @@ _SIGS = {
                                C.c_int, C.c_void_p]),
     "msf_peer_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "msf_peer_allreduce_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_int64, C.c_int, C.c_void_p]),
+    "msf_jigsaw_tiles": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float),
+                                   C.POINTER(C.c_float), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "msf_prof_begin": (C.c_int, [C.c_int]),
     "msf_prof_end": (C.c_int, [C.POINTER(ProfRecord), C.POINTER(C.c_int)]),
     "msf_prof_kernel_name": (C.c_char_p, [C.c_int]),

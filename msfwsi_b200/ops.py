@@ -592,6 +592,39 @@ def stem_s2d_weight(w: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------
+# D1: on-device data path of the views      (src/utils/data/bcss.py:171-177, 203-216 + transforms[2])
+# ------------------------------------------------------------------------------------------
+def jigsaw_tiles(src: torch.Tensor, perm: Optional[torch.Tensor], grid: int = 4, out_hw: Tuple[int, int] = (224, 224),
+                 mean: Sequence[float] = (0.485, 0.456, 0.406), std: Sequence[float] = (0.229, 0.224, 0.225),
+                 out_dtype: torch.dtype = torch.bfloat16, validate: bool = False) -> torch.Tensor:
+    """src (B, H, W, 3) uint8 HWC on the device; perm (B, grid*grid) int64 = jigsaw_idx (forward shuffle) or None.
+    Returns the (B*grid*grid, 3, oh, ow) channels-last views: tile j of sample b is source tile perm[b, j] of
+    ``blockshaped``, resized and normalised.  ``grid=1`` gives the context view of the whole image."""
+    L.require_cuda(src, perm)
+    if src.dim() != 4 or src.shape[3] != 3 or src.dtype != torch.uint8:
+        raise ValueError(f"jigsaw_tiles: src must be (B,H,W,3) uint8, got {tuple(src.shape)} {src.dtype}")
+    src = _contig(src)
+    B, H, W, _ = src.shape
+    K = grid * grid
+    if perm is not None:
+        if tuple(perm.shape) != (B, K) or perm.dtype != torch.int64:
+            raise AssertionError(f"jigsaw_idx must be int64 of shape ({B},{K}); got {perm.dtype} {tuple(perm.shape)}")
+        perm = _contig(perm)
+    if H % grid or W % grid:
+        raise AssertionError(f"{H} x {W} is not evenly divisible into a {grid} x {grid} grid")  # bcss.py:212-213
+    oh, ow = int(out_hw[0]), int(out_hw[1])
+    out = torch.empty((B * K, 3, oh, ow), dtype=out_dtype, device=src.device, memory_format=torch.channels_last)
+    flag = torch.zeros(1, dtype=torch.int32, device=src.device) if validate else None
+    m3, s3 = (C.c_float * 3)(*[float(v) for v in mean]), (C.c_float * 3)(*[float(v) for v in std])
+    L.check(L.lib().msf_jigsaw_tiles(L.ptr(src), B, H, W, grid, L.ptr(perm), oh, ow, m3, s3, L.ptr(out), L.dtype_code(out_dtype), L.ptr(flag),
+                                     L.stream_ptr()), "msf_jigsaw_tiles")
+    L.launch_count += 1
+    if validate and int(flag.item()) != 0:
+        raise IndexError(f"jigsaw_idx holds values outside [-{K}, {K})")
+    return out
+
+
+# ------------------------------------------------------------------------------------------
 # E1: multi-tensor EMA (extension)
 # ------------------------------------------------------------------------------------------
 class EmaUpdater:
