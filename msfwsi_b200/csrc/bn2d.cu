@@ -59,13 +59,6 @@ inline int reduce_grid(Kern kern, size_t smem, const Layout& l, int64_t rows, in
   return static_cast<int>(g);
 }
 
-template <int DT>
-__device__ __forceinline__ float round_store(float v) {  // the value a store in dtype DT followed by a load returns
-  if (DT == MSF_BF16) return __bfloat162float(__float2bfloat16_rn(v));
-  if (DT == MSF_F16) return __half2float(__float2half_rn(v));
-  return v;
-}
-
 // fixed-order reduction of the per-thread accumulators over the row lanes of a CTA -> partial[blk][2][C]
 template <int V>
 __device__ __forceinline__ void cta_reduce_store(const float* s, const float* q, int ct, int cvec, int cl, int rl,
@@ -802,17 +795,9 @@ int check_bn(const void* x, int64_t rows, int C, int dtype) {
   return MSF_OK;
 }
 
-inline unsigned stream_grid(int64_t items_per_thread_total) {
-  int64_t blocks = (items_per_thread_total + kThreads - 1) / kThreads;
-  const int64_t cap = static_cast<int64_t>(kNumSMs) * 16;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  return static_cast<unsigned>(blocks);
-}
-
 // grid of a grid-stride streaming kernel: exactly one wave of resident CTAs (no wave-quantisation tail), never more than
-// the work needs; kept a multiple of ... nothing: the kernels keep per-thread channel constants valid for any grid size
-// as long as gridDim.x * kThreads is a multiple of cvec, which holds whenever kThreads is.
+// the work needs.  Any grid size keeps the per-thread channel constants valid: a thread's chunk index advances by
+// gridDim.x * kThreads, a multiple of cvec whenever kThreads is.
 template <typename Kern>
 inline unsigned wave_grid(Kern kern, int64_t per_thread_items, int cvec) {
   (void)cvec;

@@ -17,7 +17,6 @@ namespace msf {
 namespace {
 
 constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kLn2 = 0.6931471805599453f;
 
 // --------------------------------------------------------------------------------------------
 // row normalisation: x -> x / max(||x||, eps), out bf16 or fp32, plus 1/max(||x||,eps)
