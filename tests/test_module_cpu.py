@@ -133,3 +133,21 @@ def test_product_ops_refuse_cpu_tensors():
     p.grad = torch.ones(4)
     with pytest.raises(RuntimeError):
         FusedAdam([p], lr=1e-3).step()
+
+
+def test_encoder_module_wiring_matches_reference_resnet18_golden(golden_dir):
+    """Same recipe as the GPU test, on CPU in fp64 (plain ATen path of FusedBatchNorm2d, plain stem convolution): pins the
+    module wiring -- parameter names, block structure, pooled features -- to the unmodified reference ResNet-18."""
+    import numpy as np
+    from oracle import make_golden_encoder as G
+    gold = np.load(os.path.join(golden_dir, "encoder_resnet18.npz"))
+    enc = M.resnet18(pretrained=False, return_features=True, zero_init_residual=True)
+    enc.fc = torch.nn.Identity()
+    enc = enc.double().train()
+    G.fill_closed_form(enc)
+    feats = enc(G.closed_form_input())
+    for i, f in enumerate(feats):
+        assert torch.allclose(f.detach(), torch.from_numpy(gold[f"feat{i}"]), rtol=1e-9, atol=1e-10), i
+    G.loss_of(feats).backward()
+    for name, p in enc.named_parameters():
+        assert abs(float(p.grad.norm()) - float(gold["gnorm/" + name])) <= 1e-8 * float(gold["gnorm/" + name]) + 1e-12, name
