@@ -1,4 +1,4 @@
-"""bench.py -- SSL pre-training tiles/s of the MSF-WSI hot path on N B200s (+ roofline of the fused InfoNCE kernel).
+"""bench.py -- SSL pre-training tiles/s of the MSF-WSI hot path on N B200s + the rooflines of its kernels.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's arm (one rank per GPU under torchrun for N>1)
     python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle port) on host cores
@@ -6,8 +6,17 @@
 A "step" is one full pre-training step of BASELINE.json configs[1] (BCSS-shaped, per-GPU batch 256, bf16 autocast,
 synthetic 1024^2-tile-shaped inputs: 2 context + 32 target 224^2 views and 2 jigsaw index rows per tile):
 ResNet-18 encoders on PyTorch/cuDNN (not a CUDA target of this repo) -> hot path (gather/concat kernel, heads,
-fused loss kernel) -> backward -> Adam.  `value` times K steps with inputs resident in HBM; `e2e` times the same
-step fed from pinned host memory with the loss read back every step.  Prints ONE JSON line on rank 0.
+fused loss kernel) -> backward -> Adam.  The default objective is the REFERENCE's (SimSiam negative cosine,
+tools/ssl_train.py:448-466) so that every arm -- this repo, the GPU-eager reference graph, the CPU port -- times the same
+thing; the same step with the north-star InfoNCE objective is timed next to it (`infonce_step`).
+
+JSON line (rank 0): `value` = K steps with inputs resident in HBM; `e2e` = the same step fed from pinned host memory
+with the loss read back every step; `roofline` = the north-star kernel (fused InfoNCE forward+backward chain at the c5
+size N = 65536) against the measured bf16 tensor peak; `roofline_kernels` = every kernel of this repo inside the timed
+steps (library profiler); `roofline_hbm` = A1 / A2 / E1 at sizes beyond L2 against the measured copy bandwidth;
+`gpu_eager_baseline` = the reference's own module graph (stock torch modules, torch.optim.Adam, oracle/torch_ref.py) on
+the same GPU(s) in the same job; `cpu_baseline` = the same graph on the host cores (N = 1 only); `dist_parity` (N > 1) =
+sharded-vs-gathered InfoNCE, peer all-reduce vs NCCL, synced batch norm vs the concatenated batch, checked before timing.
 """
 from __future__ import annotations
 
@@ -18,7 +27,6 @@ import statistics
 import subprocess
 import sys
 import tempfile
-import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -34,35 +42,46 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch in tiles (configs[1]: 256)")
+    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch in tiles (configs[1]: 256; configs[3] c4: 1024 with --heads-only)")
     ap.add_argument("--img", type=int, default=224)
-    ap.add_argument("--loss", default="infonce", choices=["infonce", "cosine"],
-                    help="infonce = north_star objective (extension); cosine = reference-exact SimSiam loss")
+    ap.add_argument("--loss", default="cosine", choices=["cosine", "infonce"],
+                    help="cosine = the reference's SimSiam objective (default, like-for-like with every baseline arm); "
+                         "infonce = the north-star extension.  The other one is timed as well (`*_step` keys)")
     ap.add_argument("--tau", type=float, default=0.07)
-    ap.add_argument("--cpu-sample", type=int, default=4, help="tiles per CPU-baseline step")
+    ap.add_argument("--cpu-sample", type=int, default=8, help="tiles per CPU-baseline step (configs[0]: batch 8)")
+    ap.add_argument("--heads-only", action="store_true",
+                    help="time the hot path alone (gather/concat + heads + loss + backward + Adam on the head parameters) from "
+                         "synthetic pooled features: the c4 regime (--batch 1024) does not fit one GPU with the encoders attached")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true")
     ap.add_argument("--no-microbench", action="store_true")
+    ap.add_argument("--no-hbm-rows", action="store_true")
+    ap.add_argument("--no-second-loss", action="store_true")
     return ap.parse_args()
 
 
 def workload_name(args):
+    if args.heads_only:
+        return (f"MSF-WSI hot path only (gather/concat + 12 projectors + 12 predictors + loss, fwd+bwd+Adam), bf16, batch {args.batch}/GPU, "
+                f"synthetic pooled pyramid features, loss={args.loss}")
     return (f"BCSS fold-0 SSL pretraining bf16, batch {args.batch}/GPU, synthetic L0_1024_s512-shaped tiles "
             f"(2x(3,{args.img},{args.img}) context + 2x(16,3,{args.img},{args.img}) target views), loss={args.loss}")
 
 
 # ------------------------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the oracle port on host cores
+# reference arm / cpu_baseline: the reference's module graph (oracle port) on host cores
 # ------------------------------------------------------------------------------------------------------------
 def run_cpu_port(sample_tiles, steps, warmup, loss, tau, img):
-    from oracle.cpu_step import CpuReferenceStep  # the one place bench.py executes oracle/
-    port = CpuReferenceStep(sample_tiles, img=img, loss=loss, tau=tau)
+    from oracle.cpu_step import ReferenceStep  # bench.py executes oracle/ only in its baseline legs
+    port = ReferenceStep(sample_tiles, img=img, loss=loss, tau=tau, device="cpu")
     for _ in range(warmup):
         port.step()
     times = [port.step() for _ in range(steps)]
     total = sum(times)
     return {"value": sample_tiles * steps / total, "unit": UNIT, "cores": port.threads, "kind": "port",
-            "sample": f"{steps} step(s) of {sample_tiles} tiles ({34 * sample_tiles} encoder images of {img}^2) after {warmup} warm-up, "
-                      f"fp32, torch CPU, full step incl. backward + Adam",
+            "sample": f"{steps} step(s) of {sample_tiles} tiles ({34 * sample_tiles} encoder images of {img}^2) after {warmup} warm-up, fp32, "
+                      f"stock torch modules on the CPU (oracle/torch_ref.py: plain ResNet-18 encoders + nn.Linear/nn.BatchNorm1d heads + "
+                      f"{loss} loss + torch.optim.Adam), full step incl. backward",
             "ms_per_step": 1e3 * total / steps}
 
 
@@ -70,8 +89,7 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # other ranks exit 0 without work
-    steps, warmup = max(1, args.steps), max(0, min(args.warmup, 1))  # bounded: each CPU step costs seconds
-    steps = min(steps, 3)
+    steps, warmup = min(max(1, args.steps), 3), max(0, min(args.warmup, 1))  # bounded: each CPU step costs seconds
     cb = run_cpu_port(args.cpu_sample, steps, warmup, args.loss, args.tau, args.img)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -157,54 +175,11 @@ def ours(args):
         dist.init_process_group("nccl", device_id=dev)
     torch.backends.cudnn.benchmark = True
     torch.manual_seed(3407 + rank)
-
-    class LossStep(torch.nn.Module):  # forward() returns the loss so DDP hooks see the whole hot path
-        def __init__(self, model):
-            super().__init__()
-            self.model = model
-
-        def forward(self, x1, x2, rev):
-            return self.model.forward_loss(x1, x2, rev, FUSER_WEIGHTS, mode=args.loss, tau=args.tau)
-
-    import warnings
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        model = M.MSFWSI(M.resnet18, 4, 2048, 512, 0.5, False)  # random init: no network for ImageNet weights
-    if world > 1:
-        model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)  # tools/ssl_train.py:160
-    model = model.to(dev).to(memory_format=torch.channels_last).train()
-    step_mod = LossStep(model)
-    if world > 1:
-        # ssl_train.py:170; SyncBN keeps the buffers identical on every rank, so the per-forward buffer broadcast is
-        # redundant; large buckets suit NVSwitch (latency-, not link-bound)
-        step_mod = torch.nn.parallel.DistributedDataParallel(step_mod, device_ids=[local], broadcast_buffers=False,
-                                                             gradient_as_bucket_view=True, bucket_cap_mb=128)
-    lr = 1e-3 * (args.batch * world) ** 0.5 / 32 ** 0.5  # ssl_train.py:155
-    groups = [{"params": [p for n, p in model.named_parameters() if n.startswith(pre)]} for pre in ("context_", "target_", "inter_")]
-    opt = M.FusedAdam(groups, lr=lr)  # torch.optim.Adam semantics (ssl_train.py:309), one msf_adam_multi launch per step
-
-    B, K, img = args.batch, 16, args.img
-    g = torch.Generator().manual_seed(3407 + rank)
-    # Host side of the input pipeline: normalised views in the layout and precision the first convolution consumes under
-    # bf16 autocast (NHWC, bf16 -- autocast would round the fp32 tensor to exactly these values on the device), pinned.
-    def view(n):
-        return torch.randn(n, 3, img, img, generator=g).to(torch.bfloat16).contiguous(memory_format=torch.channels_last).pin_memory()
-
-    host = {"c1": view(B), "c2": view(B), "t1": view(B * K), "t2": view(B * K),
-            "r1": torch.stack([torch.randperm(K, generator=g).argsort() for _ in range(B)]).pin_memory(),
-            "r2": torch.stack([torch.randperm(K, generator=g).argsort() for _ in range(B)]).pin_memory()}
-    h2d_bytes = sum(t.numel() * t.element_size() for t in host.values())
-
-    def to_dev():
-        return {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-
-    def step(d):
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            loss = step_mod((d["c1"], d["t1"]), (d["c2"], d["t2"]), [d["r1"], d["r2"]])
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        opt.step()
-        return loss
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
 
     def barrier():
         if world > 1:
@@ -218,32 +193,121 @@ def ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    dist_parity = None
+    if world > 1:
+        dist_parity = check_dist_parity(torch, dist, M, ops, dev, rank, world)  # raises when out of tolerance
+
+    class LossStep(torch.nn.Module):  # forward() returns the loss so DDP hooks see the whole hot path
+        def __init__(self, model):
+            super().__init__()
+            self.model, self.mode = model, args.loss
+
+        def forward(self, x1, x2, rev):
+            if args.heads_only:
+                return M.ssl_loss(self.model.heads(x1[0], x2[0], x1[1], x2[1], rev), FUSER_WEIGHTS, mode=self.mode, tau=args.tau)
+            return self.model.forward_loss(x1, x2, rev, FUSER_WEIGHTS, mode=self.mode, tau=args.tau)
+
+    class _NoEncoder(torch.nn.Module):
+        def __init__(self, **_):
+            super().__init__()
+            self.fc = torch.nn.Identity()
+
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        enc = (lambda **kw: _NoEncoder(**kw)) if args.heads_only else M.resnet18  # random init: no network for ImageNet weights
+        model = M.MSFWSI(enc, 4, 2048, 512, 0.5, False)
+    if world > 1:
+        model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)  # tools/ssl_train.py:160
+    model = model.to(dev).to(memory_format=torch.channels_last).train()
+    loss_step = LossStep(model)
+    step_mod = loss_step
+    if world > 1:
+        # ssl_train.py:170; SyncBN keeps the buffers identical on every rank, so the per-forward buffer broadcast is
+        # redundant; large buckets suit NVSwitch (latency-, not link-bound)
+        step_mod = torch.nn.parallel.DistributedDataParallel(step_mod, device_ids=[local], broadcast_buffers=False,
+                                                             gradient_as_bucket_view=True, bucket_cap_mb=128)
+    lr = 1e-3 * (args.batch * world) ** 0.5 / 32 ** 0.5  # ssl_train.py:155
+    groups = [{"params": [p for n, p in model.named_parameters() if n.startswith(pre)]} for pre in ("context_", "target_", "inter_")]
+    groups = [g for g in groups if g["params"]]
+    opt = M.FusedAdam(groups, lr=lr)  # torch.optim.Adam semantics (ssl_train.py:309), one msf_adam_multi launch per step
+    M.bind_optimizer(model, opt)      # the kernel also rewrites the bf16 GEMM operands of the head Linears (no cast pass per step)
+
+    B, K, img = args.batch, 16, args.img
+    g = torch.Generator().manual_seed(3407 + rank)
+    # Host side of the input pipeline: normalised views in the layout and precision the first convolution consumes under
+    # bf16 autocast (NHWC, bf16 -- autocast would round the fp32 tensor to exactly these values on the device), pinned.
+    if args.heads_only:
+        def feats(n):
+            return [torch.randn(n, d, generator=g).abs().to(torch.bfloat16).pin_memory() for d in (64, 128, 256, 512)]
+        host = {"c1": feats(B), "c2": feats(B), "t1": feats(B * K), "t2": feats(B * K)}
+    else:
+        def view(n):
+            return torch.randn(n, 3, img, img, generator=g).to(torch.bfloat16).contiguous(memory_format=torch.channels_last).pin_memory()
+        host = {"c1": view(B), "c2": view(B), "t1": view(B * K), "t2": view(B * K)}
+    host["r1"] = torch.stack([torch.randperm(K, generator=g).argsort() for _ in range(B)]).pin_memory()
+    host["r2"] = torch.stack([torch.randperm(K, generator=g).argsort() for _ in range(B)]).pin_memory()
+
+    def nbytes(v):
+        return sum(nbytes(t) for t in v) if isinstance(v, (list, tuple)) else v.numel() * v.element_size()
+
+    h2d_bytes = sum(nbytes(v) for v in host.values())
+
+    def to_dev():
+        mv = lambda v: [t.to(dev, non_blocking=True) for t in v] if isinstance(v, list) else v.to(dev, non_blocking=True)
+        return {k: mv(v) for k, v in host.items()}
+
+    def step(d):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = step_mod((d["c1"], d["t1"]), (d["c2"], d["t2"]), [d["r1"], d["r2"]])
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
     resident = to_dev()
     for _ in range(max(3, args.warmup)):
         step(resident)
     barrier()
 
+    def timed(n_steps, profile):
+        clocks = Clocks(local) if (rank == 0 and profile) else None
+        if profile:
+            _lib.prof_begin(1 << 16)  # CUDA event pairs around every main kernel of this repo, on its launching stream
+        launches0 = _lib.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        # process-wide start/end range (push/pop ranges are per thread and would miss the autograd thread's launches):
+        # ncu --nvtx --nvtx-include "msf_timed_steps" captures exactly the launches of the timed steps
+        rng = torch.cuda.nvtx.range_start("msf_timed_steps") if profile else None
+        e0.record()
+        for _ in range(n_steps):
+            loss = step(resident)
+        e1.record()
+        barrier()
+        if profile:
+            torch.cuda.nvtx.range_end(rng)
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        out = {"ms": ms, "launches": _lib.launch_count - launches0, "loss": float(loss.item())}
+        if profile:
+            out["prof"], out["prof_dropped"] = _lib.prof_end()
+            out["clocks"] = clocks.stop() if clocks else None
+        return out
+
     # ---- timed region 1: inputs resident in HBM --------------------------------------------------------
-    clocks = Clocks(local) if rank == 0 else None
-    _lib.prof_begin(1 << 16)  # CUDA event pairs around every main kernel of this repo, on its launching stream
-    launches0 = _lib.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    # process-wide start/end range (push/pop ranges are per thread and would miss the autograd thread's launches):
-    # ncu --nvtx --nvtx-include "msf_timed_steps" captures exactly the launches of the timed steps
-    nvtx_range = torch.cuda.nvtx.range_start("msf_timed_steps")
-    e0.record()
-    for _ in range(args.steps):
-        loss = step(resident)
-    e1.record()
-    barrier()
-    torch.cuda.nvtx.range_end(nvtx_range)
-    ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = _lib.launch_count - launches0
-    prof, prof_dropped = _lib.prof_end()
-    clk = clocks.stop() if clocks else None
-    last_loss = float(loss.item())
+    main = timed(args.steps, True)
+    ms, launches, prof, prof_dropped, clk, last_loss = main["ms"], main["launches"], main["prof"], main["prof_dropped"], main["clocks"], main["loss"]
     value = B * world * args.steps / (ms / 1e3)
+
+    other = None
+    if not args.no_second_loss:
+        loss_step.mode = "infonce" if args.loss == "cosine" else "cosine"
+        for _ in range(3):
+            step(resident)
+        o = timed(args.steps, False)
+        other = {"loss_mode": loss_step.mode, "value": B * world * args.steps / (o["ms"] / 1e3), "unit": UNIT, "ms_per_step": o["ms"] / args.steps,
+                 "gpu_launches": o["launches"], "loss": o["loss"]}
+        loss_step.mode = args.loss
 
     # ---- timed region 2: end to end from pinned host memory, loss read back every step -------------------
     # Every step's inputs are copied host -> device inside the timed region (K copies for K steps); the copy of step
@@ -257,8 +321,9 @@ def ours(args):
             d = to_dev()
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        for t in d.values():
-            t.record_stream(main_stream)
+        for v in d.values():
+            for t in (v if isinstance(v, list) else [v]):
+                t.record_stream(main_stream)
         return d, ev
 
     def e2e_steps(n):
@@ -271,6 +336,7 @@ def ours(args):
 
     e2e_steps(2)
     barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     e2e_steps(args.steps)
     e1.record()
@@ -278,14 +344,9 @@ def ours(args):
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     e2e = B * world * args.steps / (ms_e2e / 1e3)
 
-    # ---- roofline of the dominant kernel of this repo inside the timed steps ----------------------------
+    # ---- every kernel of this repo inside the timed steps -------------------------------------------------
     # per kernel family: algorithmic work (bytes or FLOP) summed over the launches of the timed
     # region / device time between the event pairs the library recorded around them
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
     traffic = {}
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
@@ -308,33 +369,26 @@ def ours(args):
                         "share_of_step": r["ms"] / ms, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
                         "work_per_launch": r["work"] / r["launches"], "avg_us": 1e3 * r["ms"] / r["launches"]})
     kernels.sort(key=lambda k: -k["ms_per_step"])
-    roofline = None
-    if any("frac" in k for k in kernels):
-        top = next(k for k in kernels if "frac" in k)
-        t = traffic.get(top["kernel"])
-        roofline = {"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"],
-                    "frac": top["frac"], "traffic": None if t is None else t.get("dram_bytes_per_launch"),
-                    "traffic_note": None if t is None else (f"ncu capture at {t.get('shape')}: {t.get('dram_bytes_per_launch'):.4g} B of DRAM traffic for "
-                                                            f"{t.get('algorithmic_bytes_per_launch'):.4g} algorithmic B (ratio {t.get('ratio_to_algorithmic'):.3f}); "
-                                                            f"{t.get('source')}"),
-                    "peak_source": ("MEASURED_PEAKS.json " + ("hbm_gbs" if top["bound"] == "hbm" else "bf16_tflops_sustained")) if peaks else "fallback (B200_PROFILING.md)",
-                    "launches": top["launches"], "avg_us": top["avg_us"], "work_per_launch": top["work_per_launch"],
-                    "share_of_step": top["share_of_step"],
-                    "timing": "cudaEventRecord by the library on the launching stream immediately before/after the kernel, "
-                              "summed over the timed steps (dominant kernel of this repo by device time)",
-                    "all_kernels_share_of_step": sum(k["share_of_step"] for k in kernels), "events_dropped": prof_dropped}
-    micro = None
-    if rank == 0 and not args.no_microbench:
-        micro = infonce_microbench(torch, ops, _lib, dev, peaks)
-    if roofline is None and micro:
-        roofline = micro["roofline"]
-    if micro:
-        for k in kernels:  # the north-star kernel at its c5 size next to its in-step (N = 16 * batch) numbers
-            if k["kernel"] == "infonce_flash_fwd":
-                k["c5_microbench_frac_of_burst_peak"] = max(r["frac_fwd"] for r in micro["rows"])
 
+    # ---- the contract's roofline: the north-star kernel (fused InfoNCE fwd+bwd, c5 size), measured in this process ----
+    micro = roofline = None
+    if rank == 0 and not args.no_microbench:
+        micro = infonce_microbench(torch, ops, _lib, dev, peaks, traffic)
+        roofline = micro["roofline"]
+    hbm_rows = None
+    if rank == 0 and not args.no_hbm_rows:
+        hbm_rows = hbm_microbench(torch, ops, _lib, dev, peaks)
+
+    # ---- baselines: the reference's own module graph on the same GPU(s) (all ranks), and on the host cores (N = 1) ----
+    del model, loss_step, step_mod, opt
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    gpu_eager = None
+    if not args.no_gpu_eager and not args.heads_only:
+        gpu_eager = gpu_eager_baseline(torch, dist, args, dev, world, rank, barrier, max_over_ranks, value, e2e)
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.heads_only:
         cb = run_cpu_port(args.cpu_sample, 2, 1, args.loss, args.tau, args.img)
         cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
@@ -343,23 +397,144 @@ def ours(args):
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic",
                 "config": {"workload": workload_name(args), "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
-                           "encoder": "resnet18 random-init (PyTorch/cuDNN, channels_last)", "optimizer": "Adam, 3 lr groups (msf_adam_multi)",
-                           "l2_policy": "per-step inputs (2.6 GB bf16) and activations exceed the 126 MB L2",
+                           "encoder": "none (heads only)" if args.heads_only else "resnet18 random-init (PyTorch/cuDNN, channels_last)",
+                           "optimizer": "Adam, 3 lr groups (msf_adam_multi, bf16 GEMM operands rewritten in the same pass)",
+                           "l2_policy": "per-step inputs (2.6 GB bf16) and activations exceed the 126 MB L2; microbenchmarks flush L2 between iterations",
                            "host_inputs": "bf16 NHWC pinned (what the first convolution consumes under bf16 autocast)"},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline, "loss": last_loss,
-                "encoder_images_per_sec": value * 34}
+                "encoder_images_per_sec": None if args.heads_only else value * 34}
+        if other:
+            line[other["loss_mode"] + "_step"] = other
+        if gpu_eager:
+            line["gpu_eager_baseline"] = gpu_eager
+        if dist_parity:
+            line["dist_parity"] = dist_parity
         line["roofline_kernels"] = kernels
+        line["roofline_kernels_note"] = ("cudaEventRecord by the library on the launching stream immediately before/after each kernel, summed over the "
+                                         f"timed steps; share of the step covered: {sum(k['share_of_step'] for k in kernels):.3f}; events dropped: {prof_dropped}")
         if micro:
             line["roofline_microbench"] = micro["rows"]
+        if hbm_rows:
+            line["roofline_hbm"] = hbm_rows
         emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
-def infonce_microbench(torch, ops, _lib, dev, peaks):
-    """c5 rows measured in the same process: the fused InfoNCE forward (main tcgen05 kernel + finalize) and the
-    whole fwd+bwd chain (row-normalise x2, forward, backward) with CUDA events, L2 flushed between iterations."""
+# ------------------------------------------------------------------------------------------------------------
+# multi-GPU parity, checked on the box before anything is timed (N > 1)
+# ------------------------------------------------------------------------------------------------------------
+def check_dist_parity(torch, dist, M, ops, dev, rank, world):
+    """Max errors of the three cross-rank pieces of the path against their single-process definitions:
+    (a) sharded InfoNCE (local queries x all-gathered keys) vs the loss / gradient of the gathered problem on one rank,
+    (b) the NVLink peer all-reduce vs NCCL's, (c) batch norm with synced statistics vs batch norm of the concatenated batch.
+    Raises if a bound is exceeded; the numbers go into the JSON line."""
+    out = {}
+    g = torch.Generator(device=dev).manual_seed(99)  # same stream on every rank: everyone can build the global problem
+    rows, tau = 512, 0.07
+    for dim in (128, 576):
+        z_all = torch.randn(world * rows, dim, device=dev, generator=g)
+        p_all = (0.5 * z_all + torch.randn(world * rows, dim, device=dev, generator=g)).to(torch.bfloat16)
+        z_all = z_all.to(torch.bfloat16)
+        sl = slice(rank * rows, (rank + 1) * rows)
+        p = p_all[sl].clone().requires_grad_(True)
+        loss = ops.infonce_loss(p, z_all[sl].contiguous(), tau=tau, group=dist.group.WORLD)  # local mean over local queries
+        loss.backward()
+        pf = p_all.clone().requires_grad_(True)
+        full = ops.infonce_loss(pf, z_all, tau=tau, group=False)  # whole problem on this rank, no collective
+        full.backward()
+        t = loss.detach().clone()
+        dist.all_reduce(t)
+        out[f"infonce_d{dim}_loss_rel"] = abs(float(t) / world - float(full)) / abs(float(full))
+        # d(mean over all rows)/dp_local = d(local mean)/dp_local / world
+        a, b = (p.grad.double() / world).flatten(), pf.grad[sl].double().flatten()
+        out[f"infonce_d{dim}_grad_cos"] = float((a @ b) / (a.norm() * b.norm()))
+        out[f"infonce_d{dim}_grad_rel"] = float((a - b).norm() / b.norm())
+        assert out[f"infonce_d{dim}_loss_rel"] <= 1e-5 and out[f"infonce_d{dim}_grad_cos"] >= 0.9999, out
+    red = ops.PeerReducer.get(dist.group.WORLD, dev) if ops.USE_PEER_ALLREDUCE else None
+    v = torch.randn(9217, device=dev, dtype=torch.float64, generator=torch.Generator(device=dev).manual_seed(rank))
+    want = v.clone()
+    dist.all_reduce(want)
+    if red is not None:
+        got = red.all_reduce_(v.clone())
+        out["peer_allreduce_max_abs"] = float((got - want).abs().max())
+        assert out["peer_allreduce_max_abs"] <= 1e-12 * world, out
+    else:
+        out["peer_allreduce_max_abs"] = None  # symmetric memory unavailable: statistics go through NCCL
+    bn = M.module.FusedBatchNorm1d(256, act="relu").to(dev).train()
+    x_all = torch.randn(world * 64, 256, device=dev, generator=g) * 2 + 0.5
+    x = x_all[rank * 64:(rank + 1) * 64].clone().requires_grad_(True)
+    y = bn(x)
+    (y * y).sum().backward()
+    xa = x_all.clone().double().requires_grad_(True)
+    ya = torch.relu(torch.nn.functional.batch_norm(xa, None, None, None, None, True, 0.1, 1e-5))
+    (ya * ya).sum().backward()
+    out["syncbn_out_max_abs"] = float((y.detach().double() - ya.detach()[rank * 64:(rank + 1) * 64]).abs().max())
+    out["syncbn_dx_rel"] = float((x.grad.double() - xa.grad[rank * 64:(rank + 1) * 64]).norm() / xa.grad[rank * 64:(rank + 1) * 64].norm())
+    out["syncbn_running_var_rel"] = float(((bn.running_var.double() - (0.9 + 0.1 * x_all.double().var(0, unbiased=True))).abs() /
+                                            (0.9 + 0.1 * x_all.double().var(0, unbiased=True))).max())
+    assert out["syncbn_out_max_abs"] <= 2e-5 and out["syncbn_dx_rel"] <= 1e-4 and out["syncbn_running_var_rel"] <= 1e-5, out
+    worst = torch.tensor([v if v is not None and "cos" not in k else 0.0 for k, v in out.items()], dtype=torch.float64, device=dev)
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX)  # worst rank
+    keys = list(out)
+    for i, k in enumerate(keys):
+        if out[k] is not None and "cos" not in k:
+            out[k] = float(worst[i])
+    out["ranks"] = world
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# baseline: the reference's module graph on the same GPU(s), PyTorch eager (cuBLAS / cuDNN / ATen / NCCL)
+# ------------------------------------------------------------------------------------------------------------
+def gpu_eager_baseline(torch, dist, args, dev, world, rank, barrier, max_over_ranks, value, e2e):
+    from oracle.cpu_step import ReferenceStep  # baseline leg only
+    steps, warm = max(2, min(args.steps, 10)), 3
+    batch = args.batch
+    note = None
+    while True:
+        try:
+            ref = ReferenceStep(batch, img=args.img, loss=args.loss, tau=args.tau, seed=3407 + rank, device=str(dev), autocast_dtype=torch.bfloat16,
+                                lr=1e-3 * (batch * world) ** 0.5 / 32 ** 0.5)
+            for _ in range(warm):
+                ref.step()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                ref.step()
+            e1.record()
+            barrier()
+            ms = max_over_ranks(e0.elapsed_time(e1))
+            break
+        except torch.OutOfMemoryError:
+            ref = None
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+            if world > 1 or batch <= 16:  # ranks must agree on the batch: no per-rank fallback under DDP
+                return {"unavailable": f"out of memory at batch {batch}/GPU"}
+            batch //= 2
+            note = f"out of memory at batch {args.batch}/GPU: measured at {batch}/GPU"
+    v = batch * world * steps / (ms / 1e3)
+    out = {"value": v, "unit": UNIT, "ms_per_step": ms / steps, "steps": steps, "warmup": warm, "per_gpu_batch": batch, "loss_mode": args.loss,
+           "loss": float(ref.last.item()),
+           "what": "the reference's module graph with stock torch modules (oracle/torch_ref.py: nn.Conv2d/BatchNorm2d ResNet-18 encoders, "
+                   "nn.Linear/nn.BatchNorm1d heads, advanced-index gather + cat, 24 nn.CosineSimilarity calls, torch.optim.Adam; "
+                   "SyncBatchNorm + DDP at N > 1), bf16 autocast, inputs resident, as tools/ssl_train.py:441-474 runs it",
+           "speedup_value_over_eager": value / v, "speedup_e2e_over_eager": e2e / v}
+    if note:
+        out["note"] = note
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# microbenchmarks measured in the same process
+# ------------------------------------------------------------------------------------------------------------
+def infonce_microbench(torch, ops, _lib, dev, peaks, traffic):
+    """c5 rows: the fused InfoNCE forward (main tcgen05 kernel + finalize) and the whole fwd+bwd chain (row-normalise
+    x2, forward, backward) with CUDA events on the launching stream, L2 flushed between iterations."""
     L = _lib
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     peak = peaks.get("bf16_tflops", 1590.0)
@@ -375,6 +550,7 @@ def infonce_microbench(torch, ops, _lib, dev, peaks):
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         loss, gout, gq = torch.empty((), device=dev), torch.ones((), device=dev), torch.empty_like(q)
         st = L.stream_ptr()
+        ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
         def fwd():
             L.check(L.lib().msf_infonce_fwd(qh.data_ptr(), kh.data_ptr(), n, n, d, 0, 0.07, L.MSF_BF16, loss.data_ptr(), 0, ws.data_ptr(), wsb, st), "fwd")
@@ -403,11 +579,79 @@ def infonce_microbench(torch, ops, _lib, dev, peaks):
             out[f"tflops_{name}"] = out["flops"] / out[f"ms_{name}"] / 1e9
             out[f"frac_{name}"] = out[f"tflops_{name}"] / peak
         rows.append(out)
-    best = max(rows, key=lambda r: r["frac_fwd_bwd"])
-    roof = {"kernel": f"infonce_tc_kernel N={best['N']} D={best['D']} (fwd+bwd chain)", "bound": "tensor", "achieved": best["tflops_fwd_bwd"],
-            "peak": peak, "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback", "unit": "TFLOP/s",
-            "frac": best["frac_fwd_bwd"], "traffic": None}
+    top = rows[-1]  # N = 65536, D = 256: the configuration the ncu traffic capture was taken on
+    t = traffic.get("infonce_flash_fwd")
+    roof = {"kernel": f"infonce_tc_kernel<{top['D']}> N=Nq={top['N']} tau=0.07: forward+backward chain (row-normalise x2, fused tcgen05 "
+                      "main loop, finalize, backward)",
+            "bound": "tensor", "achieved": top["tflops_fwd_bwd"], "peak": peak, "unit": "TFLOP/s", "frac": top["frac_fwd_bwd"],
+            "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst: the kernel is timed alone)" if peaks else "fallback 1590 (B200_PROFILING.md)",
+            "algorithmic_flops_per_launch": top["flops"], "ms": top["ms_fwd_bwd"],
+            "main_kernel_only": {"achieved": top["tflops_fwd"], "frac": top["frac_fwd"], "ms": top["ms_fwd"]},
+            "d128": {"achieved": rows[1]["tflops_fwd_bwd"], "frac": rows[1]["frac_fwd_bwd"], "ms": rows[1]["ms_fwd_bwd"]},
+            "traffic": None if t is None else t.get("dram_bytes_per_launch"),
+            "traffic_note": None if t is None else (f"ncu capture at {t.get('shape')}: {t.get('dram_bytes_per_launch'):.4g} B of DRAM traffic for "
+                                                    f"{t.get('algorithmic_bytes_per_launch'):.4g} algorithmic B (ratio {t.get('ratio_to_algorithmic'):.3f}); "
+                                                    f"{t.get('source')}"),
+            "timing": "torch.cuda.Event pair on the current stream = the stream the C-ABI call launches on; median of 7 after 3 warm-ups, "
+                      "256 MB L2 flush between iterations"}
     return {"rows": rows, "roofline": roof}
+
+
+def hbm_microbench(torch, ops, _lib, dev, peaks):
+    """A1 (gather/concat at the c4 size), A2 (crop-resample: 4x bilinear zoom and the integer copy) and E1 (EMA over the
+    reference's 123.6 M parameters) against the measured copy bandwidth; working sets beyond the 126 MB L2."""
+    L = _lib
+    peak = peaks.get("hbm_gbs", 6650.0)
+    rows = []
+
+    def timeit(fn, iters=7, reps=4):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(iters):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) / reps)
+        return statistics.median(ts)
+
+    def rec(name, nbytes, ms, note):
+        rows.append({"kernel": name, "bound": "hbm", "bytes": nbytes, "ms": ms, "achieved": nbytes / ms / 1e6, "peak": peak, "unit": "GB/s",
+                     "frac": nbytes / ms / 1e6 / peak, "note": note})
+
+    B, K, dims, e = 1024, 16, (64, 128, 256, 512), 2  # c4: 1024 tiles per GPU
+    g = torch.Generator(device=dev).manual_seed(1)
+    ctx = [torch.randn(B, d, device=dev, generator=g).to(torch.bfloat16) for _ in range(2) for d in dims]
+    tgt = [torch.randn(B * K, d, device=dev, generator=g).to(torch.bfloat16) for _ in range(2) for d in dims]
+    rev = [torch.stack([torch.randperm(K) for _ in range(B)]).to(dev)] * 8
+    outs = [(torch.empty_like(t), torch.empty((B, 9 * c.shape[1]), dtype=c.dtype, device=dev)) for c, t in zip(ctx, tgt)]
+    items = (L.GatherItem * 8)()
+    for i in range(8):
+        items[i] = L.GatherItem(tgt[i].data_ptr(), ctx[i].data_ptr(), rev[i].data_ptr(), outs[i][0].data_ptr(), outs[i][1].data_ptr(), ctx[i].shape[1], 0)
+    st = L.stream_ptr()
+    nb = sum((2 * B * K * d + B * d + 9 * B * d) * e for d in dims) * 2 + 2 * B * K * 8
+    rec("A1 gather_concat fwd bf16", nb, timeit(lambda: L.check(L.lib().msf_gather_concat_fwd(items, 8, B, K, 8, L.MSF_BF16, None, st), "gather")),
+        f"c4 size: B={B}/GPU, 4 levels x 2 views in one launch ({nb / 1e6:.0f} MB; 4x that at B=4096 runs at the same rate)")
+    del ctx, tgt, outs
+    for (Bc, Cc, H, W, oh, ow, tag) in ((64, 128, 128, 128, 128, 128, "4x bilinear zoom"), (256, 128, 128, 128, 32, 32, "integer copy (hooknet.py:29-32 case)")):
+        feat = torch.randn(Bc, Cc, H, W, device=dev, generator=g).to(torch.bfloat16)
+        boxes = ops.footprint_boxes(Bc, 4, H, W, dev)
+        outp = torch.empty((Bc, 16, Cc, oh, ow), dtype=torch.bfloat16, device=dev)
+        nb = feat.numel() * e + outp.numel() * e + Bc * 16 * 16
+        fn = lambda: L.check(L.lib().msf_crop_resample_fwd(feat.data_ptr(), Bc, Cc, H, W, boxes.data_ptr(), 16, oh, ow, L.MSF_BF16, outp.data_ptr(), st), "crop")
+        rec(f"A2 crop_resample fwd bf16, {tag}", nb, timeit(fn), f"feat {tuple(feat.shape)} -> 16 footprints of {oh}x{ow}; {100 * outp.numel() * e // nb}% of the bytes are writes")
+        del feat, outp
+    sizes = [64 * 3 * 49, 64, 64] + [64 * 64 * 9] * 4 + [128 * 64 * 9, 128 * 128 * 9] + [256 * 256 * 9] * 3 + [512 * 512 * 9] * 3 + \
+            [4608 * 4608] * 3 + [2304 * 2304] * 3 + [1152 * 1152] * 3 + [576 * 576] * 3 + [512, 256, 128, 64] * 8
+    teacher = [torch.randn(n, device=dev) for n in sizes]
+    student = [torch.randn(n, device=dev) for n in sizes]
+    up = ops.EmaUpdater(teacher, student)
+    rec("E1 ema_multi fp32", 12 * up.numel, timeit(lambda: up.step(0.996)), f"{len(sizes)} tensors, {up.numel / 1e6:.1f} M parameters, one launch")
+    return rows
 
 
 def main():

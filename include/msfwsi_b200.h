@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MSF_ABI_VERSION 1
+#define MSF_ABI_VERSION 2
 
 typedef enum { MSF_F32 = 0, MSF_BF16 = 1, MSF_F16 = 2 } msf_dtype;
 
@@ -54,6 +54,9 @@ int msf_device_check(int* sm_count, int* cc_major, int* cc_minor);
  *   ms_f[b, :]             = [ ctx_f[b, :] | tgt_f[b*K + 0, :] | ... | tgt_f[b*K + n_keep-1, :] ]
  * Exact copies (bit-exact for every dtype).  rev entries outside [-K, K) set bit 0 of
  * *status_flag (device int32, may be NULL) and are clamped; the reference raises IndexError.
+ * ms_f is filled from tgt_f independently of rev, as in the reference, so the forward is defined for ANY in-range index
+ * tensor; the backward (a scatter by the same indices) requires every rev row to be a permutation, which is what the
+ * datasets produce (argsort(randperm(K)), src/utils/data/bcss.py:171-177).
  * ---------------------------------------------------------------------------------------- */
 typedef struct {
   const void* tgt_f;    /* (B*K, d)  target vectors in the shuffled order the encoder saw */
@@ -271,6 +274,8 @@ int msf_bn2d_pool_bwd_elemt(const void* x, const void* dpool, const uint8_t* tap
  *   g = grad * *inv_scale (+ weight_decay * p);  m = m + (1-beta1)*(g - m);  v = beta2*v + (1-beta2)*g*g;
  *   p -= lr[group] / (1 - beta1^t) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps);   t = *step (already incremented)
  *   teacher = ema_momentum * teacher + (1 - ema_momentum) * p   (entries with ema != NULL, when with_ema != 0)
+ *   shadow  = (bf16 | fp16)(p)   (entries with shadow != NULL): the 16-bit operand copy the head GEMMs read, so no
+ *             separate fp32 -> bf16 cast pass runs per step and the copy can never go stale behind a raw-pointer update
  * Nothing is written when *found_inf != 0.  params / exp_avg / exp_avg_sq / ema are fp32; grads fp32, bf16 or fp16.
  * `entries` and `chunk_prefix` are DEVICE arrays (msf_adam_plan fills a HOST prefix from HOST numels; chunks of
  * MSF_ADAM_CHUNK elements); lr is a DEVICE array indexed by entry.group; step / inv_scale / found_inf are DEVICE scalars
@@ -286,7 +291,8 @@ typedef struct {
   void* ema;      /* teacher copy of this parameter or NULL */
   int64_t numel;
   int32_t group;  /* index into lr[] */
-  int32_t reserved;
+  int32_t shadow_dtype; /* MSF_BF16 / MSF_F16 when `shadow` is set, else 0 */
+  void* shadow;   /* 16-bit copy of this parameter (the GEMM operand of the head Linears) rewritten in the same pass, or NULL */
 } msf_adam_entry;
 int msf_adam_plan(const int64_t* numels /*host*/, int n_tensors, int32_t* chunk_prefix /*host, n+1*/);
 /* *found_inf = 1 if any gradient element is NaN/Inf (never cleared here: the caller zeroes it once per step). */

@@ -13,10 +13,10 @@ Importing the package never touches the GPU; the first operator call loads
 lib/libmsfwsi_b200.so and raises if it has not been built (no CPU fallback).
 """
 from . import ops  # noqa: F401
-from .module import DEFAULT_FUSER_WEIGHTS, MSFWSI, TCLinear, make_predictor, make_projector, ssl_loss  # noqa: F401
+from .module import DEFAULT_FUSER_WEIGHTS, MSFWSI, TCLinear, bind_optimizer, make_predictor, make_projector, ssl_loss  # noqa: F401
 from . import checkpoint  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
 from .resnet import resnet18, resnet34  # noqa: F401
 
 __all__ = ["MSFWSI", "ssl_loss", "resnet18", "resnet34", "ops", "make_projector", "make_predictor",
-           "DEFAULT_FUSER_WEIGHTS", "FusedAdam", "checkpoint"]
+           "DEFAULT_FUSER_WEIGHTS", "FusedAdam", "bind_optimizer", "checkpoint"]

@@ -54,7 +54,7 @@ MSF_PEER_MAX_WORLD = 32
 
 class AdamEntry(C.Structure):
     _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("ema", C.c_void_p),
-                ("numel", C.c_int64), ("group", C.c_int32), ("reserved", C.c_int32)]
+                ("numel", C.c_int64), ("group", C.c_int32), ("shadow_dtype", C.c_int32), ("shadow", C.c_void_p)]
 
 
 class EmaEntry(C.Structure):
@@ -121,6 +121,16 @@ EXPORTS = tuple(_SIGS)
 
 _lib = None
 launch_count = 0  # number of C-ABI compute calls made (bench.py reports kernel launches from it)
+
+# Parameters are also written through raw pointers (msf_adam_multi, msf_ema_multi), which never moves a tensor's
+# `_version`.  Every such writer bumps this epoch; anything derived from parameter values (the 16-bit operand copies of
+# the head Linears) keys its cache on it -- unless the writer itself keeps the copy in sync (FusedAdam shadows).
+param_epoch = 0
+
+
+def bump_param_epoch() -> None:
+    global param_epoch
+    param_epoch += 1
 
 
 def lib() -> C.CDLL:

@@ -36,16 +36,25 @@ def save_checkpoint(path: str, model: torch.nn.Module, optimizer: Optional[torch
 
 
 def load_checkpoint(path: str, model: torch.nn.Module, optimizer: Optional[torch.optim.Optimizer] = None, scaler=None,
-                    map_location="cpu", strict: bool = True) -> int:
+                    map_location="cpu", strict: bool = True, weights_only: bool = True, resume_eps: Optional[float] = None) -> int:
     """Resume like ssl_train.py:312-330: accepts checkpoints written by the reference (``module.`` prefix) or by a
-    non-DDP run (no prefix).  Returns the stored epoch."""
-    ckpt = torch.load(path, map_location=map_location, weights_only=False)
+    non-DDP run (no prefix).  Returns the stored epoch.
+
+    ``weights_only=True`` (default) restricts unpickling to tensors and plain containers -- everything this format
+    holds -- so a checkpoint file cannot execute code; pass False only for trusted files with exotic payloads.
+    ``resume_eps``: the reference force-sets Adam's ``eps`` on every param group after a resume (``eps = 0.1``,
+    ssl_train.py:325-326); pass ``resume_eps=0.1`` to reproduce a resumed reference run exactly, leave None to keep
+    the optimizer's own eps."""
+    ckpt = torch.load(path, map_location=map_location, weights_only=weights_only)
     sd = ckpt["state_dict"]
     if all(k.startswith(PREFIX) for k in sd):
         sd = OrderedDict((k[len(PREFIX):], v) for k, v in sd.items())
     _unwrap(model).load_state_dict(sd, strict=strict)
     if optimizer is not None and ckpt.get("optimizer"):
         optimizer.load_state_dict(ckpt["optimizer"])
+        if resume_eps is not None:
+            for group in optimizer.param_groups:
+                group["eps"] = float(resume_eps)
     if scaler is not None and ckpt.get("scaler"):
         scaler.load_state_dict(ckpt["scaler"])
     return int(ckpt.get("epoch", 0))

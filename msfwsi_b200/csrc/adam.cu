@@ -7,7 +7,8 @@
 //                          p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps);  [teacher = mom*teacher + (1-mom)*p]
 //                          skipped entirely when *found_inf != 0 (what GradScaler.step does)
 // HBM-bound: one CTA per 4096-element chunk of a device-resident tensor table (same plan as E1), 16 x 128-bit loads in
-// flight per thread.  Algorithmic bytes per parameter: 16 read (p, g, m, v fp32) + 12 written = 28 B (+8 with EMA).
+// flight per thread.  Algorithmic bytes per parameter: 16 read (p, g, m, v fp32) + 12 written = 28 B (+8 with EMA,
+// +2 where a 16-bit shadow of the parameter -- the GEMM operand of the head Linears -- is rewritten in the same pass).
 #include "common.cuh"
 
 namespace msf {
@@ -148,6 +149,22 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(const msf_adam_entry* __
     store4(static_cast<float*>(e.exp_avg), i, n, vec[q], m[q]);
     store4(static_cast<float*>(e.exp_avg_sq), i, n, vec[q], v[q]);
     if (EMA) store4(static_cast<float*>(e.ema), i, n, vec[q], tch[q]);
+    if (e.shadow) {  // 16-bit operand copy of the stepped parameter (tensor-uniform branch)
+      uint16_t h[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (e.shadow_dtype == MSF_F16) { const __half t = __float2half_rn(p[q][k]); h[k] = *reinterpret_cast<const uint16_t*>(&t); }
+        else { const __nv_bfloat16 t = __float2bfloat16_rn(p[q][k]); h[k] = *reinterpret_cast<const uint16_t*>(&t); }
+      }
+      uint16_t* dst = static_cast<uint16_t*>(e.shadow) + i;
+      if (vec[q] && (reinterpret_cast<uintptr_t>(dst) & 7u) == 0) {
+        *reinterpret_cast<uint2*>(dst) = make_uint2(h[0] | (static_cast<uint32_t>(h[1]) << 16), h[2] | (static_cast<uint32_t>(h[3]) << 16));
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (i + k < n) dst[k] = h[k];
+      }
+    }
   }
 }
 

@@ -24,7 +24,7 @@ struct Segment {
   int32_t mode;        // 0 plain copy; 1 gather src row via idx; 2 scatter dst row via idx (+src2 if dstrow%K<n_keep)
 };
 
-constexpr int kMaxSeg = 2 * MSF_GATHER_MAX_ITEMS;
+constexpr int kMaxSeg = 3 * MSF_GATHER_MAX_ITEMS;
 struct Params {
   Segment seg[kMaxSeg];
   int n_seg;
@@ -174,12 +174,14 @@ extern "C" int msf_gather_concat_fwd(const msf_gather_item* items, int n_items, 
     const uint32_t cpr = it.d / vec;
     const uint32_t ms_stride = (n_keep + 1) * cpr;
     // sorted[b*K+j] = tgt_f[b*K + rev[b,j]]
-    // sorted[b*K+j] = tgt_f[b*K + rev[b,j]]; the same load also fills ms[b, (1+s)*d ...] when the source row
-    // s = rev[b,j] is one of the first n_keep shuffled vectors, so every target row is read exactly once
-    int bad = push(P, it.tgt_f, nullptr, it.tgt_sorted, it.rev, B * K, cpr, cpr, 0, cpr, 1,
-                   static_cast<char*>(it.ms_f) + static_cast<size_t>(cpr) * 16, ms_stride);
+    int bad = push(P, it.tgt_f, nullptr, it.tgt_sorted, it.rev, B * K, cpr, cpr, 0, cpr, 1);
     // ms[b, 0:d] = ctx_f[b]
     bad |= push(P, it.ctx_f, nullptr, it.ms_f, nullptr, B, cpr, cpr, 0, ms_stride, 0);
+    // ms[b, d:(1+n_keep)*d] = tgt_f[b*K : b*K + n_keep].flatten()  -- the first n_keep SHUFFLED vectors of the sample are
+    // adjacent rows, so this is one contiguous n_keep*d copy per sample, independent of `rev` (backbone.py:195-202 builds
+    // ms_f from target_f_split[:, :n_keep] whatever the index tensor holds); the re-read is served by L2
+    bad |= push(P, it.tgt_f, nullptr, static_cast<char*>(it.ms_f) + static_cast<size_t>(cpr) * 16, nullptr, B,
+                static_cast<uint32_t>(n_keep) * cpr, static_cast<uint32_t>(K) * cpr, 0, ms_stride, 0);
     MSF_REQUIRE(!bad, MSF_ERR_UNSUPPORTED, "item %d: more than 2^31 16-byte chunks in one tensor", i);
   }
   P.K = K;

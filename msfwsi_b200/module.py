@@ -25,20 +25,55 @@ DEFAULT_FUSER_WEIGHTS = (0.1, 0.4, 0.7, 1.0)  # --fuser_weights default, tools/s
 
 
 class TCLinear(nn.Linear):
-    """nn.Linear whose bf16-autocast CUDA forward/backward run on this repo's tcgen05 GEMM (ops.linear_tc).
-    Same parameters and state-dict keys as nn.Linear; outside bf16 autocast it is exactly nn.Linear (cuBLAS)."""
+    """nn.Linear whose 16-bit-autocast CUDA forward/backward run on this repo's tcgen05 GEMM (ops.linear_tc).
+    Same parameters and state-dict keys as nn.Linear.
+
+    The GEMM reads a 16-bit copy of the fp32 master weight (what autocast's cast cache holds for F.linear).  The copy
+    is refreshed whenever the parameter changed: ATen in-place writes move ``weight._version``; raw-pointer writers
+    (msf_adam_multi, msf_ema_multi) bump ``_lib.param_epoch`` instead -- unless the copy is *maintained*, i.e. registered
+    with ``FusedAdam.attach_shadows`` (see :func:`bind_optimizer`), in which case the optimizer kernel rewrites it in the
+    same pass as the parameter and no cast runs per step."""
     use_tc = True
 
+    def lowp_weight(self, dtype: torch.dtype) -> torch.Tensor:
+        from . import _lib
+        w = self.weight
+        st = self.__dict__.setdefault("_lowp", {}).get(dtype)
+        key = (w._version, w.data_ptr(), w.device)
+        # maintained = the optimizer bound to THIS storage rewrites the copy itself (a deepcopy / .to() of the module is not)
+        if st is not None and st["key"] == key and (st["maintained_ptr"] == w.data_ptr() or st["epoch"] == _lib.param_epoch):
+            return st["t"]
+        with torch.no_grad():
+            if st is not None and st["t"].device == w.device and st["t"].shape == w.shape:
+                st["t"].copy_(w)  # in place: a maintained shadow keeps its address (the optimizer's table points at it)
+            else:
+                st = {"t": w.detach().to(dtype), "maintained_ptr": None}
+                self._lowp[dtype] = st
+        st["key"], st["epoch"] = key, _lib.param_epoch
+        return st["t"]
+
     def forward(self, x):
-        if (TCLinear.use_tc and x.is_cuda and x.dim() == 2 and torch.is_autocast_enabled()
-                and torch.get_autocast_dtype("cuda") == torch.bfloat16 and self.in_features % 8 == 0 and self.out_features % 8 == 0):
-            # bf16 copy of the master weight, refreshed when the optimizer has written the parameter (both views of a
-            # step share it, like autocast's per-forward cast cache)
-            key = (self.weight._version, self.weight.data_ptr())
-            if getattr(self, "_wb_key", None) != key:
-                self._wb, self._wb_key = self.weight.detach().to(torch.bfloat16), key
-            return ops.linear_tc(x, self.weight, self.bias, self._wb)
+        if TCLinear.use_tc and x.is_cuda and x.dim() == 2 and torch.is_autocast_enabled() and self.in_features % 8 == 0 and self.out_features % 8 == 0:
+            dt = torch.get_autocast_dtype("cuda")
+            if dt == torch.bfloat16:
+                return ops.linear_tc(x, self.weight, self.bias, self.lowp_weight(dt))
         return super().forward(x)
+
+
+def bind_optimizer(model: nn.Module, optimizer, dtype: torch.dtype = torch.bfloat16) -> int:
+    """Register the 16-bit operand copies of every TCLinear weight in ``model`` with a ``FusedAdam`` so that
+    msf_adam_multi rewrites them in the same pass as the fp32 masters (2 extra bytes per head parameter instead of a
+    separate cast of the 99.8 M head parameters every step).  Returns the number of weights bound.  Optional: without it
+    the copies are re-cast after every optimizer step (``_lib.param_epoch``)."""
+    stepped = {id(p) for g in optimizer.param_groups for p in g["params"]}
+    pairs = []
+    for m in model.modules():
+        if isinstance(m, TCLinear) and m.weight.is_cuda and id(m.weight) in stepped:
+            sh = m.lowp_weight(dtype)
+            m._lowp[dtype]["maintained_ptr"] = m.weight.data_ptr()
+            pairs.append((m.weight, sh))
+    optimizer.attach_shadows(pairs)
+    return len(pairs)
 
 
 class FusedBatchNorm1d(nn.Module):
@@ -72,6 +107,8 @@ class FusedBatchNorm1d(nn.Module):
         if self.training and x.is_cuda and x.dim() == 2 and self.num_features % vec == 0:
             import torch.distributed as dist
             sync = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+            if x.shape[0] * (dist.get_world_size() if sync else 1) <= 1:  # what nn.BatchNorm1d / SyncBatchNorm raise
+                raise ValueError(f"Expected more than 1 value per channel when training, got input size {tuple(x.shape)}")
             self.num_batches_tracked.add_(1)
             return ops.bn_act2d(x, self.weight, self.bias, self.running_mean, self.running_var, self.eps, self.momentum,
                                 relu=self.act == "relu", sync_group=dist.group.WORLD if sync else None)

@@ -51,8 +51,14 @@ class _GatherConcat(torch.autograd.Function):
         L.check(L.lib().msf_gather_concat_fwd(items, n_items, B, K, n_keep, L.dtype_code(dt), L.ptr(flag), L.stream_ptr()),
                 "msf_gather_concat_fwd")
         L.launch_count += 1
-        if validate and int(flag.item()) != 0:  # host sync: only on the validating path
-            raise IndexError(f"jigsaw_idx holds values outside [-{K}, {K})")
+        if validate:  # host syncs: only on the validating path
+            if int(flag.item()) != 0:
+                raise IndexError(f"jigsaw_idx holds values outside [-{K}, {K})")
+            want = torch.arange(K, device=rev[0].device)
+            for r in {t.data_ptr(): t for t in rev}.values():
+                if not bool((torch.sort(r.remainder(K), dim=1).values == want).all().item()):
+                    raise ValueError("jigsaw_idx rows must be permutations of range(K) (argsort(randperm(K)), bcss.py:171-177): "
+                                     "the backward scatters by them")
         ctx.save_for_backward(*rev)
         ctx.meta = (K, n_keep, n_items, B, dt, [t.shape[1] for t in ctx_f])
         return (*outs_sorted, *outs_ms)
@@ -84,7 +90,9 @@ class _GatherConcat(torch.autograd.Function):
 def gather_concat(ctx_f: Sequence[torch.Tensor], tgt_f: Sequence[torch.Tensor], rev: Sequence[torch.Tensor],
                   K: int = 16, n_keep: int = 8, validate: bool = False):
     """All items in one launch.  ``ctx_f[i]`` (B,d_i), ``tgt_f[i]`` (B*K,d_i) shuffled, ``rev[i]`` (B,K) int64
-    -> ``(tgt_sorted, ms_f)`` lists.  ``rev`` rows must be permutations (argsort(randperm), bcss.py:171-177)."""
+    -> ``(tgt_sorted, ms_f)`` lists.  The forward is defined for any in-range ``rev`` (``ms_f`` is built from
+    ``tgt_f`` alone, as in the reference); the backward needs ``rev`` rows to be permutations (argsort(randperm),
+    bcss.py:171-177) -- ``validate=True`` checks both, at the cost of host syncs."""
     n = len(ctx_f)
     if not (n == len(tgt_f) == len(rev)) or n == 0 or n > L.MSF_GATHER_MAX_ITEMS:
         raise ValueError("gather_concat: need 1..16 (ctx, tgt, rev) triples")
@@ -180,8 +188,9 @@ def infonce_precision_for(dim: int, dtype: torch.dtype) -> torch.dtype:
 
 
 def all_gather_keys(k_hat: torch.Tensor, group=None) -> Tuple[torch.Tensor, int]:
-    """Rank-major all-gather of the normalised keys.  Returns (keys_all, pos_offset)."""
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+    """Rank-major all-gather of the normalised keys.  Returns (keys_all, pos_offset).
+    ``group=None`` is the default (world) group; ``group=False`` means "this rank holds every key" (no collective)."""
+    if group is False or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return k_hat, 0
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     out = torch.empty((world * k_hat.shape[0], k_hat.shape[1]), dtype=k_hat.dtype, device=k_hat.device)
@@ -662,3 +671,4 @@ class EmaUpdater:
         L.check(L.lib().msf_ema_multi(L.ptr(self._table), L.ptr(self._prefix), self.n, self.total_chunks, L.dtype_code(self.tdt),
                                       L.dtype_code(self.sdt), float(momentum), float(1.0 - float(momentum)), L.stream_ptr()), "msf_ema_multi")
         L.launch_count += 1
+        L.bump_param_epoch()  # teachers changed through raw pointers: derived 16-bit copies must refresh

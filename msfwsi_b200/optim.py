@@ -35,6 +35,8 @@ class FusedAdam(torch.optim.Adam):
         self._keep = None
         self._ema: Dict[int, torch.Tensor] = {}
         self._ema_momentum = None
+        self._shadow: Dict[int, torch.Tensor] = {}
+        self._steps_verified = False  # all `step` counters equal (one shared device counter drives the bias corrections)
         # GradScaler.step() protocol of torch's fused optimizers: the scaler leaves the gradients scaled, sets
         # `self.grad_scale` / `self.found_inf` (device tensors) and this step unscales / skips on the device
         self._step_supports_amp_scaling = True
@@ -52,21 +54,58 @@ class FusedAdam(torch.optim.Adam):
         self._ema_momentum = float(momentum)
         self._table_key = None
 
+    # ---- 16-bit operand copies of parameters (the head Linears' GEMM operands), rewritten in the same pass -----
+    def attach_shadows(self, pairs) -> None:
+        """pairs: iterable of (parameter, shadow) with shadow a dense CUDA bf16 / fp16 tensor of the parameter's shape
+        and strides.  After every step shadow == parameter.to(shadow.dtype), written by msf_adam_multi itself, so a
+        consumer never sees a copy that went stale behind the raw-pointer update (and no cast pass runs per step)."""
+        for p, sh in pairs:
+            if sh.shape != p.shape or sh.stride() != p.stride() or not sh.is_cuda or sh.dtype not in (torch.bfloat16, torch.float16):
+                raise ValueError("attach_shadows: shadows must be CUDA bf16 / fp16 tensors with the parameter's shape and strides")
+            self._shadow[id(p)] = sh
+        self._table_key = None
+
+    def load_state_dict(self, state_dict) -> None:
+        """torch.optim.Adam.load_state_dict + invalidation of the device pointer table (it holds the addresses of the
+        moment tensors, which this call replaces) and of the equal-steps check."""
+        super().load_state_dict(state_dict)
+        self._table_key = None
+        self._keep = None
+        self._steps_verified = False
+
+    def add_param_group(self, param_group) -> None:
+        super().add_param_group(param_group)
+        self._table_key = None
+        self._steps_verified = False
+
     def _build(self, params, grads, groups_of):
         dev = params[0].device
         n = len(params)
+        fresh = 0
         for p in params:
             st = self.state[p]
             if len(st) == 0:
+                fresh += 1
                 st["step"] = torch.zeros((), dtype=torch.float32, device=dev)
                 st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
             elif not st["step"].is_cuda:
                 st["step"] = st["step"].to(device=dev, dtype=torch.float32)  # checkpoints written by the unfused optimizer
+        # One device step counter (the first parameter's) drives the bias corrections of every entry, so all counters
+        # must agree: a parameter that joins later (first gradient after others have stepped) or a checkpoint with
+        # heterogeneous steps is refused instead of silently getting the wrong correction.  Host check only when the
+        # set of states changed (fresh states, load_state_dict), never in the steady state.
+        if 0 < fresh < n or not self._steps_verified:
+            steps = torch.stack([self.state[p]["step"].reshape(()).to(device=dev, dtype=torch.float32) for p in params])
+            if not bool((steps == steps[0]).all().item()):
+                raise RuntimeError("FusedAdam: parameters carry different `step` counts (a parameter received its first gradient "
+                                   "later than the others, or the checkpoint has heterogeneous steps); one shared counter drives "
+                                   "the bias corrections here -- use torch.optim.Adam for this state")
+            self._steps_verified = True
         numels = (C.c_int64 * n)(*[p.numel() for p in params])
         prefix = (C.c_int32 * (n + 1))()
         L.check(L.lib().msf_adam_plan(numels, n, prefix), "msf_adam_plan")
-        table = torch.empty((n, 7), dtype=torch.int64).pin_memory()  # pinned: the upload below never drains the stream
+        table = torch.zeros((n, 8), dtype=torch.int64).pin_memory()  # pinned: the upload below never drains the stream
         any_ema = False
         for i, (p, g) in enumerate(zip(params, grads)):
             st = self.state[p]
@@ -75,7 +114,10 @@ class FusedAdam(torch.optim.Adam):
             table[i, 0], table[i, 1], table[i, 2], table[i, 3] = p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
             table[i, 4] = 0 if t is None else t.data_ptr()
             table[i, 5] = p.numel()
-            table[i, 6] = groups_of[i]  # int32 group in the low half, reserved = 0 (little-endian)
+            sh = self._shadow.get(id(p))
+            # int32 group in the low half, int32 shadow dtype in the high half (little-endian struct layout)
+            table[i, 6] = groups_of[i] | ((L.dtype_code(sh.dtype) if sh is not None else 0) << 32)
+            table[i, 7] = 0 if sh is None else sh.data_ptr()
         prefix_h = torch.tensor(list(prefix), dtype=torch.int32).pin_memory()
         self._keep = (table.to(dev, non_blocking=True), prefix_h.to(dev, non_blocking=True), int(prefix[n]), n, any_ema)
         self._pinned = (table, prefix_h)  # must outlive the asynchronous copies
@@ -118,10 +160,10 @@ class FusedAdam(torch.optim.Adam):
         gdt = grads[0].dtype
         if any(g.dtype != gdt for g in grads):
             raise RuntimeError("FusedAdam: all gradients must share one dtype")
-        key = (tuple(p.data_ptr() for p in params), tuple(g.data_ptr() for g in grads))
+        key = self._key(params, grads)
         if key != self._table_key:  # gradients are re-allocated by zero_grad(set_to_none=True): rebuild the pointer table
             self._build(params, grads, groups_of)
-            self._table_key = key
+            self._table_key = self._key(params, grads)  # _build may have created the moment tensors
         table, prefix, total_chunks, n, any_ema = self._keep
         g0 = self.param_groups[0]
         for group in self.param_groups:
@@ -144,8 +186,20 @@ class FusedAdam(torch.optim.Adam):
                                        float(g0["betas"][1]), float(g0["eps"]), float(g0["weight_decay"]), L.ptr(step_t), L.ptr(inv_scale),
                                        L.ptr(found_inf), int(any_ema), float(m), float(1.0 - m), L.stream_ptr()), "msf_adam_multi")
         L.launch_count += 1
+        L.bump_param_epoch()  # parameters changed behind autograd's back (no `_version` bump): derived caches must refresh
         self._last = (lr, grads)  # keep the device lr array and the gradient tensors alive until the kernel has run
         return loss
+
+    def _key(self, params, grads):
+        """Everything the device pointer table bakes in: parameter, gradient, moment, teacher and shadow addresses."""
+        ptrs = []
+        for p, g in zip(params, grads):
+            st = self.state.get(p, {})
+            m, v = st.get("exp_avg"), st.get("exp_avg_sq")
+            t, sh = self._ema.get(id(p)), self._shadow.get(id(p))
+            ptrs.append((p.data_ptr(), g.data_ptr(), 0 if m is None else m.data_ptr(), 0 if v is None else v.data_ptr(),
+                         0 if t is None else t.data_ptr(), 0 if sh is None else sh.data_ptr()))
+        return tuple(ptrs)
 
     @torch.no_grad()
     def check_grads(self, found_inf: torch.Tensor) -> None:
@@ -154,11 +208,11 @@ class FusedAdam(torch.optim.Adam):
         if not params:
             return
         grads = [_like_layout(p.grad, p) for p in params]
-        key = (tuple(p.data_ptr() for p in params), tuple(g.data_ptr() for g in grads))
+        key = self._key(params, grads)
         if key != self._table_key:
             groups_of = [gi for gi, g in enumerate(self.param_groups) for p in g["params"] if p.grad is not None]
             self._build(params, grads, groups_of)
-            self._table_key = key
+            self._table_key = self._key(params, grads)
         table, prefix, total_chunks, n, _ = self._keep
         L.check(L.lib().msf_grad_check_multi(L.ptr(table), L.ptr(prefix), n, total_chunks, L.dtype_code(grads[0].dtype), L.ptr(found_inf),
                                              L.stream_ptr()), "msf_grad_check_multi")

@@ -31,7 +31,7 @@ def test_every_declared_symbol_is_exported_and_bound():
     for n in names:
         assert hasattr(handle, n), f"{n} declared in include/msfwsi_b200.h but not exported"
     assert sorted(L.EXPORTS) == names, "ctypes binding and header disagree"
-    assert L.lib().msf_abi_version() == 1
+    assert L.lib().msf_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
