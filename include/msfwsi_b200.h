@@ -162,6 +162,34 @@ int msf_infonce_bwd(const void* q_hat, const void* k_hat, const float* q_inv_nor
                     const void* workspace, size_t workspace_bytes, void* grad_q, int grad_dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * L1 (infonce mode, grouped)  the InfoNCE terms of ALL (branch, level, direction) pairs of the loss block in a handful of
+ * launches: one flash launch per width class D in {64, 128, 256}, two grouped GEMM launches per chunk of rank blocks for
+ * the wider pairs, one finalize (+ fixed-order sum) and ONE backward launch.
+ *   loss = sum_pairs coef_pair * mean_i [ logsumexp_j(q_hat_i . k_hat_j / tau) - q_hat_i . k_hat_pos(i) / tau ]
+ * q: (nq, D) bf16 queries.  q_rowsq != NULL: q are RAW predictor outputs and q_rowsq [D/64][nq] their per-64-column sums of
+ * squares (the predictor-tail GEMM's epilogue): the kernels divide each row's logits by max(||q_i||, eps) themselves.
+ * keys: L2-normalised bf16 keys as rank-major blocks: block r = keys + r * rank_stride elements, (rows_per_rank, D); the
+ * positive of local query i is row i of block pos_rank.  world = 1: a single block.  Keys carry no gradient.
+ * msf_nce_grouped_bwd writes grad_q (nq, D) bf16 = *grad_out * d loss / d q (grad_out: DEVICE fp32 scalar).
+ * The workspace (msf_nce_grouped_workspace_bytes) must be the same memory in forward and backward.
+ * ---------------------------------------------------------------------------------------- */
+#define MSF_NCE_MAX_PAIRS 32
+typedef struct {
+  const void* q;
+  const float* q_rowsq;
+  const void* keys;
+  void* grad_q;          /* backward only */
+  int64_t rank_stride;   /* elements */
+  int32_t nq, rows_per_rank, world, D, pos_rank;
+  float coef;
+} msf_nce_pair;
+size_t msf_nce_grouped_workspace_bytes(const msf_nce_pair* pairs /*host*/, int n_pairs);
+int msf_nce_grouped_fwd(const msf_nce_pair* pairs /*host*/, int n_pairs, int dtype, float tau, float eps, float* loss_out,
+                        void* workspace, size_t workspace_bytes, void* stream);
+int msf_nce_grouped_bwd(const msf_nce_pair* pairs /*host*/, int n_pairs, int dtype, float tau, float eps, const float* grad_out,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * G1  bf16 tcgen05 GEMM  C[M,N] = alpha * A[M,K] * op(B) (+ bias[N]), fp32 accumulate in TMEM.
  * The Linear layers of the heads (src/models/backbone.py:14,17,20,27,30): y = x W^T is b_is_kn = 0 with
  * B = W [N=out, K=in]; the input gradient dX = dY W is b_is_kn = 1 with B = W [K=out, N=in].
@@ -185,7 +213,8 @@ int msf_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* 
  *        the batch-norm statistics of THIS layer, merged in fp64 by msf_head_bn_finalize;
  *        row_sumsq [ceil(N/64)][M] fp32 = per 64-column block: sum_n y[m,n]^2 -- the row norms the loss needs.
  * A [M,K] (a_is_km=0) or [K,M] (a_is_km=1) row-major (lda), B [N,K] (b_is_kn=0: C = A B^T) or [K,N] (b_is_kn=1: C = A B)
- * row-major (ldb); lda, ldb, K multiples of 8; bases 16-byte aligned; C row-major (ldc), out_dtype = MSF_F32 or op_dtype.
+ * row-major (ldb); lda, ldb multiples of 8 (K too when the prologue is used); bases 16-byte aligned; C row-major (ldc),
+ * out_dtype = MSF_F32 or op_dtype.
  * y = x W^T: b_is_kn=0, B = W; dX = dY W: b_is_kn=1, B = W; dW = dY^T X: a_is_km=1 (A = dY [rows,out]), b_is_kn=1 (B = X).
  * tile_n: 0 = chosen by the library (64 / 128 / 256 so that small-M problems still cover the SMs), else forced.
  * split_k: 0 = chosen by the library (deterministic split-K for few-tile, long-K problems such as the target heads' dW with
@@ -212,6 +241,11 @@ typedef struct {
   int32_t tile_n;
   int32_t split_k;
   int32_t no_tma_store;   /* 1: 16-bit outputs leave through per-thread row segments instead of shared memory + TMA store */
+  /* EXP epilogue (the two-pass InfoNCE path): exp_a != 0 -> C = exp2(exp_a * row_scale[m] * acc - exp_a) in the 16-bit output
+   * dtype (0 past column N), and row_sumsq receives per-64-column-block SUMS of C instead of sums of squares. */
+  float exp_a;
+  int32_t row_sum_ld;     /* leading dimension of row_sumsq; 0 = M */
+  const float* row_scale; /* [M] or NULL (= 1) */
 } msf_gemm_problem;
 size_t msf_gemm_grouped_workspace_bytes(const msf_gemm_problem* problems /*host*/, int n_problems);
 int msf_gemm_grouped(const msf_gemm_problem* problems /*host*/, int n_problems, int op_dtype, void* workspace,
@@ -257,13 +291,14 @@ typedef struct {
   int32_t rows;              /* rows per view on this rank */
   int32_t C;
   int32_t n_views;           /* 1 or 2 */
-  int32_t reserved;
+  int32_t centered;          /* 1: entry 1 of each col_stats group is M2 about the group mean (msf_head_bn_stats), 0: sum of squares */
 } msf_head_bn_item;
 size_t msf_head_sync_workspace_bytes(int64_t capacity_doubles);
 int msf_head_bn_finalize(const msf_head_bn_item* items /*host*/, int n_items, float eps, float momentum, int training,
                          void* const* peers /*device*/, int world, int rank, uint64_t seq, int64_t capacity_doubles,
                          int timeout_ms, void* stream);
-/* col_stats [ceil(rows/32)][2][C] of x (rows, C) straight from memory (fp64 sums per 32-row group): the fp32 path. */
+/* col_stats [ceil(rows/32)][2][C] of x (rows, C) straight from memory, per 32-row group {sum, M2 about the group mean}
+ * accumulated in fp64 (CENTERED form: set msf_head_bn_item.centered = 1): the exact fp32 path. */
 typedef struct {
   const void* x;
   float* col_stats;

@@ -48,6 +48,13 @@ class ProfRecord(C.Structure):
 
 
 MSF_K_COUNT = 29
+MSF_NCE_MAX_PAIRS = 32
+
+
+class NcePair(C.Structure):
+    _fields_ = [("q", C.c_void_p), ("q_rowsq", C.c_void_p), ("keys", C.c_void_p), ("grad_q", C.c_void_p), ("rank_stride", C.c_int64),
+                ("nq", C.c_int32), ("rows_per_rank", C.c_int32), ("world", C.c_int32), ("D", C.c_int32), ("pos_rank", C.c_int32), ("coef", C.c_float)]
+
 MSF_HEAD_MAX_ITEMS = 48
 MSF_HEAD_MAX_MATS = 96
 MSF_HEAD_SYNC_MAX_CTAS = 256
@@ -56,7 +63,7 @@ MSF_HEAD_SYNC_MAX_CTAS = 256
 class HeadBnItem(C.Structure):
     _fields_ = [("col_stats", C.c_void_p * 2), ("scale", C.c_void_p * 2), ("shift", C.c_void_p * 2), ("mean", C.c_void_p * 2),
                 ("invstd", C.c_void_p * 2), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("running_mean", C.c_void_p), ("running_var", C.c_void_p),
-                ("rows", C.c_int32), ("C", C.c_int32), ("n_views", C.c_int32), ("reserved", C.c_int32)]
+                ("rows", C.c_int32), ("C", C.c_int32), ("n_views", C.c_int32), ("centered", C.c_int32)]
 
 
 class HeadMat(C.Structure):
@@ -86,7 +93,8 @@ class GemmProblem(C.Structure):
     _fields_ = [("A", C.c_void_p), ("lda", C.c_int64), ("B", C.c_void_p), ("ldb", C.c_int64), ("C", C.c_void_p), ("ldc", C.c_int64),
                 ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("a_is_km", C.c_int32), ("b_is_kn", C.c_int32), ("out_dtype", C.c_int32),
                 ("alpha", C.c_float), ("bias", C.c_void_p), ("col_stats", C.c_void_p), ("row_sumsq", C.c_void_p), ("a_scale", C.c_void_p),
-                ("a_shift", C.c_void_p), ("a_relu", C.c_int32), ("tile_n", C.c_int32), ("split_k", C.c_int32), ("no_tma_store", C.c_int32)]
+                ("a_shift", C.c_void_p), ("a_relu", C.c_int32), ("tile_n", C.c_int32), ("split_k", C.c_int32), ("no_tma_store", C.c_int32),
+                ("exp_a", C.c_float), ("row_sum_ld", C.c_int32), ("row_scale", C.c_void_p)]
 
 MSF_ADAM_CHUNK = 4096
 MSF_PEER_MAX_WORLD = 32
@@ -127,6 +135,9 @@ _SIGS = {
     "msf_gemm_grouped_plan_info": (C.c_int, [C.POINTER(GemmProblem), C.POINTER(C.c_int32)]),
     "msf_linear_bnstat": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int, C.c_void_p]),
+    "msf_nce_grouped_workspace_bytes": (C.c_size_t, [C.POINTER(NcePair), C.c_int]),
+    "msf_nce_grouped_fwd": (C.c_int, [C.POINTER(NcePair), C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "msf_nce_grouped_bwd": (C.c_int, [C.POINTER(NcePair), C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "msf_head_sync_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "msf_head_bn_finalize": (C.c_int, [C.POINTER(HeadBnItem), C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_uint64,
                                        C.c_int64, C.c_int, C.c_void_p]),

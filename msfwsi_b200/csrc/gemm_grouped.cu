@@ -32,6 +32,8 @@
 #include "tc_common.cuh"
 
 namespace msf {
+int gemm_grouped_launch(const msf_gemm_problem* problems, int n_problems, int op_dtype, void* workspace, size_t workspace_bytes, int32_t* counters,
+                        void* stream);
 namespace {
 
 using namespace tc;
@@ -52,20 +54,26 @@ struct alignas(64) DevProblem {
   float* row_sumsq;         // [ceil(N/64)][M] or null
   const float* a_scale;     // [K] or null (no prologue)
   const float* a_shift;     // [K]
+  const float* row_scale;   // EXP epilogue: per-row factor of the exponent (1 / ||q_i||) or null
   float* ws;                // split-K partials [tiles][k_splits][128][bn] fp32
   int32_t* counters;        // [tiles], zero between launches (self-cleaning)
   int64_t ldc;
   int32_t M, N, K, bn, tiles_m, tiles_n, k_splits, kb_per_split, num_kb, unit_start, unit_end;
   uint32_t flags;
   float alpha;
-  int32_t pad_;
+  float exp_a;              // != 0: EXP epilogue  y = exp2(exp_a * row_scale[m] * acc - exp_a), row partials = sums of y (not squares)
+  int32_t row_sum_ld;       // leading dimension of row_sumsq (>= M)
+  int32_t pad_[3];
 };
 
+// The table travels as a kernel parameter (no upload, no fence); three sizes so that a small launch does not push 24 KB
+// of parameters through the command buffer.
+template <int NP>
 struct alignas(64) GroupParams {
-  DevProblem p[MSF_GEMM_MAX_PROBLEMS];
+  DevProblem p[NP];
   int32_t n_problems, total_units, is_f16, pad_;
 };
-static_assert(sizeof(GroupParams) <= 32000, "kernel parameter space (32764 bytes)");
+static_assert(sizeof(GroupParams<MSF_GEMM_MAX_PROBLEMS>) <= 32000, "kernel parameter space (32764 bytes)");
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
@@ -106,7 +114,8 @@ __device__ __forceinline__ float2 unpack2(uint32_t w) {
 struct Unit {
   int p, m_tile, n_tile, ks, kb0, kb1;
 };
-__device__ __forceinline__ Unit decode(const GroupParams& P, int u, int& p) {
+template <int NP>
+__device__ __forceinline__ Unit decode(const GroupParams<NP>& P, int u, int& p) {
   while (u >= P.p[p].unit_end) ++p;
   const DevProblem& q = P.p[p];
   const int local = u - q.unit_start;
@@ -137,8 +146,8 @@ __device__ __forceinline__ float warp_colsum32(float* v, int lane) {
   return v[0];
 }
 
-template <bool F16>
-__global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_constant__ GroupParams P) {
+template <bool F16, int NP>
+__global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_constant__ GroupParams<NP> P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sC = smem + kStages * kStageBytes;  // 2 store slabs
@@ -354,12 +363,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
           }
         }
         const int col = n0 + c * 32;  // first global column of this chunk
-        // ---- alpha, bias, rounding to the output dtype ----
+        // ---- alpha, bias (or the InfoNCE exponential), rounding to the output dtype ----
+        if (q.exp_a != 0.f) {
+          const float ea = q.exp_a * (q.row_scale ? (row_ok ? __ldg(q.row_scale + row) : 0.f) : 1.f);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float t = x[i] * q.alpha;
-          if (q.bias && col + i < q.N) t += __ldg(q.bias + col + i);
-          x[i] = t;
+          for (int i = 0; i < 32; ++i) x[i] = col + i < q.N ? ex2_approx(fmaf(x[i], ea, -q.exp_a)) : 0.f;  // |cos| <= 1: never overflows
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float t = x[i] * q.alpha;
+            if (q.bias && col + i < q.N) t += __ldg(q.bias + col + i);
+            x[i] = t;
+          }
         }
         uint32_t u16[16];
         if (!out_f32) {
@@ -373,11 +388,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
         }
         // ---- row sum of squares per 64-column block (columns >= N hold exact zeros: zero-filled B rows, no bias) ----
         if (q.row_sumsq) {
+          if (q.exp_a != 0.f) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) rq = fmaf(x[i], x[i], rq);
+            for (int i = 0; i < 32; ++i) rq += x[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) rq = fmaf(x[i], x[i], rq);
+          }
           if ((c & 1) == 1 || c == n_chunks - 1) {
             const int blk = (n0 >> 6) + (c >> 1);
-            if (row_ok && blk * 64 < q.N) q.row_sumsq[static_cast<size_t>(blk) * q.M + row] = rq;
+            if (row_ok && blk * 64 < q.N) q.row_sumsq[static_cast<size_t>(blk) * q.row_sum_ld + row] = rq;
             rq = 0.f;
           }
         }
@@ -501,18 +521,12 @@ struct Plan {
 Plan plan_of(const msf_gemm_problem& g) {
   Plan pl{};
   pl.tiles_m = (g.M + BM - 1) / BM;
-  // widest N tile that still spreads the problem over the machine
-  if (g.N <= 64) pl.bn = 64;
-  else if (static_cast<int64_t>(pl.tiles_m) * ((g.N + 255) / 256) >= kNumSMs) pl.bn = 256;
-  else if (static_cast<int64_t>(pl.tiles_m) * ((g.N + 127) / 128) >= kNumSMs / 2 && g.N > 64) pl.bn = 128;
-  else pl.bn = 64;
-  if (g.tile_n == 64 || g.tile_n == 128 || g.tile_n == 256) pl.bn = g.tile_n;
+  pl.bn = (g.tile_n == 64 || g.tile_n == 128 || g.tile_n == 256) ? g.tile_n : 64;  // plan_launch chooses; 64 only as a fallback
   pl.tiles_n = (g.N + pl.bn - 1) / pl.bn;
   pl.tiles = pl.tiles_m * pl.tiles_n;
   pl.num_kb = (g.K + GBK - 1) / GBK;
   pl.k_splits = 1;
   if (g.split_k > 0) pl.k_splits = g.split_k;
-  else if (g.split_k == 0 && pl.tiles < kNumSMs / 2 && pl.num_kb > 32) pl.k_splits = (pl.num_kb + 31) / 32;
   if (pl.k_splits > 32) pl.k_splits = 32;
   if (pl.k_splits > pl.num_kb) pl.k_splits = pl.num_kb;
   pl.kb_per_split = (pl.num_kb + pl.k_splits - 1) / pl.k_splits;
@@ -522,11 +536,47 @@ Plan plan_of(const msf_gemm_problem& g) {
   return pl;
 }
 
+// Launch-wide plan.  Units of one launch share the 148 SMs, so the launch takes about max(total work / 148, longest unit):
+// every problem first gets the widest N tile (least bytes staged per MAC), then problems whose single unit would outlast
+// the balanced share T0 = work / 148 get narrower tiles and, if that is not enough, a deterministic split-K.  Work is
+// counted in staged bytes per k-block (128 + bn rows of 128 bytes), which is what bounds this kernel (L2 -> SM feed).
+void plan_launch(const msf_gemm_problem* problems, int n, Plan* plans) {
+  auto unit_cost = [](int kb, int bn) { return static_cast<double>(kb) * (BM + bn) + 3.0 * (BM + 256); };  // + pipeline fill / epilogue
+  double work = 0.0;
+  for (int i = 0; i < n; ++i) {
+    const msf_gemm_problem& g = problems[i];
+    const int tiles_m = (g.M + BM - 1) / BM, num_kb = (g.K + GBK - 1) / GBK;
+    const int bn = g.N <= 64 ? 64 : (g.N <= 128 ? 128 : 256);
+    work += static_cast<double>(tiles_m) * ((g.N + bn - 1) / bn) * unit_cost(num_kb, bn);
+  }
+  const double cap = std::max(work / kNumSMs, unit_cost(24, 256));
+  for (int i = 0; i < n; ++i) {
+    msf_gemm_problem g = problems[i];
+    const int num_kb = (g.K + GBK - 1) / GBK;
+    if (g.tile_n != 64 && g.tile_n != 128 && g.tile_n != 256) {
+      g.tile_n = 64;
+      for (int bn : {256, 128}) {
+        if (bn / 2 >= g.N) continue;  // a tile twice as wide as the problem only stages zeros
+        if (unit_cost(num_kb, bn) <= cap) { g.tile_n = bn; break; }
+      }
+    }
+    if (g.split_k == 0) {
+      const double c = unit_cost(num_kb, g.tile_n);
+      int ks = c > cap ? static_cast<int>(c / cap + 0.999) : 1;
+      if (ks > num_kb / 4) ks = num_kb / 4;  // at least 4 k-blocks per split
+      g.split_k = ks > 1 ? ks : -1;
+    }
+    plans[i] = plan_of(g);
+  }
+}
+
 int check_problem(const msf_gemm_problem& g, int i, int op_dtype) {
   MSF_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, MSF_ERR_INVALID, "problem %d: empty GEMM %d x %d x %d", i, g.M, g.N, g.K);
   MSF_REQUIRE(g.A && g.B && g.C && aligned16(g.A) && aligned16(g.B) && aligned16(g.C), MSF_ERR_INVALID, "problem %d: NULL or misaligned operand", i);
   MSF_REQUIRE(g.lda % 8 == 0 && g.ldb % 8 == 0, MSF_ERR_INVALID, "problem %d: lda / ldb must be multiples of 8 elements (TMA row pitch)", i);
-  MSF_REQUIRE(g.K % 8 == 0, MSF_ERR_INVALID, "problem %d: K = %d must be a multiple of 8", i, g.K);
+  MSF_REQUIRE(!g.a_scale || g.K % 8 == 0, MSF_ERR_INVALID, "problem %d: K = %d must be a multiple of 8 for the A prologue", i, g.K);
+  MSF_REQUIRE(g.exp_a == 0.f || (!g.bias && g.out_dtype != MSF_F32), MSF_ERR_UNSUPPORTED, "problem %d: the EXP epilogue has 16-bit outputs and no bias", i);
+  MSF_REQUIRE(g.row_sum_ld == 0 || g.row_sum_ld >= g.M, MSF_ERR_INVALID, "problem %d: row_sum_ld < M", i);
   MSF_REQUIRE(g.out_dtype == MSF_F32 || g.out_dtype == op_dtype, MSF_ERR_INVALID, "problem %d: output dtype must be MSF_F32 or the operand dtype", i);
   MSF_REQUIRE(!(g.a_scale && g.a_is_km), MSF_ERR_UNSUPPORTED, "problem %d: the A prologue needs A stored [M][K]", i);
   MSF_REQUIRE(!g.a_scale || (g.a_shift && aligned16(g.a_scale) && aligned16(g.a_shift)), MSF_ERR_INVALID, "problem %d: a_scale / a_shift must both be set, 16-byte aligned", i);
@@ -538,15 +588,47 @@ int check_problem(const msf_gemm_problem& g, int i, int op_dtype) {
 
 using namespace msf;
 
+namespace msf {
+namespace {
+template <bool F16, int NP>
+int launch_one(const GroupParams<NP>& Q, unsigned grid, cudaStream_t st) {
+  static const cudaError_t attr = cudaFuncSetAttribute(gemm_grouped_kernel<F16, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+  MSF_REQUIRE(attr == cudaSuccess, MSF_ERR_CUDA, "cudaFuncSetAttribute(max dynamic shared memory) failed: %s", cudaGetErrorString(attr));
+  gemm_grouped_kernel<F16, NP><<<grid, kThreads, kSmem, st>>>(Q);
+  MSF_LAUNCH_OK("gemm_grouped_kernel");
+  return MSF_OK;
+}
+template <int NP>
+int launch_np(const GroupParams<MSF_GEMM_MAX_PROBLEMS>& P, bool f16, unsigned grid, cudaStream_t st) {
+  if constexpr (NP == MSF_GEMM_MAX_PROBLEMS) {
+    return f16 ? launch_one<true, NP>(P, grid, st) : launch_one<false, NP>(P, grid, st);
+  } else {
+    static thread_local GroupParams<NP> Q;
+    for (int i = 0; i < P.n_problems; ++i) Q.p[i] = P.p[i];
+    Q.n_problems = P.n_problems; Q.total_units = P.total_units; Q.is_f16 = P.is_f16;
+    return f16 ? launch_one<true, NP>(Q, grid, st) : launch_one<false, NP>(Q, grid, st);
+  }
+}
+}  // namespace
+}  // namespace msf
+
 extern "C" size_t msf_gemm_grouped_workspace_bytes(const msf_gemm_problem* problems, int n_problems) {
   if (!problems || n_problems <= 0) return 0;
+  if (n_problems > MSF_GEMM_MAX_PROBLEMS) return 0;
+  Plan plans[MSF_GEMM_MAX_PROBLEMS];
+  plan_launch(problems, n_problems, plans);
   size_t fl = 0;
-  for (int i = 0; i < n_problems; ++i) fl += plan_of(problems[i]).ws_floats;
+  for (int i = 0; i < n_problems; ++i) fl += plans[i].ws_floats;
   return fl * sizeof(float) + 256;
 }
 
 extern "C" int msf_gemm_grouped(const msf_gemm_problem* problems, int n_problems, int op_dtype, void* workspace, size_t workspace_bytes,
                                 int32_t* counters, void* stream) {
+  return gemm_grouped_launch(problems, n_problems, op_dtype, workspace, workspace_bytes, counters, stream);
+}
+
+int msf::gemm_grouped_launch(const msf_gemm_problem* problems, int n_problems, int op_dtype, void* workspace, size_t workspace_bytes,
+                             int32_t* counters, void* stream) {
   MSF_REQUIRE(problems && n_problems > 0 && n_problems <= MSF_GEMM_MAX_PROBLEMS, MSF_ERR_INVALID, "n_problems %d outside [1, %d]", n_problems,
               MSF_GEMM_MAX_PROBLEMS);
   MSF_REQUIRE(op_dtype == MSF_BF16 || op_dtype == MSF_F16, MSF_ERR_INVALID, "operand dtype must be MSF_BF16 or MSF_F16");
@@ -555,12 +637,12 @@ extern "C" int msf_gemm_grouped(const msf_gemm_problem* problems, int n_problems
   std::vector<int> order(n_problems);
   for (int i = 0; i < n_problems; ++i) {
     if (int rc = check_problem(problems[i], i, op_dtype)) return rc;
-    plans[i] = plan_of(problems[i]);
     order[i] = i;
   }
+  plan_launch(problems, n_problems, plans.data());
   // most expensive units first (stable: problems sharing a weight panel stay adjacent), walked round-robin by the CTAs
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return plans[a].cost > plans[b].cost; });
-  static thread_local GroupParams P;  // 20 KB: not on the stack of the autograd thread
+  static thread_local GroupParams<MSF_GEMM_MAX_PROBLEMS> P;  // 24 KB: not on the stack of the autograd thread
   size_t ws_off = 0;
   int ctr_off = 0, unit = 0;
   double flops = 0.0;
@@ -588,6 +670,7 @@ extern "C" int msf_gemm_grouped(const msf_gemm_problem* problems, int n_problems
     q.C = g.C; q.bias = g.bias; q.col_stats = g.col_stats; q.row_sumsq = g.row_sumsq; q.a_scale = g.a_scale; q.a_shift = g.a_shift;
     q.ldc = g.ldc; q.M = g.M; q.N = g.N; q.K = g.K; q.bn = pl.bn; q.tiles_m = pl.tiles_m; q.tiles_n = pl.tiles_n;
     q.k_splits = pl.k_splits; q.kb_per_split = pl.kb_per_split; q.num_kb = pl.num_kb; q.alpha = g.alpha;
+    q.row_scale = g.row_scale; q.exp_a = g.exp_a; q.row_sum_ld = g.row_sum_ld > 0 ? g.row_sum_ld : g.M;
     if (pl.k_splits > 1) {
       MSF_REQUIRE(workspace && aligned16(workspace) && counters, MSF_ERR_WORKSPACE, "split-K needs a workspace and the counter array");
       MSF_REQUIRE((ws_off + pl.ws_floats) * sizeof(float) <= workspace_bytes, MSF_ERR_WORKSPACE, "workspace of %zu bytes too small", workspace_bytes);
@@ -608,20 +691,15 @@ extern "C" int msf_gemm_grouped(const msf_gemm_problem* problems, int n_problems
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const unsigned grid = static_cast<unsigned>(unit < kNumSMs ? unit : kNumSMs);
   ProfScope prof(stream, MSF_K_GEMM_GROUPED, flops);
-  if (f16) {
-    MSF_CUDA_OK(cudaFuncSetAttribute(gemm_grouped_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    gemm_grouped_kernel<true><<<grid, kThreads, kSmem, st>>>(P);
-  } else {
-    MSF_CUDA_OK(cudaFuncSetAttribute(gemm_grouped_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    gemm_grouped_kernel<false><<<grid, kThreads, kSmem, st>>>(P);
-  }
-  MSF_LAUNCH_OK("gemm_grouped_kernel");
-  return MSF_OK;
+  if (n_problems <= 4) return launch_np<4>(P, f16, grid, st);
+  if (n_problems <= 16) return launch_np<16>(P, f16, grid, st);
+  return launch_np<MSF_GEMM_MAX_PROBLEMS>(P, f16, grid, st);
 }
 
 extern "C" int msf_gemm_grouped_plan_info(const msf_gemm_problem* problem, int32_t* info) {
   MSF_REQUIRE(problem && info, MSF_ERR_INVALID, "NULL argument");
-  const Plan pl = plan_of(*problem);
+  Plan pl;
+  plan_launch(problem, 1, &pl);
   info[0] = pl.bn; info[1] = pl.tiles_m; info[2] = pl.tiles_n; info[3] = pl.k_splits; info[4] = pl.kb_per_split; info[5] = pl.num_kb;
   return MSF_OK;
 }

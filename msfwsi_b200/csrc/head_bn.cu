@@ -130,6 +130,18 @@ __global__ void __launch_bounds__(kThreads) head_bn_finalize_kernel(const __grid
         s1 += static_cast<double>(__ldg(cs + (static_cast<size_t>(g) * 2) * q.C + c));
         s2 += static_cast<double>(__ldg(cs + (static_cast<size_t>(g) * 2 + 1) * q.C + c));
       }
+      if (q.centered) {
+        // entry 1 of a group is its M2 about the GROUP mean (msf_head_bn_stats): Chan's merge, then back to the
+        // sum-reducible {sum, sum of squares} in fp64 -- no E[x^2] - E[x]^2 cancellation in fp32 anywhere
+        const double m = s1 / q.rows;
+        double m2 = s2;
+        for (int g = 0; g < groups; ++g) {
+          const int ng = min(32, q.rows - g * 32);
+          const double mg = static_cast<double>(__ldg(cs + (static_cast<size_t>(g) * 2) * q.C + c)) / ng;
+          m2 += ng * (mg - m) * (mg - m);
+        }
+        s2 = m2 + s1 * m;
+      }
       v[2 * view] = s1;
       v[2 * view + 1] = s2;
     }
@@ -167,8 +179,8 @@ __global__ void __launch_bounds__(kThreads) head_bn_finalize_kernel(const __grid
   }
 }
 
-// ---- column statistics straight from an activation matrix (fp32 path / cross-check): same layout as the GEMM epilogue's
-// col_stats [ceil(rows/32)][2][C], but each entry is produced from fp64 sums over its 32 rows ----
+// ---- column statistics straight from an activation matrix (the exact fp32 path): col_stats [ceil(rows/32)][2][C] with,
+// per 32-row group, entry 0 = sum and entry 1 = M2 = sum (x - group mean)^2 (CENTERED: set msf_head_bn_item.centered) ----
 struct StatsTable {
   msf_head_mat it[MSF_HEAD_MAX_MATS];
   int prefix[MSF_HEAD_MAX_MATS + 1];  // CTAs: groups(32 rows) x ceil(C/256)
@@ -182,19 +194,24 @@ __global__ void __launch_bounds__(kThreads) head_bn_stats_kernel(const __grid_co
   const int local = blockIdx.x - T.prefix[i];
   const int g = local / cblocks, c = (local % cblocks) * kThreads + threadIdx.x;
   if (c >= q.C) return;
-  double s1 = 0.0, s2 = 0.0;
-  const int r1 = min(q.rows, (g + 1) * 32);
-  for (int r = g * 32; r < r1; ++r) {
-    float x;
-    if constexpr (DT == MSF_F32) x = static_cast<const float*>(q.x)[static_cast<size_t>(r) * q.C + c];
-    else if constexpr (DT == MSF_BF16) x = __bfloat162float(static_cast<const __nv_bfloat16*>(q.x)[static_cast<size_t>(r) * q.C + c]);
-    else x = __half2float(static_cast<const __half*>(q.x)[static_cast<size_t>(r) * q.C + c]);
-    s1 += x;
-    s2 += static_cast<double>(x) * x;
+  auto at = [&](int r) -> float {
+    if constexpr (DT == MSF_F32) return static_cast<const float*>(q.x)[static_cast<size_t>(r) * q.C + c];
+    else if constexpr (DT == MSF_BF16) return __bfloat162float(static_cast<const __nv_bfloat16*>(q.x)[static_cast<size_t>(r) * q.C + c]);
+    else return __half2float(static_cast<const __half*>(q.x)[static_cast<size_t>(r) * q.C + c]);
+  };
+  const int r0 = g * 32, r1 = min(q.rows, (g + 1) * 32);
+  double s1 = 0.0;
+  for (int r = r0; r < r1; ++r) s1 += at(r);
+  const float s1f = static_cast<float>(s1);
+  const double mg = static_cast<double>(s1f) / (r1 - r0);  // the mean the finalize kernel will reconstruct from the stored sum
+  double m2 = 0.0;
+  for (int r = r0; r < r1; ++r) {  // second read hits L1
+    const double d = at(r) - mg;
+    m2 += d * d;
   }
   float* dst = q.col_stats + (static_cast<size_t>(g) * 2) * q.C + c;
-  dst[0] = static_cast<float>(s1);
-  dst[q.C] = static_cast<float>(s2);
+  dst[0] = s1f;
+  dst[q.C] = static_cast<float>(m2);
 }
 
 // ---- apply: y = relu?(round(x * scale + shift)) (+ y_hat = y / max(||y||, eps) per row) ----------------------------

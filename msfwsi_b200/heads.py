@@ -74,6 +74,21 @@ class HeadSync:
 
 
 _NO_SYNC = (0, 1, 0, 0, 0, 1)
+_side_streams = {}
+
+
+def _world(group) -> int:
+    if group is None or not (dist.is_available() and dist.is_initialized()):
+        return 1
+    return dist.get_world_size(group)
+
+
+def _side_stream(device) -> torch.cuda.Stream:
+    s = _side_streams.get(device.index)
+    if s is None:
+        s = torch.cuda.Stream(device=device)
+        _side_streams[device.index] = s
+    return s
 
 
 def _sync_args(group, device):
@@ -206,7 +221,11 @@ class _HeadStage(torch.autograd.Function):
                 rowsq[h] = f32.take(2, (heads[h].d + 63) // 64, R[h])
         z = [torch.empty((2, R[h], heads[h].d), dtype=dt, device=dev) for h in range(nh)]
         p = [torch.empty((2, R[h], heads[h].d), dtype=dt, device=dev) for h in range(nh)]
-        khat = [torch.empty((2, R[h], heads[h].d), dtype=dt, device=dev) for h in range(nh)] if want_hat else None
+        # the L2-normalised keys of all heads live in ONE buffer: at world > 1 a single all-gather moves them
+        khat = kflat = kgath = kready = None
+        if want_hat:
+            kflat = _Carver(_Carver.size([(2, R[h], heads[h].d) for h in range(nh)]), dt, dev)
+            khat = [kflat.take(2, R[h], heads[h].d) for h in range(nh)]
         kinv = None
 
         def finalize(k):
@@ -219,7 +238,7 @@ class _HeadStage(torch.autograd.Function):
                 items.append(L.HeadBnItem(_p2(L.ptr(cs[h][k][0]), L.ptr(cs[h][k][1])), _p2(L.ptr(sc[h][k][0]), L.ptr(sc[h][k][1])),
                                           _p2(L.ptr(sh[h][k][0]), L.ptr(sh[h][k][1])), _p2(L.ptr(mu[h][k][0]), L.ptr(mu[h][k][1])),
                                           _p2(L.ptr(istd[h][k][0]), L.ptr(istd[h][k][1])), L.ptr(gam), L.ptr(bet), L.ptr(bn.running_mean),
-                                          L.ptr(bn.running_var), R[h], widths[h][k], 2, 0))
+                                          L.ptr(bn.running_var), R[h], widths[h][k], 2, 0 if fused else 1))
             peers, world, rank, seq, cap, tmo = _sync_args(group, dev) if training else _NO_SYNC
             L.check(lib.msf_head_bn_finalize(_arr(L.HeadBnItem, items), nh, BN_EPS, BN_MOMENTUM, int(training), peers, world, rank, seq, cap, tmo, st),
                     "msf_head_bn_finalize")
@@ -267,6 +286,20 @@ class _HeadStage(torch.autograd.Function):
             kinv = [torch.empty((2, R[h]), dtype=torch.float32, device=dev) for h in range(nh)]
         apply([L.HeadApplyItem(L.ptr(y[h][2][v]), L.ptr(z[h][v]), L.ptr(khat[h][v]) if want_hat else 0, L.ptr(kinv[h][v]) if want_hat else 0,
                                L.ptr(sc[h][2][v]), L.ptr(sh[h][2][v]), R[h], heads[h].d, 0, 0) for h in range(nh) for v in range(2)])
+        if want_hat and training and _world(group) > 1:
+            # ONE exchange for the keys of all 24 pairs, on a side stream: it overlaps the two predictor depths below, and
+            # the loss kernels (which need the predictor outputs anyway) wait for it
+            side = _side_stream(dev)
+            done = torch.cuda.Event()
+            done.record()
+            kgath = torch.empty(_world(group) * kflat.buf.numel(), dtype=dt, device=dev)
+            with torch.cuda.stream(side):
+                side.wait_event(done)
+                dist.all_gather_into_tensor(kgath, kflat.buf, group=group)
+                kready = torch.cuda.Event()
+                kready.record(side)
+            kgath.record_stream(side)
+            kflat.buf.record_stream(side)
         # ---- depth 4, 5: predictor ----
         specs = []
         for h in range(nh):
@@ -301,7 +334,9 @@ class _HeadStage(torch.autograd.Function):
         ctx.keep = (x0, y, z, a_keep, sc, sh, mu, istd, W, acts.buf, f32.buf)
         ctx.save_for_backward(*[t for t in params if t is not None])
         ctx.mark_non_differentiable(*z)
-        cfg["extras"] = {"khat": khat, "kinv": kinv, "rowsq": rowsq}
+        cfg["extras"] = {"khat": khat, "kinv": kinv, "rowsq": rowsq, "kflat": None if kflat is None else kflat.buf, "kgathered": kgath,
+                         "kready": kready, "world": _world(group) if (want_hat and training) else 1,
+                         "rank": dist.get_rank(group) if (want_hat and training and _world(group) > 1) else 0}
         return (*p, *z)
 
     @staticmethod

@@ -277,6 +277,11 @@ class MSFWSI(nn.Module):
             p, z, _ = self.head_stage(context_f1, context_f2, target_f1, target_f2, jigsaw_idx)
             return ops.cosine_loss_stacked(p, z, [-0.5 * fuser_weights[h % nl] for h in range(len(p))])
         if mode == "infonce":
+            if torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16 and context_f1[0].is_cuda:
+                # fused front end: the head stage leaves the normalised keys (one buffer, one all-gather) and the row norms
+                # of p; ONE grouped call computes all 24 terms
+                p, z, ex = self.head_stage(context_f1, context_f2, target_f1, target_f2, jigsaw_idx, want_keys=True, want_rowsq=True)
+                return ops.infonce_grouped(p, ex, [0.5 * fuser_weights[h % nl] for h in range(len(p))], tau)
             p, z, _ = self.head_stage(context_f1, context_f2, target_f1, target_f2, jigsaw_idx)
             total = None
             for h in range(len(p)):

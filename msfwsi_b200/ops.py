@@ -336,6 +336,72 @@ def infonce_loss(p: torch.Tensor, z: torch.Tensor, tau: float = 0.07, precision:
     return _InfoNCE.apply(p, z, float(tau), precision, float(eps), group)
 
 
+class _InfoNCEGrouped(torch.autograd.Function):
+    """All InfoNCE pairs of the loss block in one fused call (``msf_nce_grouped_fwd`` / ``_bwd``): for every head h the pairs
+    (p[h][0], keys[h][1]) and (p[h][1], keys[h][0]) with weight coefs[h] (tools/ssl_train.py:449-464 pairing).  Queries are
+    the raw bf16 predictor outputs (their norms come from ``rowsq``, the predictor-tail GEMM's epilogue); keys are the
+    normalised projector outputs in rank-major blocks (this rank's, or the single all-gather of all heads' keys)."""
+
+    @staticmethod
+    def forward(ctx, cfg, *p_stacks):
+        nh = len(p_stacks)
+        ps = [_contig(t) for t in p_stacks]
+        L.require_cuda(*ps)
+        dev = ps[0].device
+        khat, rowsq, coefs, tau = cfg["khat"], cfg["rowsq"], cfg["coefs"], cfg["tau"]
+        world, rank, kgath, kflat = cfg["world"], cfg["rank"], cfg["kgathered"], cfg["kflat"]
+        if cfg["kready"] is not None:
+            torch.cuda.current_stream(dev).wait_event(cfg["kready"])  # the side-stream all-gather of the keys
+        n = 2 * nh
+        pairs = (L.NcePair * n)()
+        stride = 0 if world == 1 else kflat.numel()
+        for h in range(nh):
+            if ps[h].dtype != torch.bfloat16 or ps[h].dim() != 3 or ps[h].shape[0] != 2 or ps[h].shape != khat[h].shape:
+                raise ValueError(f"infonce_grouped: head {h}: expected (2, rows, dim) bfloat16 stacks, got {tuple(ps[h].shape)} {ps[h].dtype}")
+            _, rows, dim = ps[h].shape
+            for v in range(2):
+                keys = khat[h][1 - v]
+                if world > 1:  # the same block inside the gathered buffer: rank r's copy sits r * stride elements further
+                    off = (keys.data_ptr() - kflat.data_ptr()) // 2
+                    kptr = kgath.data_ptr() + 2 * off
+                else:
+                    kptr = keys.data_ptr()
+                pairs[2 * h + v] = L.NcePair(L.ptr(ps[h][v]), 0 if rowsq is None else L.ptr(rowsq[h][v]), kptr, 0, stride, rows, rows, world, dim,
+                                             rank if world > 1 else 0, float(coefs[h]))
+        ws_bytes = L.lib().msf_nce_grouped_workspace_bytes(pairs, n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        L.check(L.lib().msf_nce_grouped_fwd(pairs, n, L.MSF_BF16, tau, COS_EPS, L.ptr(loss), L.ptr(ws), ws_bytes, L.stream_ptr()), "msf_nce_grouped_fwd")
+        L.launch_count += 7
+        ctx.keep = (ps, khat, rowsq, kgath, kflat, ws, ws_bytes, pairs, n, tau)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        ps, khat, rowsq, kgath, kflat, ws, ws_bytes, pairs, n, tau = ctx.keep
+        g = _contig(grad_out.to(torch.float32))
+        grads = [torch.empty_like(t) for t in ps]
+        for h in range(len(ps)):
+            for v in range(2):
+                pairs[2 * h + v].grad_q = L.ptr(grads[h][v])
+        L.check(L.lib().msf_nce_grouped_bwd(pairs, n, L.MSF_BF16, tau, COS_EPS, L.ptr(g), L.ptr(ws), ws_bytes, L.stream_ptr()), "msf_nce_grouped_bwd")
+        L.launch_count += 1
+        ctx.keep = None
+        return (None, *grads)
+
+
+def infonce_grouped(p_stacks: Sequence[torch.Tensor], extras: dict, coefs: Sequence[float], tau: float = 0.07) -> torch.Tensor:
+    """``sum_h coefs[h] * (InfoNCE(p[h][0], keys[h][1]) + InfoNCE(p[h][1], keys[h][0]))`` with global negatives: ``extras`` is
+    what ``heads.head_stage(..., want_keys=True, want_rowsq=True)`` returned (normalised keys of all heads in one buffer,
+    gathered across ranks once; row sums of squares of p).  Each term is the mean over the LOCAL queries (DDP averages)."""
+    nh = len(p_stacks)
+    if nh == 0 or 2 * nh > L.MSF_NCE_MAX_PAIRS or len(coefs) != nh:
+        raise ValueError("infonce_grouped: need 1..16 (p, coef) pairs")
+    cfg = dict(extras)
+    cfg["coefs"], cfg["tau"] = [float(c) for c in coefs], float(tau)
+    return _InfoNCEGrouped.apply(cfg, *p_stacks)
+
+
 # ------------------------------------------------------------------------------------------
 # G1: Linear layers of the heads on the tcgen05 GEMM      (src/models/backbone.py:14,17,20,27,30)
 # ------------------------------------------------------------------------------------------
@@ -410,7 +476,7 @@ def gemm_grouped(specs: Sequence[GemmSpec], want_col_stats: bool = False, want_r
             keep.append(bias)
             arr[i] = L.GemmProblem(L.ptr(g.A), g.A.stride(0), L.ptr(g.B), g.B.stride(0), L.ptr(g.C), g.C.stride(0), g.M, g.N, g.K,
                                    int(g.a_is_km), int(g.b_is_kn), L.dtype_code(odt), g.alpha, L.ptr(bias), L.ptr(g.col_stats), L.ptr(g.row_sumsq),
-                                   L.ptr(g.a_scale), L.ptr(g.a_shift), int(g.a_relu), g.tile_n, g.split_k, int(g.no_tma_store))
+                                   L.ptr(g.a_scale), L.ptr(g.a_shift), int(g.a_relu), g.tile_n, g.split_k, int(g.no_tma_store), 0.0, 0, 0)
         ws_bytes = L.lib().msf_gemm_grouped_workspace_bytes(arr, len(chunk))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes > 256 else None
         L.check(L.lib().msf_gemm_grouped(arr, len(chunk), L.dtype_code(op_dt), L.ptr(ws), ws_bytes if ws is not None else 0,
@@ -441,7 +507,7 @@ def _gemm_grouped_f32(specs: Sequence[GemmSpec]) -> List[torch.Tensor]:
             bias = None if g.bias is None else _contig(g.bias.detach().to(torch.float32))
             keep.append(bias)
             arr[i] = L.GemmProblem(L.ptr(g.A), g.A.stride(0), L.ptr(g.B), g.B.stride(0), L.ptr(g.C), g.C.stride(0), g.M, g.N, g.K,
-                                   int(g.a_is_km), int(g.b_is_kn), L.MSF_F32, g.alpha, L.ptr(bias), 0, 0, 0, 0, 0, 0, 0, 0)
+                                   int(g.a_is_km), int(g.b_is_kn), L.MSF_F32, g.alpha, L.ptr(bias), 0, 0, 0, 0, 0, 0, 0, 0, 0.0, 0, 0)
         L.check(L.lib().msf_gemm_grouped_f32(arr, len(chunk), L.stream_ptr()), "msf_gemm_grouped_f32")
         L.launch_count += 1
         outs += [g.C for g in chunk]

@@ -5,7 +5,9 @@ graph -- nn.Linear / nn.BatchNorm1d / ReLU heads of src/models/backbone.py:12-31
 
 Tolerances: fp32 (exact SIMT path) outputs 2e-5, gradients 1e-4 relative; bf16 / fp16 autocast: outputs within 3e-2 relative
 Frobenius of torch's own 16-bit run (two 16-bit evaluations of a 5-layer head with batch norms differ by rounding noise of
-that size), loss within 2e-3, every parameter gradient cosine >= 0.99 and the whole gradient vector >= 0.9999."""
+that size), loss within 2e-3, every parameter gradient cosine >= 0.99 to torch's 16-bit gradient, and the whole gradient
+vector at least as close to the fp32 gradient of the same graph as torch's own 16-bit gradient is (>= 0.999; measured on the
+B200: both ~0.9997, while the two 16-bit runs agree with each other to ~0.9995)."""
 import pytest
 import torch
 
@@ -91,7 +93,17 @@ def test_head_stage_matches_reference_module_graph(dtype, B):
                 assert a.requires_grad == name.startswith("p")
     assert abs(float(loss_m) - float(loss_r)) <= (1e-5 if dtype is None else 2e-3) * max(1.0, abs(float(loss_r)))
     pr = dict(ref.named_parameters())
-    gm, gr = [], []
+    truth = None
+    if dtype is not None:
+        # 16-bit runs are judged against the fp32 gradient of the same graph: this repo's 16-bit gradient must be as close
+        # to it as torch's own 16-bit gradient is (two 16-bit evaluations differ from each other by more than either
+        # differs from the truth when batch norms over few rows amplify the rounding noise)
+        ref32 = R.RefMSFWSI(lambda **kw: _Null(**kw), 4).to(DEV).train()
+        ref32.load_state_dict({k: v for k, v in mine.state_dict().items() if not k.endswith("num_batches_tracked")}, strict=False)
+        f32 = lambda vs: [tuple(t.float() for t in v) for v in vs]
+        _run(ref32, lambda o: R.ref_ssl_loss(o, W), f32(cf), f32(tf), rev, None)
+        truth = dict(ref32.named_parameters())
+    gm, gr, gt = [], [], []
     worst = 1.0
     for n, p in mine.named_parameters():
         assert p.grad is not None and pr[n].grad is not None, n
@@ -102,9 +114,15 @@ def test_head_stage_matches_reference_module_graph(dtype, B):
             assert _rel(p.grad, pr[n].grad) <= grad_tol, (n, _rel(p.grad, pr[n].grad))
         else:
             assert c >= 0.99, (n, c)  # small tensors (16-wide batch-norm betas) carry visible 16-bit noise; the whole vector is checked below
+            gt.append(truth[n].grad.flatten().double())
         gm.append(p.grad.flatten().double())
         gr.append(pr[n].grad.flatten().double())
-    assert _cos(torch.cat(gm), torch.cat(gr)) >= 0.9999
+    if dtype is None:
+        assert _cos(torch.cat(gm), torch.cat(gr)) >= 0.9999
+    else:
+        c_mine, c_torch = _cos(torch.cat(gm), torch.cat(gt)), _cos(torch.cat(gr), torch.cat(gt))
+        print(f"gradient cosine to the fp32 truth: this repo {c_mine:.6f}, torch {dtype} {c_torch:.6f}; between the two 16-bit runs {_cos(torch.cat(gm), torch.cat(gr)):.6f}")
+        assert c_mine >= 0.999 and c_mine >= c_torch - 3e-4, (c_mine, c_torch)
     for vm, vr in zip(lc_m + lt_m, lc_r + lt_r):
         for a, b in zip(vm, vr):
             assert a.grad is not None and a.grad.dtype == a.dtype
@@ -188,3 +206,25 @@ def test_heads_loss_stacked_equals_tuple_api():
     gb = torch.autograd.grad(b, [p for p in mine.parameters()])
     assert float(a) == float(b)
     assert all(torch.equal(x, y) for x, y in zip(ga, gb)), "deterministic kernels: the two entry points must agree bit for bit"
+
+
+def test_heads_loss_infonce_grouped_follows_torch_expression():
+    """bf16 autocast, mode="infonce": fused front end (keys normalised in the batch-norm apply, row norms of p from the
+    predictor-tail GEMM epilogue, ONE grouped InfoNCE call for all 24 pairs) vs the torch expression on the reference graph."""
+    mine, ref = _pair(16)
+    cf, tf, rev = _features(48, torch.bfloat16)
+    before = L.launch_count
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        a = mine.heads_loss(cf[0], cf[1], tf[0], tf[1], rev, W, mode="infonce", tau=0.07)
+    a.backward()
+    launches = L.launch_count - before
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        b = R.ref_ssl_loss(ref.heads(cf[0], cf[1], tf[0], tf[1], rev), W, mode="infonce", tau=0.07)
+    b.backward()
+    assert abs(float(a) - float(b)) <= 5e-3 * abs(float(b)), (float(a), float(b))
+    pr = dict(ref.named_parameters())
+    gm = torch.cat([p.grad.flatten().double() for n, p in mine.named_parameters()])
+    gr = torch.cat([pr[n].grad.flatten().double() for n, p in mine.named_parameters()])
+    print(f"infonce grouped: loss {float(a):.5f} vs torch {float(b):.5f}; gradient cosine {_cos(gm, gr):.6f}; {launches} launches fwd+bwd")
+    assert _cos(gm, gr) >= 0.999
+    assert launches <= 40
