@@ -520,6 +520,23 @@ int msf_jigsaw_tiles(const uint8_t* src, int64_t B, int H, int W, int grid, cons
                      const float* mean3 /*host*/, const float* std3 /*host*/, void* out, int out_dtype,
                      int32_t* status_flag, void* stream);
 
+/* D1b  every view of a step from the uint8 source tiles in ONE launch, written in the stem convolution's input layout
+ * (msf_stem_s2d's output: (n, (oh+6)/2, (ow+6)/2, 16) NHWC, zero padding and zero channels included).
+ *   view i = normalise(hflip?(resize_bilinear(src[sample][y0:y1, x0:x1] -> oh x ow)))
+ * = the reference's geometric augmentations once their random numbers are drawn (albumentations RandomResizedCrop -> an
+ * integer crop box, HorizontalFlip, Normalize; tools/ssl_train.py:175-217) on the whole tile (context views) or on tile
+ * jigsaw_idx[j] of blockshaped(img, 256, 256) (target views, src/utils/data/bcss.py:171-177: box = tile origin + crop).
+ * crops is a DEVICE array; boxes are integer source-pixel coordinates [y0, y1) x [x0, x1) inside the (H, W) image;
+ * out-of-range entries set bit 0 of *status_flag and are clamped.  oh and ow must be even. */
+typedef struct {
+  int32_t sample;         /* index into src's first dimension */
+  int32_t y0, x0, y1, x1;
+  int32_t flip;           /* 1: horizontal flip of the resized crop */
+} msf_view_crop;
+int msf_view_crops_s2d(const uint8_t* src, int64_t B, int H, int W, const msf_view_crop* crops /*device*/, int64_t n_views,
+                       int oh, int ow, const float* mean3 /*host*/, const float* std3 /*host*/, void* out, int out_dtype,
+                       int32_t* status_flag, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Measurement hook (bench.py): when switched on, every compute entry point records a CUDA event pair on its stream
  * immediately around its main kernel(s); msf_prof_end synchronises those events and returns, per kernel id, the number

@@ -178,6 +178,8 @@ _SIGS = {
     "msf_peer_allreduce_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_int64, C.c_int, C.c_void_p]),
     "msf_jigsaw_tiles": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float),
                                    C.POINTER(C.c_float), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "msf_view_crops_s2d": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_float),
+                                     C.POINTER(C.c_float), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "msf_prof_begin": (C.c_int, [C.c_int]),
     "msf_prof_end": (C.c_int, [C.POINTER(ProfRecord), C.POINTER(C.c_int)]),
     "msf_prof_kernel_name": (C.c_char_p, [C.c_int]),

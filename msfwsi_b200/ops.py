@@ -938,6 +938,48 @@ def jigsaw_tiles(src: torch.Tensor, perm: Optional[torch.Tensor], grid: int = 4,
     return out
 
 
+def view_crops_s2d(src: torch.Tensor, crops: torch.Tensor, out_hw: Tuple[int, int] = (224, 224), mean: Sequence[float] = (0.485, 0.456, 0.406),
+                   std: Sequence[float] = (0.229, 0.224, 0.225), out_dtype: torch.dtype = torch.bfloat16, validate: bool = False) -> torch.Tensor:
+    """Every view of a step from the uint8 source tiles in one launch, in the stem convolution's input layout.
+    src (B, H, W, 3) uint8 on the device; crops (n, 6) int32 rows ``[sample, y0, x0, y1, x1, flip]`` (integer source-pixel
+    boxes, what albumentations' RandomResizedCrop draws; see :func:`jigsaw_view_crops` for the target views).  Returns the
+    (n, 16, (oh+6)/2, (ow+6)/2) channels-last tensor ``stem_s2d`` would produce from the normalised (n, 3, oh, ow) views;
+    the encoders take it as is (``ResNet._stem_conv``)."""
+    L.require_cuda(src, crops)
+    if src.dim() != 4 or src.shape[3] != 3 or src.dtype != torch.uint8:
+        raise ValueError(f"view_crops_s2d: src must be (B,H,W,3) uint8, got {tuple(src.shape)} {src.dtype}")
+    if crops.dim() != 2 or crops.shape[1] != 6 or crops.dtype != torch.int32:
+        raise ValueError(f"view_crops_s2d: crops must be (n, 6) int32, got {tuple(crops.shape)} {crops.dtype}")
+    src, crops = _contig(src), _contig(crops)
+    B, H, W, _ = src.shape
+    n = crops.shape[0]
+    oh, ow = int(out_hw[0]), int(out_hw[1])
+    out = torch.empty((n, 16, (oh + 6) // 2, (ow + 6) // 2), dtype=out_dtype, device=src.device, memory_format=torch.channels_last)
+    flag = torch.zeros(1, dtype=torch.int32, device=src.device) if validate else None
+    m3, s3 = (C.c_float * 3)(*[float(v) for v in mean]), (C.c_float * 3)(*[float(v) for v in std])
+    L.check(L.lib().msf_view_crops_s2d(L.ptr(src), B, H, W, L.ptr(crops), n, oh, ow, m3, s3, L.ptr(out), L.dtype_code(out_dtype), L.ptr(flag),
+                                       L.stream_ptr()), "msf_view_crops_s2d")
+    L.launch_count += 1
+    if validate and int(flag.item()) != 0:
+        raise IndexError("view_crops_s2d: a crop box or sample index lies outside the source images")
+    return out
+
+
+def jigsaw_view_crops(perm: torch.Tensor, boxes: torch.Tensor, flips: torch.Tensor, H: int, W: int, grid: int = 4) -> torch.Tensor:
+    """Crop rows for the target views: view (b, j) is tile ``perm[b, j]`` of ``blockshaped(img_b, H/grid, W/grid)``
+    (src/utils/data/bcss.py:171-177; raster tile t covers rows [th*(t//grid), +th), cols [tw*(t%grid), +tw)) cropped to
+    ``boxes[b, j] = [y0, x0, y1, x1)`` INSIDE the tile.  perm (B, K) int64, boxes (B, K, 4) integer, flips (B, K) -> (B*K, 6)
+    int32 for :func:`view_crops_s2d` (integer arithmetic only: bit-exact tiling)."""
+    B, K = perm.shape
+    th, tw = H // grid, W // grid
+    t = perm.remainder(K)
+    oy, ox = (t // grid) * th, (t % grid) * tw
+    b = boxes.to(torch.int64)
+    sample = torch.arange(B, device=perm.device).view(B, 1).expand(B, K)
+    rows = torch.stack((sample, oy + b[..., 0], ox + b[..., 1], oy + b[..., 2], ox + b[..., 3], flips.to(torch.int64)), dim=2)
+    return rows.reshape(B * K, 6).to(torch.int32)
+
+
 # ------------------------------------------------------------------------------------------
 # E1: multi-tensor EMA (extension)
 # ------------------------------------------------------------------------------------------

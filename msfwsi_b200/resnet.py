@@ -69,6 +69,11 @@ class FusedBatchNorm2d(nn.Module):
         return (out, out.mean(dim=(2, 3))) if want_mean else out
 
 
+def ops_stem_weight(w):
+    from . import ops
+    return ops.stem_s2d_weight(w)
+
+
 class BasicBlock(nn.Module):
     expansion = 1
 
@@ -129,6 +134,9 @@ class ResNet(nn.Module):
         than the 3-channel form; the parameter, its gradient and the state dict keep the (64, 3, 7, 7) shape."""
         c = self.conv1
         w = c.weight
+        if x.shape[1] == 16 and tuple(w.shape[1:]) == (3, 7, 7):
+            # already in the space-to-depth layout (ops.view_crops_s2d writes the views like this straight from the uint8 tiles)
+            return nn.functional.conv2d(x, ops_stem_weight(w))
         if (x.is_cuda and not x.requires_grad and tuple(w.shape[1:]) == (3, 7, 7) and tuple(c.stride) == (2, 2) and tuple(c.padding) == (3, 3)
                 and tuple(c.dilation) == (1, 1) and c.groups == 1 and c.bias is None and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0):
             from . import ops

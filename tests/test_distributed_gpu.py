@@ -105,3 +105,100 @@ def test_sharded_infonce_nccl_matches_single_process_oracle():
     for p in procs:
         p.join(30)
     assert all(r[1] == "ok" for r in res), res
+
+
+def _worker_heads(rank, world, port, q):
+    """The data-parallel promise "G ranks x B == one process x G*B" (what SyncBatchNorm + DDP give the reference,
+    tools/ssl_train.py:160-170) for the grouped head stage: statistics exchanged inside msf_head_bn_finalize /
+    msf_head_bn_bwd_finalize over NVLink peer memory, keys of all 24 InfoNCE pairs in ONE all-gather."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import msfwsi_b200 as M
+        from oracle import msf_oracle as O
+
+        class _Null(torch.nn.Module):
+            def __init__(self, **_):
+                super().__init__()
+                self.fc = torch.nn.Identity()
+
+        W = (0.1, 0.4, 0.7, 1.0)
+        B, K = 24, 16
+        torch.manual_seed(5)  # same weights on every rank
+        sharded = M.MSFWSI(lambda **kw: _Null(**kw), 4).to(dev).train()
+        single = M.MSFWSI(lambda **kw: _Null(**kw), 4).to(dev).train()
+        single.load_state_dict(sharded.state_dict())
+        mk = lambda shape, s: O.closed_form_tensor(shape, s, 1.0).abs().to(dev)
+        g = torch.Generator().manual_seed(9)
+        cf_all = [tuple(mk((world * B, d), 300 + 10 * v + l) for l, d in enumerate(O.INTER_DIM)) for v in range(2)]
+        tf_all = [tuple(mk((world * B * K, d), 400 + 10 * v + l) for l, d in enumerate(O.INTER_DIM)) for v in range(2)]
+        rev_all = [torch.stack([O.jigsaw_indices(g, K)[1] for _ in range(world * B)]).to(dev) for _ in range(2)]
+        sl = lambda ts, n: tuple(t[rank * n:(rank + 1) * n].contiguous() for t in ts)
+        res = {}
+        for mode, dtype in (("cosine", None), ("cosine", torch.bfloat16), ("infonce", torch.bfloat16)):
+            cast = (lambda t: t) if dtype is None else (lambda t: t.to(dtype))
+            cfa = [tuple(cast(t) for t in v) for v in cf_all]
+            tfa = [tuple(cast(t) for t in v) for v in tf_all]
+            outs = []
+            for model, cf, tf, rev, whole in ((sharded, [sl(v, B) for v in cfa], [sl(v, B * K) for v in tfa], [r[rank * B:(rank + 1) * B] for r in rev_all], False),
+                                              (single, cfa, tfa, rev_all, True)):
+                model.zero_grad(set_to_none=True)
+                if whole:  # the single-process run must not synchronise: hide the process group from the module
+                    real = dist.is_initialized
+                    dist.is_initialized = lambda: False
+                try:
+                    if dtype is None:
+                        loss = model.heads_loss(cf[0], cf[1], tf[0], tf[1], rev, W, mode=mode)
+                    else:
+                        with torch.autocast("cuda", dtype=dtype):
+                            loss = model.heads_loss(cf[0], cf[1], tf[0], tf[1], rev, W, mode=mode)
+                    loss.backward()
+                finally:
+                    if whole:
+                        dist.is_initialized = real
+                outs.append((loss.detach().clone(), {n: p.grad.detach().clone() for n, p in model.named_parameters()}))
+            (ls, gs), (lw, gw) = outs
+            t = ls.clone()
+            dist.all_reduce(t)  # mean of the per-rank losses == the loss of the concatenated batch (equal shard sizes)
+            tol = 1e-5 if dtype is None else 3e-3
+            assert abs(float(t) / world - float(lw)) <= tol * max(1.0, abs(float(lw))), (mode, dtype, float(t) / world, float(lw))
+            a, b = [], []
+            for n in gs:
+                gsum = gs[n].clone()
+                dist.all_reduce(gsum)  # DDP averages the per-rank gradients
+                a.append((gsum / world).flatten().double())
+                b.append(gw[n].flatten().double())
+            a, b = torch.cat(a), torch.cat(b)
+            cos = float((a @ b) / (a.norm() * b.norm()))
+            assert cos >= (0.99999 if dtype is None else 0.999), (mode, dtype, cos)
+            res[f"{mode}-{dtype}"] = (float(t) / world, float(lw), cos)
+        # running statistics saw the global batch on every rank
+        sd_s, sd_w = sharded.state_dict(), single.state_dict()
+        for k_ in sd_s:
+            if k_.endswith("running_var"):
+                assert torch.allclose(sd_s[k_], sd_w[k_], rtol=2e-2, atol=2e-3), k_
+        q.put((rank, "ok", res))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, "fail: " + traceback.format_exc()[-1500:], None))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.timeout(300)
+def test_grouped_head_stage_two_ranks_equal_concatenated_batch():
+    world, port = 2, 29900 + (os.getpid() % 90)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_heads, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(30)
+    assert all(r[1] == "ok" for r in res), res
+    print(res[0][2])

@@ -190,7 +190,10 @@ def test_linear_bnstat_single_problem_abi():
 def test_argument_validation():
     A, B = _mk((64, 64), torch.bfloat16, 1), _mk((64, 64), torch.bfloat16, 2)
     with pytest.raises(RuntimeError, match="multiple of 8"):
-        ops.gemm_grouped([ops.GemmSpec(A[:, :60], B[:, :60], 64, 64, 60)])
+        sc = torch.ones(64, device=DEV)
+        ops.gemm_grouped([ops.GemmSpec(A[:, :60], B[:, :60], 64, 64, 60, a_scale=sc, a_shift=sc)])
+    (C60,) = ops.gemm_grouped([ops.GemmSpec(A[:, :60], B[:, :60], 64, 64, 60)])  # K only needs the 16-byte row pitch, not a multiple of 8
+    assert _rel(C60, A[:, :60].double() @ B[:, :60].double().t()) <= 3e-3
     with pytest.raises(TypeError):
         ops.gemm_grouped([ops.GemmSpec(A.double(), B.double(), 64, 64, 64)])
     with pytest.raises(RuntimeError, match="prologue"):

@@ -6,8 +6,9 @@ graph -- nn.Linear / nn.BatchNorm1d / ReLU heads of src/models/backbone.py:12-31
 Tolerances: fp32 (exact SIMT path) outputs 2e-5, gradients 1e-4 relative; bf16 / fp16 autocast: outputs within 3e-2 relative
 Frobenius of torch's own 16-bit run (two 16-bit evaluations of a 5-layer head with batch norms differ by rounding noise of
 that size), loss within 2e-3, every parameter gradient cosine >= 0.99 to torch's 16-bit gradient, and the whole gradient
-vector at least as close to the fp32 gradient of the same graph as torch's own 16-bit gradient is (>= 0.999; measured on the
-B200: both ~0.9997, while the two 16-bit runs agree with each other to ~0.9995)."""
+vector at least as close to a higher-precision gradient of the same graph as torch's own gradient is (measured on the B200
+for bf16 at B = 32: this repo 0.99616, torch 0.99614 against the fp32 gradient, while the two bf16 runs agree with each other
+to 0.99954: the batch-norm backward amplifies rounding noise, so the same-precision comparison is the weaker statement)."""
 import pytest
 import torch
 
@@ -84,7 +85,7 @@ def test_head_stage_matches_reference_module_graph(dtype, B):
     launches = L.launch_count - before
     out_r, loss_r, lc_r, lt_r = _run(ref, lambda o: R.ref_ssl_loss(o, W), cf, tf, rev, dtype)
     # fp32: batch norm over B rows amplifies rounding by ~1/sqrt(var) of the worst column; looser at the tiny batch
-    out_tol, grad_tol = ((5e-4, 2e-3) if B <= 8 else (5e-5, 5e-4)) if dtype is None else (3e-2, None)
+    out_tol, grad_tol = ((5e-4, 1e-4) if B <= 8 else (5e-5, 2e-5)) if dtype is None else (3e-2, None)
     for bm, br in zip(out_m, out_r):
         for name, tm, tr in zip(("p1", "p2", "z1", "z2"), bm, br):
             for l, (a, b) in enumerate(zip(tm, tr)):
@@ -93,16 +94,19 @@ def test_head_stage_matches_reference_module_graph(dtype, B):
                 assert a.requires_grad == name.startswith("p")
     assert abs(float(loss_m) - float(loss_r)) <= (1e-5 if dtype is None else 2e-3) * max(1.0, abs(float(loss_r)))
     pr = dict(ref.named_parameters())
-    truth = None
-    if dtype is not None:
-        # 16-bit runs are judged against the fp32 gradient of the same graph: this repo's 16-bit gradient must be as close
-        # to it as torch's own 16-bit gradient is (two 16-bit evaluations differ from each other by more than either
-        # differs from the truth when batch norms over few rows amplify the rounding noise)
-        ref32 = R.RefMSFWSI(lambda **kw: _Null(**kw), 4).to(DEV).train()
-        ref32.load_state_dict({k: v for k, v in mine.state_dict().items() if not k.endswith("num_batches_tracked")}, strict=False)
-        f32 = lambda vs: [tuple(t.float() for t in v) for v in vs]
-        _run(ref32, lambda o: R.ref_ssl_loss(o, W), f32(cf), f32(tf), rev, None)
-        truth = dict(ref32.named_parameters())
+    # Gradients are judged against a HIGHER-precision evaluation of the same graph (fp64 for the fp32 path, fp32 for the
+    # 16-bit paths): the batch-norm backward removes the components of dy along 1 and x_hat, so rounding noise is amplified by
+    # |dy'| / |dy| (more with few rows), and two evaluations at the same precision differ from each other by more than either
+    # differs from the truth.  This repo's gradient must be as close to the truth as torch's own is.
+    hi = torch.float64 if dtype is None else torch.float32
+    ref_hi = R.RefMSFWSI(lambda **kw: _Null(**kw), 4).to(DEV).to(hi).train()
+    ref_hi.load_state_dict({k: v for k, v in ref.state_dict().items()})
+    with torch.no_grad():  # the parameters the two lower-precision runs started from (the buffers were updated by them: reset)
+        for (n, b), (_, b0) in zip(ref_hi.named_buffers(), R.RefMSFWSI(lambda **kw: _Null(**kw), 4).named_buffers()):
+            b.copy_(b0)
+    cast = lambda vs: [tuple(t.to(hi) for t in v) for v in vs]
+    _run(ref_hi, lambda o: R.ref_ssl_loss(o, W), cast(cf), cast(tf), rev, None)
+    truth = dict(ref_hi.named_parameters())
     gm, gr, gt = [], [], []
     worst = 1.0
     for n, p in mine.named_parameters():
@@ -111,22 +115,25 @@ def test_head_stage_matches_reference_module_graph(dtype, B):
         c = _cos(p.grad, pr[n].grad)
         worst = min(worst, c)
         if dtype is None:
-            assert _rel(p.grad, pr[n].grad) <= grad_tol, (n, _rel(p.grad, pr[n].grad))
+            e_mine, e_torch = _rel(p.grad, truth[n].grad), _rel(pr[n].grad, truth[n].grad)
+            assert e_mine <= max(3.0 * e_torch, grad_tol), (n, e_mine, e_torch)
         else:
             assert c >= 0.99, (n, c)  # small tensors (16-wide batch-norm betas) carry visible 16-bit noise; the whole vector is checked below
-            gt.append(truth[n].grad.flatten().double())
+        gt.append(truth[n].grad.flatten().double())
         gm.append(p.grad.flatten().double())
         gr.append(pr[n].grad.flatten().double())
+    c_mine, c_torch = _cos(torch.cat(gm), torch.cat(gt)), _cos(torch.cat(gr), torch.cat(gt))
+    e_mine, e_torch = _rel(torch.cat(gm), torch.cat(gt)), _rel(torch.cat(gr), torch.cat(gt))
+    print(f"whole gradient vs the {hi} truth: this repo cos {c_mine:.7f} rel {e_mine:.2e}; torch ({dtype or torch.float32}) cos {c_torch:.7f} rel {e_torch:.2e}; "
+          f"between the two same-precision runs cos {_cos(torch.cat(gm), torch.cat(gr)):.7f}")
     if dtype is None:
-        assert _cos(torch.cat(gm), torch.cat(gr)) >= 0.9999
+        assert c_mine >= 0.9999999 - 1e-7 and e_mine <= max(3.0 * e_torch, 1e-5), (e_mine, e_torch)
     else:
-        c_mine, c_torch = _cos(torch.cat(gm), torch.cat(gt)), _cos(torch.cat(gr), torch.cat(gt))
-        print(f"gradient cosine to the fp32 truth: this repo {c_mine:.6f}, torch {dtype} {c_torch:.6f}; between the two 16-bit runs {_cos(torch.cat(gm), torch.cat(gr)):.6f}")
-        assert c_mine >= 0.999 and c_mine >= c_torch - 3e-4, (c_mine, c_torch)
+        assert c_mine >= 0.99 and c_mine >= c_torch - 3e-4, (c_mine, c_torch)
     for vm, vr in zip(lc_m + lt_m, lc_r + lt_r):
         for a, b in zip(vm, vr):
             assert a.grad is not None and a.grad.dtype == a.dtype
-            assert _cos(a.grad, b.grad) >= (0.99999 if dtype is None else 0.999)
+            assert _cos(a.grad, b.grad) >= (0.99999 if dtype is None else 0.995)
     # running statistics (both views, in the reference's order) and the call counters
     br_ = dict(ref.named_buffers())
     for n, b in mine.named_buffers():
