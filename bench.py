@@ -57,6 +57,9 @@ def parse():
     ap.add_argument("--no-microbench", action="store_true")
     ap.add_argument("--no-hbm-rows", action="store_true")
     ap.add_argument("--no-second-loss", action="store_true")
+    ap.add_argument("--e2e-source", default="uint8", choices=["uint8", "bf16"],
+                    help="what the end-to-end step copies from the host: uint8 = the 1024^2 source tiles + crop boxes / flips / jigsaw "
+                         "permutations, views built on the device (msf_view_crops_s2d); bf16 = the 34 normalised views per tile")
     return ap.parse_args()
 
 
@@ -252,6 +255,36 @@ def ours(args):
         return sum(nbytes(t) for t in v) if isinstance(v, (list, tuple)) else v.numel() * v.element_size()
 
     h2d_bytes = sum(nbytes(v) for v in host.values())
+    MEAN, STD = (0.6998, 0.4785, 0.6609), (0.2203, 0.2407, 0.1983)  # scripts/bcss.sh:13-14
+    host_u8 = None
+    if not args.heads_only and args.e2e_source == "uint8":
+        # What a dataloader hands over once the augmentations' random numbers are drawn (tools/ssl_train.py:175-217,
+        # src/utils/data/bcss.py:164-182): the uint8 L0 tile, per view a RandomResizedCrop(scale=(0.5, 1)) box + flip bit, per
+        # target view the jigsaw permutation.  Everything else (tiling, shuffle, crop, resize, flip, normalise, layout) runs
+        # on the device in one launch.
+        S, T = 1024, 256
+
+        def rrc(n, side):  # albumentations / torchvision RandomResizedCrop box sampling, integer boxes
+            area = side * side * (0.5 + 0.5 * torch.rand(n, generator=g))
+            ratio = torch.exp(torch.empty(n).uniform_(-0.2876820724517809, 0.2876820724517809, generator=g))  # log(3/4) .. log(4/3)
+            w = torch.sqrt(area * ratio).round().clamp(8, side).long()
+            h = torch.sqrt(area / ratio).round().clamp(8, side).long()
+            y0 = (torch.rand(n, generator=g) * (side - h + 1).float()).long().clamp(max=side - 1)
+            x0 = (torch.rand(n, generator=g) * (side - w + 1).float()).long().clamp(max=side - 1)
+            return torch.stack((y0, x0, torch.minimum(y0 + h, torch.tensor(side)), torch.minimum(x0 + w, torch.tensor(side))), dim=1)
+
+        perms = [torch.stack([torch.randperm(K, generator=g) for _ in range(B)]) for _ in range(2)]
+        crop_rows = []
+        for v in range(2):  # context views: crop of the whole tile
+            bx = rrc(B, S)
+            crop_rows.append(torch.cat((torch.arange(B).view(B, 1), bx, torch.randint(0, 2, (B, 1), generator=g)), dim=1))
+        for v in range(2):  # target views: tile perm[b, j] of blockshaped(img, 256, 256), cropped inside the tile
+            bx = rrc(B * K, T).view(B, K, 4)
+            crop_rows.append(ops.jigsaw_view_crops(perms[v], bx, torch.randint(0, 2, (B, K), generator=g), S, S, 4).long())
+        host_u8 = {"src": torch.randint(0, 256, (B, S, S, 3), dtype=torch.uint8, generator=g).pin_memory(),
+                   "crops": torch.cat(crop_rows).to(torch.int32).pin_memory(),
+                   "r1": perms[0].argsort(dim=1).pin_memory(), "r2": perms[1].argsort(dim=1).pin_memory()}  # rev = argsort(perm), bcss.py:172
+        h2d_bytes = sum(nbytes(v) for v in host_u8.values())
 
     def to_dev():
         mv = lambda v: [t.to(dev, non_blocking=True) for t in v] if isinstance(v, list) else v.to(dev, non_blocking=True)
@@ -318,7 +351,7 @@ def ours(args):
 
     def fetch():
         with torch.cuda.stream(copy_stream):
-            d = to_dev()
+            d = to_dev() if host_u8 is None else {k: v.to(dev, non_blocking=True) for k, v in host_u8.items()}
             ev = torch.cuda.Event()
             ev.record(copy_stream)
         for v in d.values():
@@ -326,13 +359,20 @@ def ours(args):
                 t.record_stream(main_stream)
         return d, ev
 
+    def build_views(d):
+        """uint8 tiles + crop rows -> the 34 views per tile in the stem's input layout, one launch (D1b)."""
+        if host_u8 is None:
+            return d
+        views = ops.view_crops_s2d(d["src"], d["crops"], (img, img), MEAN, STD, torch.bfloat16)
+        return {"c1": views[:B], "c2": views[B:2 * B], "t1": views[2 * B:2 * B + B * K], "t2": views[2 * B + B * K:], "r1": d["r1"], "r2": d["r2"]}
+
     def e2e_steps(n):
         nxt = fetch()
         for i in range(n):
             d, ev = nxt
             main_stream.wait_event(ev)
             nxt = fetch() if i + 1 < n else None
-            step(d).item()  # device -> host read of the step's result
+            step(build_views(d)).item()  # device -> host read of the step's result
 
     e2e_steps(2)
     barrier()
@@ -400,7 +440,9 @@ def ours(args):
                            "encoder": "none (heads only)" if args.heads_only else "resnet18 random-init (PyTorch/cuDNN, channels_last)",
                            "optimizer": "Adam, 3 lr groups (msf_adam_multi, bf16 GEMM operands rewritten in the same pass)",
                            "l2_policy": "per-step inputs (2.6 GB bf16) and activations exceed the 126 MB L2; microbenchmarks flush L2 between iterations",
-                           "host_inputs": "bf16 NHWC pinned (what the first convolution consumes under bf16 autocast)"},
+                           "host_inputs": ("e2e: uint8 1024^2 source tiles + crop boxes / flips / jigsaw permutations, pinned; the 34 views per tile are built on "
+                                           "the device in one launch (msf_view_crops_s2d)" if host_u8 is not None else
+                                           "bf16 NHWC pinned (what the first convolution consumes under bf16 autocast)")},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline, "loss": last_loss,
                 "encoder_images_per_sec": None if args.heads_only else value * 34}

@@ -291,7 +291,8 @@ typedef struct {
   int32_t rows;              /* rows per view on this rank */
   int32_t C;
   int32_t n_views;           /* 1 or 2 */
-  int32_t centered;          /* 1: entry 1 of each col_stats group is M2 about the group mean (msf_head_bn_stats), 0: sum of squares */
+  int32_t centered;          /* 1 (exact fp32 path): entry 1 of each col_stats group is M2 about the group mean (msf_head_bn_stats) and
+                              * shift receives beta (consumers evaluate (x - mean) * scale + shift); 0: sums of squares, shift = beta - mean * scale */
 } msf_head_bn_item;
 size_t msf_head_sync_workspace_bytes(int64_t capacity_doubles);
 int msf_head_bn_finalize(const msf_head_bn_item* items /*host*/, int n_items, float eps, float momentum, int training,
@@ -314,6 +315,7 @@ typedef struct {
   float* inv_norm;      /* (rows) or NULL */
   const float* scale;   /* [C] */
   const float* shift;   /* [C] */
+  const float* mean;    /* NULL, or [C]: centered form y = (x - mean) * scale + shift (shift = beta; finalize items with centered = 1) */
   int32_t rows, C, relu, reserved;
 } msf_head_apply_item;
 int msf_head_bn_apply(const msf_head_apply_item* items /*host*/, int n, int dtype, float norm_eps, void* stream);
@@ -335,7 +337,8 @@ typedef struct {
   const float* invstd;
   const float* c1;      /* [C] (elemt in) */
   const float* c2;
-  int32_t rows, C, relu, reserved;
+  int32_t rows, C, relu;
+  int32_t centered;     /* 1: the forward evaluated (y - mean) * scale + shift (shift = beta): the ReLU mask is rebuilt the same way */
 } msf_head_bwd_item;
 typedef struct {
   const float* partial[2];

@@ -72,13 +72,13 @@ class HeadMat(C.Structure):
 
 class HeadApplyItem(C.Structure):
     _fields_ = [("x", C.c_void_p), ("y", C.c_void_p), ("y_hat", C.c_void_p), ("inv_norm", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
-                ("rows", C.c_int32), ("C", C.c_int32), ("relu", C.c_int32), ("reserved", C.c_int32)]
+                ("mean", C.c_void_p), ("rows", C.c_int32), ("C", C.c_int32), ("relu", C.c_int32), ("reserved", C.c_int32)]
 
 
 class HeadBwdItem(C.Structure):
     _fields_ = [("g", C.c_void_p), ("y", C.c_void_p), ("dy", C.c_void_p), ("partial", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
                 ("mean", C.c_void_p), ("invstd", C.c_void_p), ("c1", C.c_void_p), ("c2", C.c_void_p),
-                ("rows", C.c_int32), ("C", C.c_int32), ("relu", C.c_int32), ("reserved", C.c_int32)]
+                ("rows", C.c_int32), ("C", C.c_int32), ("relu", C.c_int32), ("centered", C.c_int32)]
 
 
 class HeadBwdFinItem(C.Structure):

@@ -169,7 +169,9 @@ __global__ void __launch_bounds__(kThreads) head_bn_finalize_kernel(const __grid
     const float invstd = rsqrtf(var + eps);
     const float sc = gam * invstd;
     q.scale[view][c] = sc;
-    q.shift[view][c] = fmaf(-mean, sc, bet);
+    // centered (exact fp32 path): consumers evaluate (x - mean) * scale + beta, torch's own association -- near a ReLU zero
+    // crossing x * scale and mean * scale are large and nearly cancel, so the folded shift would cost a digit there
+    q.shift[view][c] = q.centered ? bet : fmaf(-mean, sc, bet);
     if (q.mean[view]) q.mean[view][c] = mean;
     if (q.invstd[view]) q.invstd[view][c] = invstd;
   }
@@ -248,8 +250,9 @@ __global__ void __launch_bounds__(kThreads) head_bn_apply_kernel(const __grid_co
       Elem<DT>::unpack(ldg_keep(src + static_cast<size_t>(c) * 16), f);
 #pragma unroll
       for (int e = 0; e < V; ++e) {
-        float t = round_to<DT>(fmaf(f[e], __ldg(q.scale + c * V + e), __ldg(q.shift + c * V + e)));  // the 16-bit BN output ...
-        if (q.relu) t = fmaxf(t, 0.f);                                                                 // ... then the ReLU on it
+        const float xc = q.mean ? f[e] - __ldg(q.mean + c * V + e) : f[e];
+        float t = round_to<DT>(fmaf(xc, __ldg(q.scale + c * V + e), __ldg(q.shift + c * V + e)));  // the 16-bit BN output ...
+        if (q.relu) t = fmaxf(t, 0.f);                                                               // ... then the ReLU on it
         f[e] = t;
         ss = fmaf(t, t, ss);
       }
@@ -267,7 +270,8 @@ __global__ void __launch_bounds__(kThreads) head_bn_apply_kernel(const __grid_co
     Elem<DT>::unpack(ldg_keep(src + static_cast<size_t>(c) * 16), f);
 #pragma unroll
     for (int e = 0; e < V; ++e) {
-      float t = round_to<DT>(fmaf(f[e], __ldg(q.scale + c * V + e), __ldg(q.shift + c * V + e)));
+      const float xc = q.mean ? f[e] - __ldg(q.mean + c * V + e) : f[e];
+      float t = round_to<DT>(fmaf(xc, __ldg(q.scale + c * V + e), __ldg(q.shift + c * V + e)));
       if (q.relu) t = fmaxf(t, 0.f);
       f[e] = t * inv;
     }
@@ -318,7 +322,7 @@ __global__ void __launch_bounds__(kThreads) head_bn_bwd_reduce_kernel(const __gr
       for (int e = 0; e < V; ++e) {
         float d = g[e];
         if (q.y) {
-          if (q.relu && !(round_to<DT>(fmaf(y[e], sc[e], sh[e])) > 0.f)) d = 0.f;  // the mask of the forward's ReLU
+          if (q.relu && !(round_to<DT>(fmaf(q.centered ? y[e] - mu[e] : y[e], sc[e], sh[e])) > 0.f)) d = 0.f;  // the mask of the forward's ReLU
           s2[e] = fmaf(d, (y[e] - mu[e]) * is[e], s2[e]);
         }
         s1[e] += d;
@@ -401,7 +405,7 @@ __global__ void __launch_bounds__(kThreads) head_bn_bwd_elemt_kernel(const __gri
       const int col = c * V + e;
       const float sc = __ldg(q.scale + col), sh = __ldg(q.shift + col), mu = __ldg(q.mean + col), is = __ldg(q.invstd + col);
       float d = g[e];
-      if (q.relu && !(round_to<DT>(fmaf(y[e], sc, sh)) > 0.f)) d = 0.f;
+      if (q.relu && !(round_to<DT>(fmaf(q.centered ? y[e] - mu : y[e], sc, sh)) > 0.f)) d = 0.f;
       o[e] = sc * (d - __ldg(q.c1 + col) - (y[e] - mu) * is * __ldg(q.c2 + col));
     }
     stg_stream(static_cast<char*>(q.dy) + ch * 16, Elem<DT>::pack(o));

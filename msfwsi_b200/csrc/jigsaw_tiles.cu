@@ -164,7 +164,9 @@ __global__ void __launch_bounds__(256) view_crops_s2d_kernel(const unsigned char
     c.y1 = min(max(c.y1, c.y0 + 1), g.H); c.x1 = min(max(c.x1, c.x0 + 1), g.W);
   }
   const int ch = c.y1 - c.y0, cw = c.x1 - c.x0;
-  const float sy = static_cast<float>(ch) / g.oh, sx = static_cast<float>(cw) / g.ow;
+  // source coordinates in double: in fp32 the scale's rounding error times the output index reaches 2e-5 pixels, which a
+  // 255-level step between neighbouring pixels turns into 1e-4 of a normalised value (one DFMA per coordinate is noise here)
+  const double sy = static_cast<double>(ch) / g.oh, sx = static_cast<double>(cw) / g.ow;
   const unsigned char* base = src + ((static_cast<int64_t>(c.sample) * g.H + c.y0) * g.W + c.x0) * 3;
   const unsigned char* end = src + src_bytes;
   const int64_t pitch = static_cast<int64_t>(g.W) * 3;
@@ -183,10 +185,10 @@ __global__ void __launch_bounds__(256) view_crops_s2d_kernel(const unsigned char
       }
       if (c.flip) x = g.ow - 1 - x;
       // F.interpolate(align_corners=False) on the crop: source = (o + 0.5) * scale - 0.5, taps clamped at the crop border
-      const float fy = fmaxf(fmaf(y + 0.5f, sy, -0.5f), 0.f), fx = fmaxf(fmaf(x + 0.5f, sx, -0.5f), 0.f);
+      const double fy = fmax(fma(y + 0.5, sy, -0.5), 0.0), fx = fmax(fma(x + 0.5, sx, -0.5), 0.0);
       const int y0 = min(static_cast<int>(fy), ch - 1), x0 = min(static_cast<int>(fx), cw - 1);
       const int y1 = min(y0 + 1, ch - 1);
-      const float wy = y0 < ch - 1 ? fy - y0 : 0.f, wx = x0 < cw - 1 ? fx - x0 : 0.f;
+      const float wy = y0 < ch - 1 ? static_cast<float>(fy - y0) : 0.f, wx = x0 < cw - 1 ? static_cast<float>(fx - x0) : 0.f;
       const bool has_x1 = x0 < cw - 1;
       const uint64_t t0 = window8(base + y0 * pitch + x0 * 3, end), t1 = window8(base + y1 * pitch + x0 * 3, end);
 #pragma unroll

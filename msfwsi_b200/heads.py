@@ -278,14 +278,14 @@ class _HeadStage(torch.autograd.Function):
             if fused:
                 src = [y[h][k] for h in range(nh)]  # the next GEMM normalises on the fly
             elif k < 2:
-                apply([L.HeadApplyItem(L.ptr(y[h][k][v]), L.ptr(a_keep[h][k][v]), 0, 0, L.ptr(sc[h][k][v]), L.ptr(sh[h][k][v]), R[h], heads[h].d, 1, 0)
+                apply([L.HeadApplyItem(L.ptr(y[h][k][v]), L.ptr(a_keep[h][k][v]), 0, 0, L.ptr(sc[h][k][v]), L.ptr(sh[h][k][v]), L.ptr(mu[h][k][v]), R[h], heads[h].d, 1, 0)
                        for h in range(nh) for v in range(2)])
                 src = [a_keep[h][k] for h in range(nh)]
         # ---- z = BN3(y3) (no ReLU); with it the L2-normalised keys of the InfoNCE objective ----
         if want_hat:
             kinv = [torch.empty((2, R[h]), dtype=torch.float32, device=dev) for h in range(nh)]
         apply([L.HeadApplyItem(L.ptr(y[h][2][v]), L.ptr(z[h][v]), L.ptr(khat[h][v]) if want_hat else 0, L.ptr(kinv[h][v]) if want_hat else 0,
-                               L.ptr(sc[h][2][v]), L.ptr(sh[h][2][v]), R[h], heads[h].d, 0, 0) for h in range(nh) for v in range(2)])
+                               L.ptr(sc[h][2][v]), L.ptr(sh[h][2][v]), 0 if fused else L.ptr(mu[h][2][v]), R[h], heads[h].d, 0, 0) for h in range(nh) for v in range(2)])
         if want_hat and training and _world(group) > 1:
             # ONE exchange for the keys of all 24 pairs, on a side stream: it overlaps the two predictor depths below, and
             # the loss kernels (which need the predictor outputs anyway) wait for it
@@ -313,7 +313,7 @@ class _HeadStage(torch.autograd.Function):
             stats_of(3)
         finalize(3)
         if not fused:
-            apply([L.HeadApplyItem(L.ptr(y[h][3][v]), L.ptr(a_keep[h][3][v]), 0, 0, L.ptr(sc[h][3][v]), L.ptr(sh[h][3][v]), R[h], heads[h].dq, 1, 0)
+            apply([L.HeadApplyItem(L.ptr(y[h][3][v]), L.ptr(a_keep[h][3][v]), 0, 0, L.ptr(sc[h][3][v]), L.ptr(sh[h][3][v]), L.ptr(mu[h][3][v]), R[h], heads[h].dq, 1, 0)
                    for h in range(nh) for v in range(2)])
         specs = []
         for h in range(nh):
@@ -396,7 +396,7 @@ class _HeadStage(torch.autograd.Function):
                 yield items[lo:lo + cap]
 
         if fused:  # rebuild the ReLU activations the dW GEMMs read (one launch for all heads, layers and views)
-            items = [L.HeadApplyItem(L.ptr(y[h][k][v]), L.ptr(a[h][k][v]), 0, 0, L.ptr(sc[h][k][v]), L.ptr(sh[h][k][v]), R[h], widths[h][k], 1, 0)
+            items = [L.HeadApplyItem(L.ptr(y[h][k][v]), L.ptr(a[h][k][v]), 0, 0, L.ptr(sc[h][k][v]), L.ptr(sh[h][k][v]), 0, R[h], widths[h][k], 1, 0)
                      for h in range(nh) for k in (0, 1, 3) for v in range(2)]
             for ch in chunks(items, L.MSF_HEAD_MAX_MATS):
                 L.check(lib.msf_head_bn_apply(_arr(L.HeadApplyItem, ch), len(ch), code, ops.COS_EPS, st), "msf_head_bn_apply")
@@ -405,8 +405,9 @@ class _HeadStage(torch.autograd.Function):
         def bn_backward(k, g_in, dy_out, with_bias_sums=False):
             """g_in[h] (2,R,C): gradient w.r.t. relu?(bn_k(y_k)); writes dy_out[h] = gradient w.r.t. y_k."""
             relu = 0 if k == 2 else 1
+            cen = 0 if fused else 1  # the exact path evaluated (y - mean) * scale + beta in the forward: rebuild the mask the same way
             items = [L.HeadBwdItem(L.ptr(g_in[h][v]), L.ptr(y[h][k][v]), 0, L.ptr(part[h][k][v]), L.ptr(sc[h][k][v]), L.ptr(sh[h][k][v]),
-                                   L.ptr(mu[h][k][v]), L.ptr(istd[h][k][v]), 0, 0, R[h], widths[h][k], relu, 0) for h in range(nh) for v in range(2)]
+                                   L.ptr(mu[h][k][v]), L.ptr(istd[h][k][v]), 0, 0, R[h], widths[h][k], relu, cen) for h in range(nh) for v in range(2)]
             if with_bias_sums:  # column sums of dp = the bias gradient of the predictor's last Linear, in the same launch
                 items += [L.HeadBwdItem(L.ptr(gp[h][v]), 0, 0, L.ptr(part[h][4][v]), 0, 0, 0, 0, 0, 0, R[h], heads[h].d, 0, 0) for h in range(nh) for v in range(2)]
             for ch in chunks(items, L.MSF_HEAD_MAX_MATS):
@@ -422,7 +423,7 @@ class _HeadStage(torch.autograd.Function):
                     "msf_head_bn_bwd_finalize")
             L.launch_count += 1
             items = [L.HeadBwdItem(L.ptr(g_in[h][v]), L.ptr(y[h][k][v]), L.ptr(dy_out[h][v]), 0, L.ptr(sc[h][k][v]), L.ptr(sh[h][k][v]),
-                                   L.ptr(mu[h][k][v]), L.ptr(istd[h][k][v]), L.ptr(c1[h][k][v]), L.ptr(c2[h][k][v]), R[h], widths[h][k], relu, 0)
+                                   L.ptr(mu[h][k][v]), L.ptr(istd[h][k][v]), L.ptr(c1[h][k][v]), L.ptr(c2[h][k][v]), R[h], widths[h][k], relu, cen)
                      for h in range(nh) for v in range(2)]
             for ch in chunks(items, L.MSF_HEAD_MAX_MATS):
                 L.check(lib.msf_head_bn_bwd_elemt(_arr(L.HeadBwdItem, ch), len(ch), code, st), "msf_head_bn_bwd_elemt")

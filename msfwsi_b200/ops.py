@@ -865,7 +865,7 @@ def bn_eval_apply(x: torch.Tensor, weight, bias, running_mean: torch.Tensor, run
                                          L.ptr(running_mean), L.ptr(running_var), rows, Cc, 1, 0))
     L.check(L.lib().msf_head_bn_finalize(it, 1, float(eps), 0.0, 0, 0, 1, 0, 0, 0, 1, L.stream_ptr()), "msf_head_bn_finalize")
     y = torch.empty_like(x)
-    ap = (L.HeadApplyItem * 1)(L.HeadApplyItem(L.ptr(x), L.ptr(y), 0, 0, L.ptr(sc), L.ptr(sh), rows, Cc, int(relu), 0))
+    ap = (L.HeadApplyItem * 1)(L.HeadApplyItem(L.ptr(x), L.ptr(y), 0, 0, L.ptr(sc), L.ptr(sh), 0, rows, Cc, int(relu), 0))
     L.check(L.lib().msf_head_bn_apply(ap, 1, L.dtype_code(x.dtype), COS_EPS, L.stream_ptr()), "msf_head_bn_apply")
     L.launch_count += 2
     return y

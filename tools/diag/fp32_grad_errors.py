@@ -24,6 +24,13 @@ def rel(a, b):
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 torch.manual_seed(11)
 mine = M.MSFWSI(lambda **kw: _Null(**kw), 4).to(DEV).train()
+if len(sys.argv) > 2 and sys.argv[2] == "affine":
+    with torch.no_grad():
+        for n, p in mine.named_parameters():
+            if p.dim() == 1 and n.endswith("weight"):
+                p.uniform_(0.5, 1.5)
+            elif p.dim() == 1:
+                p.uniform_(-0.3, 0.3)
 ref = R.RefMSFWSI(lambda **kw: _Null(**kw), 4).to(DEV).train()
 ref.load_state_dict(mine.state_dict())
 ref64 = R.RefMSFWSI(lambda **kw: _Null(**kw), 4).to(DEV).double().train()
