@@ -442,6 +442,7 @@ struct PairPlan {
   int splits;      // O partials: flash key splits, or world (one per rank block)
   int rs_splits;   // row-sum partials
   int q_tiles, k_tiles, tiles_per_rank, tiles_per_split, nq_pad;
+  int p_ranks;     // two-pass: rank blocks whose P matrices are resident at once (the rest reuse the slots in later rounds)
   size_t off_rowsum, off_o, off_stat, off_p, off_inv;
   int64_t ld_p;
 };
@@ -499,7 +500,15 @@ Plan make_plan(const msf_nce_pair* pr, int n) {
     p.off_inv = off;
     if (p.mode == 2) off = align256(off + static_cast<size_t>(g.nq) * sizeof(float));
     p.off_p = off;
-    if (p.mode == 2) off = align256(off + static_cast<size_t>(g.world) * g.nq * p.ld_p * 2);
+    p.p_ranks = 1;
+    if (p.mode == 2) {
+      // P = exp2(.) of one rank block is nq x rows_per_rank 16-bit values; keep at most ~256 MB of them resident per pair and
+      // walk the remaining rank blocks in later rounds (a 16384 x 131072 problem needs 512 MB instead of 4.3 GB)
+      const size_t per_rank = static_cast<size_t>(g.nq) * p.ld_p * 2;
+      const size_t fit = per_rank ? (static_cast<size_t>(256) << 20) / per_rank : 1;
+      p.p_ranks = static_cast<int>(std::max<size_t>(1, std::min<size_t>(fit, g.world)));
+      off = align256(off + static_cast<size_t>(p.p_ranks) * per_rank);
+    }
   }
   size_t blocks = 0;
   for (int i = 0; i < n; ++i) blocks += static_cast<size_t>(pr[i].nq) / 8 + 2;
@@ -646,45 +655,52 @@ extern "C" int msf_nce_grouped_fwd(const msf_nce_pair* pairs, int n_pairs, int d
     }
   }
 
-  // ---- widths above 256: per rank block, P = exp2(a_i q.k - a) (16 bit, + row sums) then O_r = P K_r ----
+  // ---- widths above 256: per rank block, P = exp2(a_i q.k - a) (16 bit, + row sums) then O_r = P K_r; rank blocks beyond
+  // the resident P budget are walked in rounds that reuse the P slots (stream order makes the reuse safe) ----
   {
-    std::vector<msf_gemm_problem> g1, g2;
-    double flops = 0.0;
+    int rounds = 0;
     for (int i = 0; i < n_pairs; ++i) {
-      const msf_nce_pair& g = pairs[i];
       const PairPlan& p = pl.pp[i];
       if (p.mode != 2) continue;
-      float* inv = reinterpret_cast<float*>(ws + p.off_inv);
-      if (g.q_rowsq) {
-        nce_inv_norm_kernel<<<(g.nq + 255) / 256, 256, 0, st>>>(g.q_rowsq, g.nq, (g.D + 63) / 64, eps, inv);
+      rounds = std::max(rounds, (pairs[i].world + p.p_ranks - 1) / p.p_ranks);
+      if (pairs[i].q_rowsq) {
+        nce_inv_norm_kernel<<<(pairs[i].nq + 255) / 256, 256, 0, st>>>(pairs[i].q_rowsq, pairs[i].nq, (pairs[i].D + 63) / 64, eps,
+                                                                       reinterpret_cast<float*>(ws + p.off_inv));
         MSF_LAUNCH_OK("nce_inv_norm_kernel");
       }
-      for (int r = 0; r < g.world; ++r) {
-        const char* kr = static_cast<const char*>(g.keys) + static_cast<size_t>(r) * (g.world > 1 ? g.rank_stride : 0) * 2;
-        char* Pm = ws + p.off_p + static_cast<size_t>(r) * g.nq * p.ld_p * 2;
-        msf_gemm_problem a1{};
-        a1.A = g.q; a1.lda = g.D; a1.B = kr; a1.ldb = g.D; a1.C = Pm; a1.ldc = p.ld_p;
-        a1.M = g.nq; a1.N = g.rows_per_rank; a1.K = g.D; a1.out_dtype = MSF_BF16; a1.alpha = 1.f; a1.split_k = -1;
-        a1.exp_a = a; a1.row_scale = g.q_rowsq ? inv : nullptr;
-        a1.row_sumsq = reinterpret_cast<float*>(ws + p.off_rowsum) + static_cast<size_t>(r) * p.tiles_per_rank * p.nq_pad;
-        a1.row_sum_ld = p.nq_pad;
-        g1.push_back(a1);
-        msf_gemm_problem a2{};
-        a2.A = Pm; a2.lda = p.ld_p; a2.B = kr; a2.ldb = g.D; a2.b_is_kn = 1;
-        a2.C = reinterpret_cast<float*>(ws + p.off_o) + static_cast<size_t>(r) * p.nq_pad * g.D; a2.ldc = g.D;
-        a2.M = g.nq; a2.N = g.D; a2.K = g.rows_per_rank; a2.out_dtype = MSF_F32; a2.alpha = 1.f; a2.split_k = -1;
-        g2.push_back(a2);
-        flops += 4.0 * g.nq * static_cast<double>(g.rows_per_rank) * g.D;
-      }
     }
-    if (!g1.empty()) {
+    for (int round = 0; round < rounds; ++round) {
+      std::vector<msf_gemm_problem> g1, g2;
+      double flops = 0.0;
+      for (int i = 0; i < n_pairs; ++i) {
+        const msf_nce_pair& g = pairs[i];
+        const PairPlan& p = pl.pp[i];
+        if (p.mode != 2) continue;
+        float* inv = reinterpret_cast<float*>(ws + p.off_inv);
+        for (int r = round * p.p_ranks; r < std::min(g.world, (round + 1) * p.p_ranks); ++r) {
+          const char* kr = static_cast<const char*>(g.keys) + static_cast<size_t>(r) * (g.world > 1 ? g.rank_stride : 0) * 2;
+          char* Pm = ws + p.off_p + static_cast<size_t>(r - round * p.p_ranks) * g.nq * p.ld_p * 2;
+          msf_gemm_problem a1{};
+          a1.A = g.q; a1.lda = g.D; a1.B = kr; a1.ldb = g.D; a1.C = Pm; a1.ldc = p.ld_p;
+          a1.M = g.nq; a1.N = g.rows_per_rank; a1.K = g.D; a1.out_dtype = MSF_BF16; a1.alpha = 1.f; a1.split_k = -1;
+          a1.exp_a = a; a1.row_scale = g.q_rowsq ? inv : nullptr;
+          a1.row_sumsq = reinterpret_cast<float*>(ws + p.off_rowsum) + static_cast<size_t>(r) * p.tiles_per_rank * p.nq_pad;
+          a1.row_sum_ld = p.nq_pad;
+          g1.push_back(a1);
+          msf_gemm_problem a2{};
+          a2.A = Pm; a2.lda = p.ld_p; a2.B = kr; a2.ldb = g.D; a2.b_is_kn = 1;
+          a2.C = reinterpret_cast<float*>(ws + p.off_o) + static_cast<size_t>(r) * p.nq_pad * g.D; a2.ldc = g.D;
+          a2.M = g.nq; a2.N = g.D; a2.K = g.rows_per_rank; a2.out_dtype = MSF_F32; a2.alpha = 1.f; a2.split_k = -1;
+          g2.push_back(a2);
+          flops += 4.0 * g.nq * static_cast<double>(g.rows_per_rank) * g.D;
+        }
+      }
+      if (g1.empty()) continue;
       ProfScope prof(stream, MSF_K_NCE_TWOPASS, flops);
       for (size_t lo = 0; lo < g1.size(); lo += MSF_GEMM_MAX_PROBLEMS) {
         const int cnt = static_cast<int>(std::min<size_t>(MSF_GEMM_MAX_PROBLEMS, g1.size() - lo));
         if (int rc = gemm_grouped_launch(g1.data() + lo, cnt, MSF_BF16, nullptr, 0, nullptr, stream)) return rc;
-      }
-      for (size_t lo = 0; lo < g2.size(); lo += MSF_GEMM_MAX_PROBLEMS) {
-        const int cnt = static_cast<int>(std::min<size_t>(MSF_GEMM_MAX_PROBLEMS, g2.size() - lo));
+        // the matching O_r = P K_r problems right behind their P producers: a later chunk of the same round may not reuse a slot
         if (int rc = gemm_grouped_launch(g2.data() + lo, cnt, MSF_BF16, nullptr, 0, nullptr, stream)) return rc;
       }
     }
