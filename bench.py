@@ -575,8 +575,9 @@ def gpu_eager_baseline(torch, dist, args, dev, world, rank, barrier, max_over_ra
 # microbenchmarks measured in the same process
 # ------------------------------------------------------------------------------------------------------------
 def infonce_microbench(torch, ops, _lib, dev, peaks, traffic):
-    """c5 rows: the fused InfoNCE forward (main tcgen05 kernel + finalize) and the whole fwd+bwd chain (row-normalise
-    x2, forward, backward) with CUDA events on the launching stream, L2 flushed between iterations."""
+    """c5 rows through the GROUPED entry points the training step calls (msf_nce_grouped_fwd / _bwd, one pair): the fused
+    InfoNCE forward (flash tcgen05 launch + finalize + sum) and the whole fwd+bwd chain (row-normalise x2, forward, backward)
+    with CUDA events on the launching stream, L2 flushed between iterations."""
     L = _lib
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     peak = peaks.get("bf16_tflops", 1590.0)
@@ -586,23 +587,24 @@ def infonce_microbench(torch, ops, _lib, dev, peaks, traffic):
         k = torch.randn(n, d, device=dev, generator=g)
         q = (0.3 * k + torch.randn(n, d, device=dev, generator=g)).to(torch.bfloat16)
         k = k.to(torch.bfloat16)
-        qh, qi = ops.rownorm(q, torch.bfloat16)
+        qh, _ = ops.rownorm(q, torch.bfloat16)
         kh, _ = ops.rownorm(k, torch.bfloat16)
-        wsb = L.lib().msf_infonce_workspace_bytes(n, n, d, L.MSF_BF16)
+        gq = torch.empty_like(q)
+        pair = (L.NcePair * 1)(L.NcePair(qh.data_ptr(), 0, kh.data_ptr(), gq.data_ptr(), 0, n, n, 1, d, 0, 1.0))
+        wsb = L.lib().msf_nce_grouped_workspace_bytes(pair, 1)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-        loss, gout, gq = torch.empty((), device=dev), torch.ones((), device=dev), torch.empty_like(q)
+        loss, gout = torch.empty((), device=dev), torch.ones((), device=dev)
         st = L.stream_ptr()
-        ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
         def fwd():
-            L.check(L.lib().msf_infonce_fwd(qh.data_ptr(), kh.data_ptr(), n, n, d, 0, 0.07, L.MSF_BF16, loss.data_ptr(), 0, ws.data_ptr(), wsb, st), "fwd")
+            L.check(L.lib().msf_nce_grouped_fwd(pair, 1, L.MSF_BF16, 0.07, 1e-8, loss.data_ptr(), ws.data_ptr(), wsb, st), "fwd")
 
         def chain():
-            a, ai = ops.rownorm(q, torch.bfloat16)
+            a, _ = ops.rownorm(q, torch.bfloat16)
             b, _ = ops.rownorm(k, torch.bfloat16)
-            L.check(L.lib().msf_infonce_fwd(a.data_ptr(), b.data_ptr(), n, n, d, 0, 0.07, L.MSF_BF16, loss.data_ptr(), 0, ws.data_ptr(), wsb, st), "fwd")
-            L.check(L.lib().msf_infonce_bwd(a.data_ptr(), b.data_ptr(), ai.data_ptr(), n, n, d, 0, 0.07, L.MSF_BF16, gout.data_ptr(), 1.0 / n,
-                                            ws.data_ptr(), wsb, gq.data_ptr(), L.MSF_BF16, st), "bwd")
+            pr = (L.NcePair * 1)(L.NcePair(a.data_ptr(), 0, b.data_ptr(), gq.data_ptr(), 0, n, n, 1, d, 0, 1.0))
+            L.check(L.lib().msf_nce_grouped_fwd(pr, 1, L.MSF_BF16, 0.07, 1e-8, loss.data_ptr(), ws.data_ptr(), wsb, st), "fwd")
+            L.check(L.lib().msf_nce_grouped_bwd(pr, 1, L.MSF_BF16, 0.07, 1e-8, gout.data_ptr(), ws.data_ptr(), wsb, st), "bwd")
 
         out = {"N": n, "D": d, "flops": 4.0 * n * n * d}
         for name, fn in (("fwd", fwd), ("fwd_bwd", chain)):
@@ -623,13 +625,14 @@ def infonce_microbench(torch, ops, _lib, dev, peaks, traffic):
         rows.append(out)
     top = rows[-1]  # N = 65536, D = 256: the configuration the ncu traffic capture was taken on
     t = traffic.get("infonce_flash_fwd")
-    roof = {"kernel": f"infonce_tc_kernel<{top['D']}> N=Nq={top['N']} tau=0.07: forward+backward chain (row-normalise x2, fused tcgen05 "
+    roof = {"kernel": f"infonce_grouped_kernel<{top['D']}> N=Nq={top['N']} tau=0.07: forward+backward chain (row-normalise x2, fused tcgen05 "
                       "main loop, finalize, backward)",
             "bound": "tensor", "achieved": top["tflops_fwd_bwd"], "peak": peak, "unit": "TFLOP/s", "frac": top["frac_fwd_bwd"],
             "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst: the kernel is timed alone)" if peaks else "fallback 1590 (B200_PROFILING.md)",
             "algorithmic_flops_per_launch": top["flops"], "ms": top["ms_fwd_bwd"],
             "main_kernel_only": {"achieved": top["tflops_fwd"], "frac": top["frac_fwd"], "ms": top["ms_fwd"]},
-            "d128": {"achieved": rows[1]["tflops_fwd_bwd"], "frac": rows[1]["frac_fwd_bwd"], "ms": rows[1]["ms_fwd_bwd"]},
+            "d128": {"achieved": rows[1]["tflops_fwd_bwd"], "frac": rows[1]["frac_fwd_bwd"], "ms": rows[1]["ms_fwd_bwd"],
+                     "main_kernel_only_frac": rows[1]["frac_fwd"]},
             "traffic": None if t is None else t.get("dram_bytes_per_launch"),
             "traffic_note": None if t is None else (f"ncu capture at {t.get('shape')}: {t.get('dram_bytes_per_launch'):.4g} B of DRAM traffic for "
                                                     f"{t.get('algorithmic_bytes_per_launch'):.4g} algorithmic B (ratio {t.get('ratio_to_algorithmic'):.3f}); "
@@ -687,6 +690,32 @@ def hbm_microbench(torch, ops, _lib, dev, peaks):
         fn = lambda: L.check(L.lib().msf_crop_resample_fwd(feat.data_ptr(), Bc, Cc, H, W, boxes.data_ptr(), 16, oh, ow, L.MSF_BF16, outp.data_ptr(), st), "crop")
         rec(f"A2 crop_resample fwd bf16, {tag}", nb, timeit(fn), f"feat {tuple(feat.shape)} -> 16 footprints of {oh}x{ow}; {100 * outp.numel() * e // nb}% of the bytes are writes")
         del feat, outp
+    # D1b: the 34 views of 64 source tiles (context crops of the whole tile, target crops inside the 256^2 tiles), stem layout out
+    Bs, S = 64, 1024
+    src = torch.randint(0, 256, (Bs, S, S, 3), dtype=torch.uint8, device=dev, generator=g)
+    cr = []
+    for v in range(2):
+        side = torch.randint(724, 1025, (Bs,), device=dev, generator=g)
+        y0 = (torch.rand(Bs, device=dev, generator=g) * (S - side + 1)).long()
+        x0 = (torch.rand(Bs, device=dev, generator=g) * (S - side + 1)).long()
+        cr.append(torch.stack((torch.arange(Bs, device=dev), y0, x0, y0 + side, x0 + side, torch.zeros_like(y0)), 1))
+    for v in range(2):
+        side = torch.randint(181, 257, (Bs, 16), device=dev, generator=g)
+        y0 = (torch.rand(Bs, 16, device=dev, generator=g) * (256 - side + 1)).long()
+        x0 = (torch.rand(Bs, 16, device=dev, generator=g) * (256 - side + 1)).long()
+        perm = torch.stack([torch.randperm(16, device=dev) for _ in range(Bs)])
+        cr.append(ops.jigsaw_view_crops(perm, torch.stack((y0, x0, y0 + side, x0 + side), 2), torch.zeros_like(y0), S, S, 4).long())
+    crops = torch.cat(cr).to(torch.int32)
+    nv = crops.shape[0]
+    area = ((crops[:, 3] - crops[:, 1]).double() * (crops[:, 4] - crops[:, 2]).double()).sum().item()
+    outv = torch.empty((nv, 16, 115, 115), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
+    m3, s3 = (L.C.c_float * 3)(0.6998, 0.4785, 0.6609), (L.C.c_float * 3)(0.2203, 0.2407, 0.1983)
+    nb = 3.0 * area + outv.numel() * 2
+    fn = lambda: L.check(L.lib().msf_view_crops_s2d(src.data_ptr(), Bs, S, S, crops.data_ptr(), nv, 224, 224, m3, s3, outv.data_ptr(), L.MSF_BF16, 0, st), "views")
+    rec("D1b view_crops_s2d uint8 -> bf16 stem layout", nb, timeit(fn),
+        f"{nv} views of {Bs} source tiles (RandomResizedCrop boxes, jigsaw permutation); bytes = cropped source regions once ({3.0 * area / 1e6:.0f} MB) + "
+        f"views written ({outv.numel() * 2 / 1e6:.0f} MB)")
+    del src, outv
     sizes = [64 * 3 * 49, 64, 64] + [64 * 64 * 9] * 4 + [128 * 64 * 9, 128 * 128 * 9] + [256 * 256 * 9] * 3 + [512 * 512 * 9] * 3 + \
             [4608 * 4608] * 3 + [2304 * 2304] * 3 + [1152 * 1152] * 3 + [576 * 576] * 3 + [512, 256, 128, 64] * 8
     teacher = [torch.randn(n, device=dev) for n in sizes]

@@ -64,6 +64,7 @@ struct alignas(64) FlashParams {
   int32_t n;
   float a, eps;
   int32_t issue_policy;
+  int32_t exp_mode;  // 0: one MUFU ex2 per logit; 1 / 2: every 4th / 2nd pair of logits through a cubic on the FMA pipes instead
 };
 
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
@@ -94,9 +95,13 @@ __global__ void __launch_bounds__(kThreads, 1) infonce_grouped_kernel(const __gr
 #pragma unroll 1
   while (pi + 1 < P.n && static_cast<int>(blockIdx.x) >= P.p[pi].cta_end) ++pi;
   const FlashProblem& q = P.p[pi];
+  // split-major inside a pair: the ~148 co-resident CTAs then hold consecutive query tiles of the SAME key split and walk the
+  // same key tiles in near lockstep, so L2 serves each key tile once to all of them (with the splits interleaved two key
+  // streams compete for the L2 -> SM feed, which this kernel uses to ~75 %: measured 0.76 vs 0.92 of peak at D = 256)
   const int local = blockIdx.x - q.cta_start;
-  const int split = local % q.splits;
-  const int64_t q0 = static_cast<int64_t>(local / q.splits) * BM;
+  const int q_tiles = (q.nq + BM - 1) / BM;
+  const int split = local / q_tiles;
+  const int64_t q0 = static_cast<int64_t>(local % q_tiles) * BM;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt0 = split * q.tiles_per_split;
   const int kt1 = min(q.k_tiles, kt0 + q.tiles_per_split);
@@ -126,14 +131,18 @@ __global__ void __launch_bounds__(kThreads, 1) infonce_grouped_kernel(const __gr
       tma_prefetch_desc(&q.tk);
       mbar_expect_tx(q_full, C::kTileBytes);
       for (int s = 0; s < C::kSlabs; ++s) tma_load_2d(sQ + s * kSlabBytes, &q.tq, s * 64, static_cast<int>(q0), q_full);
+      // a key tile never straddles two rank blocks; (rank, row) advance incrementally -- a division per tile would sit between a
+      // stage becoming free and its refill, which the two 64 KB stages of D = 256 cannot hide
+      const int tpr = q.tiles_per_rank;
+      int rank = kt0 / tpr, tile_in_rank = kt0 - rank * tpr;
       for (int t = 0; t < T; ++t) {
         const int stage = t % C::kStages;
         mbar_wait(k_empty + stage, ((t / C::kStages) & 1) ^ 1);
         mbar_expect_tx(k_full + stage, C::kTileBytes);
         uint8_t* dst = sK + stage * C::kTileBytes;
-        const int kt = kt0 + t;
-        const int rank = kt / q.tiles_per_rank, row = (kt % q.tiles_per_rank) * BN;  // a key tile never straddles two rank blocks
+        const int row = tile_in_rank * BN;
         for (int s = 0; s < C::kSlabs; ++s) tma_load_3d(dst + s * kSlabBytes, &q.tk, s * 64, row, rank, k_full + stage);
+        if (++tile_in_rank == tpr) { tile_in_rank = 0; ++rank; }
       }
     }
   } else if (warp == 1) {
@@ -235,14 +244,67 @@ __global__ void __launch_bounds__(kThreads, 1) infonce_grouped_kernel(const __gr
         u[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
       }
     };
+    // MUFU-lean variant.  At D <= 128 one ex2 per logit needs as many cycles on the SM's 16 MUFU lanes as the two GEMMs need on
+    // the tensor pipe (1024 cycles per 128 x 128 tile each), so any hiccup of either stalls the other.  Every 4th (exp_mode 1)
+    // or every 2nd (exp_mode 2) PAIR of logits therefore takes the FMA pipes instead: 2^y = 2^round(y) * p(y - round(y)) with a
+    // cubic p on [-0.5, 0.5] (max relative error 1.0e-4, far below the bf16 rounding of P) -- magic-number rounding, three packed
+    // FFMA2 and an integer add into the exponent field per pair.
+    auto chunk_mix = [&](const uint32_t* v, uint32_t* u, const int mask) {
+      const float2 magic = make_float2(12582912.f, 12582912.f), nmagic = make_float2(-12582912.f, -12582912.f), none = make_float2(-1.f, -1.f);
+      const float2 c1 = make_float2(0.6932829022407532f, 0.6932829022407532f), c2 = make_float2(0.24221095442771912f, 0.24221095442771912f),
+                   c3 = make_float2(0.05500892922282219f, 0.05500892922282219f), one = make_float2(1.f, 1.f);
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const float2 y = __ffma2_rn(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), a2, na2);
+        float2 e;
+        if (((i >> 1) & mask) == mask) {
+          const float2 r = __fadd2_rn(y, magic);                  // low mantissa bits of r = round(y) as an integer
+          const float2 f = __ffma2_rn(__fadd2_rn(r, nmagic), none, y);  // y - round(y) in [-0.5, 0.5]
+          float2 pl = __ffma2_rn(c3, f, c2);
+          pl = __ffma2_rn(pl, f, c1);
+          pl = __ffma2_rn(pl, f, one);
+          e.x = __uint_as_float(__float_as_uint(pl.x) + (__float_as_uint(r.x) << 23));  // * 2^round(y): the shift drops the magic's bits
+          e.y = __uint_as_float(__float_as_uint(pl.y) + (__float_as_uint(r.y) << 23));
+        } else {
+          e = make_float2(ex2_approx(y.x), ex2_approx(y.y));
+        }
+        rs2 = __fadd2_rn(rs2, e);
+        __nv_bfloat162 h = __floats2bfloat162_rn(e.x, e.y);
+        u[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+      }
+    };
+    const int tpr_s = q.tiles_per_rank, rows_s = q.rows_per_rank;
+    const bool ragged = (rows_s % BN) != 0;
+    const bool fast = P.exp_mode != 0;
+    const int mix_mask = P.exp_mode == 2 ? 1 : 3;
     for (int t = wg; t < T; t += 2) {
       mbar_wait(s_full + wg, (t >> 1) & 1);
       tc_fence_after();
-      const int krow0 = ((kt0 + t) % q.tiles_per_rank) * BN;
-      const int valid = min(BN, q.rows_per_rank - krow0);  // rows past a rank block are zero-filled by TMA: mask them out
+      // rows past a rank block are zero-filled by TMA and must be masked out: only the last tile of a rank block can be short
+      int valid = BN;
+      if (ragged) {
+        const int krow0 = ((kt0 + t) % tpr_s) * BN;
+        valid = min(BN, rows_s - krow0);
+      }
       uint32_t v0[32], v1[32], u[16];
       tmem_ld32(s_addr, v0);
-      if (valid == BN) {
+      if (valid == BN && fast) {
+        tmem_ld_wait();
+        tmem_ld32(s_addr + 32, v1);
+        chunk_mix(v0, u, mix_mask);
+        tmem_st16(s_addr, u);
+        tmem_ld_wait();
+        tmem_ld32(s_addr + 64, v0);
+        chunk_mix(v1, u, mix_mask);
+        tmem_st16(s_addr + 16, u);
+        tmem_ld_wait();
+        tmem_ld32(s_addr + 96, v1);
+        chunk_mix(v0, u, mix_mask);
+        tmem_st16(s_addr + 32, u);
+        tmem_ld_wait();
+        chunk_mix(v1, u, mix_mask);
+        tmem_st16(s_addr + 48, u);
+      } else if (valid == BN) {
         tmem_ld_wait();
         tmem_ld32(s_addr + 32, v1);
         chunk(v0, u, 0, BN, false);
@@ -457,14 +519,31 @@ bool flash_dim(int d) { return d == 64 || d == 128 || d == 256; }
 Plan make_plan(const msf_nce_pair* pr, int n) {
   Plan pl;
   pl.pp.resize(n);
-  // flash launches share the machine per width class: pick the tiles-per-CTA target from the class's total work
-  double work[3] = {0, 0, 0};
+  // The pairs of a width class share ONE flash launch: choose the key tiles per CTA, T, that minimises
+  // waves x (T + 3) over the whole class (3 tile-times stand for a CTA's prologue / epilogue), waves = ceil(CTAs / 148) with
+  // CTAs = sum_pairs q_tiles x ceil(k_tiles / T).  Ties go to the larger T (fewer partials to write and re-read).
   auto cls = [](int d) { return d == 64 ? 0 : (d == 128 ? 1 : 2); };
-  for (int i = 0; i < n; ++i)
-    if (flash_dim(pr[i].D)) {
-      const int qt = (pr[i].nq + BM - 1) / BM, tpr = (pr[i].rows_per_rank + BN - 1) / BN;
-      work[cls(pr[i].D)] += static_cast<double>(qt) * tpr * pr[i].world;
+  int best_T[3] = {1, 1, 1};
+  for (int c = 0; c < 3; ++c) {
+    int max_kt = 0;
+    for (int i = 0; i < n; ++i)
+      if (flash_dim(pr[i].D) && cls(pr[i].D) == c) max_kt = std::max(max_kt, ((pr[i].rows_per_rank + BN - 1) / BN) * pr[i].world);
+    double best = 1e300;
+    for (int T = max_kt; T >= 1; --T) {
+      int64_t ctas = 0;
+      bool ok = true;
+      for (int i = 0; i < n; ++i) {
+        if (!flash_dim(pr[i].D) || cls(pr[i].D) != c) continue;
+        const int64_t kt = static_cast<int64_t>((pr[i].rows_per_rank + BN - 1) / BN) * pr[i].world;
+        const int64_t sp = (kt + T - 1) / T;
+        if (sp > 32) ok = false;  // at most 32 O partials per pair
+        ctas += static_cast<int64_t>((pr[i].nq + BM - 1) / BM) * sp;
+      }
+      if (!ok) break;
+      const double cost = static_cast<double>((ctas + kNumSMs - 1) / kNumSMs) * (T + 3.0);
+      if (cost < best * 0.999) { best = cost; best_T[c] = T; }
     }
+  }
   size_t off = 0;
   for (int i = 0; i < n; ++i) {
     const msf_nce_pair& g = pr[i];
@@ -475,11 +554,7 @@ Plan make_plan(const msf_nce_pair* pr, int n) {
       p.mode = 0;
       p.tiles_per_rank = (g.rows_per_rank + BN - 1) / BN;
       p.k_tiles = p.tiles_per_rank * g.world;
-      double target = work[cls(g.D)] / (2.0 * kNumSMs);  // ~2 waves of CTAs over the class
-      if (target < 4.0) target = 4.0;
-      int s = static_cast<int>((p.k_tiles + target - 1) / target);
-      s = std::max(1, std::min({s, p.k_tiles, 32}));
-      p.tiles_per_split = (p.k_tiles + s - 1) / s;
+      p.tiles_per_split = std::min(best_T[cls(g.D)], p.k_tiles);
       p.splits = (p.k_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
       p.rs_splits = p.splits;
       p.ld_p = 0;
@@ -549,6 +624,12 @@ inline int make_map_keys(CUtensorMap* map, const void* base, int D, int rows, in
   MSF_REQUIRE(r == CUDA_SUCCESS, MSF_ERR_CUDA, "cuTensorMapEncodeTiled (3-D keys) failed with CUresult %d", static_cast<int>(r));
   return MSF_OK;
 }
+
+// which exponential the softmax warps use per width class (see chunk_fast): decided by measurement, profiles/README.md
+// Measured at N = Nq = 65536 (profiles/README.md): D = 128 forward 0.745 -> 0.785 of the bf16 peak with every 4th pair on the
+// FMA pipes (MUFU and tensor pipe both need 1024 cycles per tile there); D = 256 is tensor-bound (2048 cycles per tile) and
+// loses 3 % to the extra issue slots, so it keeps one MUFU op per logit.
+inline int kDefaultExpMode(int D) { return D <= 128 ? 1 : 0; }
 
 template <int D>
 int launch_flash(const FlashParams& FP, int ctas, cudaStream_t st) {
@@ -621,6 +702,7 @@ extern "C" int msf_nce_grouped_fwd(const msf_nce_pair* pairs, int n_pairs, int d
 
   // ---- flash launches, one per width class ----
   static thread_local FlashParams FP;
+  static const int exp_env = getenv("MSF_NCE_EXP_MODE") ? atoi(getenv("MSF_NCE_EXP_MODE")) : -1;
   for (int D : {64, 128, 256}) {
     int nf = 0, ctas = 0;
     double flops = 0.0;
@@ -629,7 +711,8 @@ extern "C" int msf_nce_grouped_fwd(const msf_nce_pair* pairs, int n_pairs, int d
       if (g.D != D) continue;
       const PairPlan& p = pl.pp[i];
       if (nf == kMaxFlash) {  // table full: flush
-        FP.n = nf; FP.a = a; FP.eps = eps; FP.issue_policy = Cfg<256>::kStages <= 2 && D == 256 ? 1 : 0;
+        FP.n = nf; FP.a = a; FP.eps = eps; FP.issue_policy = D == 256 ? 1 : 0;
+        FP.exp_mode = exp_env >= 0 ? exp_env : kDefaultExpMode(D);
         ProfScope prof(stream, MSF_K_NCE_FLASH, flops);
         if (int rc = (D == 64 ? launch_flash<64>(FP, ctas, st) : D == 128 ? launch_flash<128>(FP, ctas, st) : launch_flash<256>(FP, ctas, st))) return rc;
         nf = 0; ctas = 0; flops = 0.0;
@@ -650,6 +733,7 @@ extern "C" int msf_nce_grouped_fwd(const msf_nce_pair* pairs, int n_pairs, int d
     }
     if (nf > 0) {
       FP.n = nf; FP.a = a; FP.eps = eps; FP.issue_policy = D == 256 ? 1 : 0;
+      FP.exp_mode = exp_env >= 0 ? exp_env : kDefaultExpMode(D);
       ProfScope prof(stream, MSF_K_NCE_FLASH, flops);
       if (int rc = (D == 64 ? launch_flash<64>(FP, ctas, st) : D == 128 ? launch_flash<128>(FP, ctas, st) : launch_flash<256>(FP, ctas, st))) return rc;
     }

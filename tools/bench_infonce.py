@@ -65,8 +65,24 @@ def main():
                 L.check(L.lib().msf_infonce_bwd(qh.data_ptr(), kh.data_ptr(), qi.data_ptr(), n, n, d, 0, args.tau, prec, gout.data_ptr(),
                                                 1.0 / n, ws.data_ptr(), ws_bytes, gq.data_ptr(), L.MSF_BF16, st), "bwd")
 
+            # the grouped entry points (what the training step calls; one pair here): same flash pipeline behind a problem table
+            pair = (L.NcePair * 1)(L.NcePair(q_hat.data_ptr(), 0, k_hat.data_ptr(), gq.data_ptr(), 0, n, n, 1, d, 0, 1.0))
+            gws_bytes = L.lib().msf_nce_grouped_workspace_bytes(pair, 1)
+            gws = torch.empty(gws_bytes, dtype=torch.uint8, device=dev)
+            gloss = torch.empty((), dtype=torch.float32, device=dev)
+
+            def gfwd():
+                L.check(L.lib().msf_nce_grouped_fwd(pair, 1, prec, args.tau, 1e-8, gloss.data_ptr(), gws.data_ptr(), gws_bytes, st), "gfwd")
+
+            def gchain():
+                qh, qi = ops.rownorm(q, torch.bfloat16)
+                kh, _ = ops.rownorm(k, torch.bfloat16)
+                pr = (L.NcePair * 1)(L.NcePair(qh.data_ptr(), 0, kh.data_ptr(), gq.data_ptr(), 0, n, n, 1, d, 0, 1.0))
+                L.check(L.lib().msf_nce_grouped_fwd(pr, 1, prec, args.tau, 1e-8, gloss.data_ptr(), gws.data_ptr(), gws_bytes, st), "gfwd")
+                L.check(L.lib().msf_nce_grouped_bwd(pr, 1, prec, args.tau, 1e-8, gout.data_ptr(), gws.data_ptr(), gws_bytes, st), "gbwd")
+
             res = {}
-            for name, fn in (("fwd_kernels", fwd), ("fwd_bwd_chain", chain)):
+            for name, fn in (("fwd_kernels", fwd), ("fwd_bwd_chain", chain), ("grouped_fwd", gfwd), ("grouped_fwd_bwd", gchain)):
                 for _ in range(3):
                     fn()
                 ts = []
@@ -86,6 +102,9 @@ def main():
                    "peak_tflops": peak, "peak_source": how}
             row["frac_fwd"] = row["tflops_fwd"] / peak
             row["frac_fwd_bwd"] = row["tflops_fwd_bwd"] / peak
+            row.update({"grouped_ms_fwd": res["grouped_fwd"], "grouped_ms_fwd_bwd": res["grouped_fwd_bwd"], "grouped_frac_fwd": flops / res["grouped_fwd"] / 1e9 / peak,
+                        "grouped_frac_fwd_bwd": flops / res["grouped_fwd_bwd"] / 1e9 / peak, "grouped_loss": float(gloss.item()),
+                        "exp_mode": os.environ.get("MSF_NCE_EXP_MODE", "default")})
             rows.append(row)
             print(json.dumps(row), flush=True)
     if args.out:
