@@ -48,21 +48,28 @@ def main():
             q = q_all[rank * nq:(rank + 1) * nq].to(torch.bfloat16).contiguous()
             k = k_all[rank * nq:(rank + 1) * nq].to(torch.bfloat16).contiguous()
             del k_all, q_all
-            ws_bytes = L.lib().msf_infonce_workspace_bytes(nq, n, d, L.MSF_BF16)
+            # the grouped entry points of the training step: keys as rank-major blocks (exactly what one all-gather leaves behind),
+            # read through the 3-D TMA map {dim, row, rank}; positives in block `rank`
+            probe = (L.NcePair * 1)(L.NcePair(q.data_ptr(), 0, q.data_ptr(), q.data_ptr(), nq * d, nq, nq, world, d, rank, 1.0))
+            ws_bytes = L.lib().msf_nce_grouped_workspace_bytes(probe, 1)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             loss = torch.empty((), dtype=torch.float32, device=dev)
             gout = torch.ones((), device=dev)
             gq = torch.empty_like(q)
+            kgath = torch.empty(world * nq, d, dtype=torch.bfloat16, device=dev)
             st = L.stream_ptr()
 
             def step():
                 qh, qi = ops.rownorm(q, torch.bfloat16)
                 kh, _ = ops.rownorm(k, torch.bfloat16)
-                ka, off = ops.all_gather_keys(kh)
-                L.check(L.lib().msf_infonce_fwd(qh.data_ptr(), ka.data_ptr(), nq, n, d, off, args.tau, L.MSF_BF16, loss.data_ptr(), 0,
-                                                ws.data_ptr(), ws_bytes, st), "fwd")
-                L.check(L.lib().msf_infonce_bwd(qh.data_ptr(), ka.data_ptr(), qi.data_ptr(), nq, n, d, off, args.tau, L.MSF_BF16, gout.data_ptr(),
-                                                1.0 / n, ws.data_ptr(), ws_bytes, gq.data_ptr(), L.MSF_BF16, st), "bwd")
+                if world > 1:
+                    dist.all_gather_into_tensor(kgath, kh)
+                    keys = kgath
+                else:
+                    keys = kh
+                pr = (L.NcePair * 1)(L.NcePair(qh.data_ptr(), 0, keys.data_ptr(), gq.data_ptr(), nq * d, nq, nq, world, d, rank, 1.0))
+                L.check(L.lib().msf_nce_grouped_fwd(pr, 1, L.MSF_BF16, args.tau, 1e-8, loss.data_ptr(), ws.data_ptr(), ws_bytes, st), "fwd")
+                L.check(L.lib().msf_nce_grouped_bwd(pr, 1, L.MSF_BF16, args.tau, 1e-8, gout.data_ptr(), ws.data_ptr(), ws_bytes, st), "bwd")
 
             for _ in range(3):
                 step()
@@ -87,7 +94,7 @@ def main():
             if world > 1:
                 dist.all_reduce(total)
             flops = 4.0 * n * n * d
-            row = {"gpus": world, "N": n, "Nq_per_gpu": nq, "D": d, "mean_loss": float(total.item()) / n, "ms_fwd_bwd": ms,
+            row = {"gpus": world, "N": n, "Nq_per_gpu": nq, "D": d, "mean_loss": float(total.item()) / world, "ms_fwd_bwd": ms,
                    "tflops_whole_job": flops / ms / 1e9, "frac_of_peak": flops / ms / 1e9 / (peak1 * world), "peak_tflops_per_gpu": peak1}
             rows.append(row)
             if rank == 0:
