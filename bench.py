@@ -689,7 +689,11 @@ def hbm_microbench(torch, ops, _lib, dev, peaks):
         nb = feat.numel() * e + outp.numel() * e + Bc * 16 * 16
         fn = lambda: L.check(L.lib().msf_crop_resample_fwd(feat.data_ptr(), Bc, Cc, H, W, boxes.data_ptr(), 16, oh, ow, L.MSF_BF16, outp.data_ptr(), st), "crop")
         rec(f"A2 crop_resample fwd bf16, {tag}", nb, timeit(fn), f"feat {tuple(feat.shape)} -> 16 footprints of {oh}x{ow}; {100 * outp.numel() * e // nb}% of the bytes are writes")
-        del feat, outp
+        gfeat = torch.empty((Bc, Cc, H, W), dtype=torch.float32, device=dev)
+        nbb = outp.numel() * e + gfeat.numel() * 4 + Bc * 16 * 16
+        fnb = lambda: L.check(L.lib().msf_crop_resample_bwd(outp.data_ptr(), Bc, Cc, H, W, boxes.data_ptr(), 16, oh, ow, L.MSF_BF16, gfeat.data_ptr(), st), "crop bwd")
+        rec(f"A2 crop_resample bwd bf16 (gather form, no atomics), {tag}", nbb, timeit(fnb), f"grad_out {tuple(outp.shape)} -> fp32 grad_feat {tuple(gfeat.shape)}")
+        del feat, outp, gfeat
     # D1b: the 34 views of 64 source tiles (context crops of the whole tile, target crops inside the 256^2 tiles), stem layout out
     Bs, S = 64, 1024
     src = torch.randint(0, 256, (Bs, S, S, 3), dtype=torch.uint8, device=dev, generator=g)

@@ -362,7 +362,8 @@ int msf_head_bn_bwd_elemt(const msf_head_bwd_item* items /*host*/, int n, int dt
  * ---------------------------------------------------------------------------------------- */
 int msf_crop_resample_fwd(const void* feat, int64_t B, int C, int H, int W, const float* boxes, int K, int oh,
                           int ow, int dtype, void* out, void* stream);
-/* grad_feat (B,C,H,W) fp32, must be zero-filled by the caller; accumulates with atomics. */
+/* grad_feat (B,C,H,W) fp32, overwritten.  Gather form: one thread owns each source pixel and sums the output gradients
+ * that tap it in a fixed order -- no atomics, bit-reproducible run to run (also with overlapping boxes). */
 int msf_crop_resample_bwd(const void* grad_out, int64_t B, int C, int H, int W, const float* boxes, int K, int oh,
                           int ow, int dtype, float* grad_feat, void* stream);
 

@@ -6,6 +6,8 @@
 // HBM-bound: output rows are written with 128-bit stores (VEC consecutive ox per thread); the four
 // taps of neighbouring outputs overlap, so input traffic is the footprint once (L1/L2 hits after).
 // Algorithmic bytes: B*C*(union of footprints)*e read + B*K*C*oh*ow*e written + 16 B per box.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace msf {
@@ -327,31 +329,271 @@ __global__ void __launch_bounds__(256) crop_fwd_strip_kernel(const void* __restr
   }
 }
 
-template <int DT>
-__global__ void __launch_bounds__(256) crop_bwd_kernel(const void* __restrict__ gout, const float* __restrict__ boxes,
-                                                       float* __restrict__ gfeat, Geo g, int64_t total) {
-  for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
-       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    int64_t r = t;
-    const int ox = static_cast<int>(r % g.ow); r /= g.ow;
-    const int oy = static_cast<int>(r % g.oh); r /= g.oh;
-    const int c = static_cast<int>(r % g.C); r /= g.C;
-    const int k = static_cast<int>(r % g.K);
-    const int64_t b = r / g.K;
-    const float4 bx = __ldg(reinterpret_cast<const float4*>(boxes) + b * g.K + k);
-    int y0, y1, x0, x1;
-    float wy, wx;
-    axis_taps(bx.x, bx.z - bx.x, oy, g.oh, g.H, y0, y1, wy);
-    axis_taps(bx.y, bx.w - bx.y, ox, g.ow, g.W, x0, x1, wx);
-    const float go = ld1<DT>(gout, t);
-    float* plane = gfeat + (b * g.C + c) * static_cast<int64_t>(g.H) * g.W;
-    atomicAdd(plane + static_cast<int64_t>(y0) * g.W + x0, go * (1.f - wy) * (1.f - wx));
-    if (wx != 0.f) atomicAdd(plane + static_cast<int64_t>(y0) * g.W + x1, go * (1.f - wy) * wx);
-    if (wy != 0.f) {
-      atomicAdd(plane + static_cast<int64_t>(y1) * g.W + x0, go * wy * (1.f - wx));
-      if (wx != 0.f) atomicAdd(plane + static_cast<int64_t>(y1) * g.W + x1, go * wy * wx);
-    }
+// ---- backward, gather form: deterministic, no atomics -----------------------------------------------------------
+// grad_feat[b,c] = sum_k Wy_k^T * G_k * Wx_k with two taps per output row / column.  CTA = (sample, band of R source
+// rows, channel range); nobody else writes that part of grad_feat, and every sum runs in a fixed order (box, tap row,
+// tap column), so the result is bit-reproducible and overlapping boxes need no atomics.
+//   tables   the taps of one axis are non-decreasing in the output coordinate, so the outputs that reach a given source
+//            row / column through tap 0 (or tap 1) form ONE contiguous range: per box the CTA tabulates taps + weights
+//            (ow + oh evaluations), then finds the range ends by comparing neighbouring outputs (one writer per entry);
+//   vertical T[r][c][ox] = sum over the output rows that tap source row r, read with 128-bit loads along ox;
+//   horizon. acc[r][c][x] += sum over the output columns that tap x, from T in shared memory.
+// grad_out is read from HBM once (+ the rows shared by two bands), grad_feat written once.
+constexpr int kBwdThreads = 256, kBwdMaxGroup = 4;  // boxes per table group (<= 4: a 16-bit row x box mask)
+
+struct BwdPlan {
+  int R, cchunk, KL, csplit, bands, owp;
+  size_t off_wx, off_wy, off_ax, off_ay, off_xr, off_yr, off_list, off_flag, smem;
+};
+
+// column of T: one pad float per 16, so that lanes reading every 4th .. 16th column (1x .. 4x zoom, 4 pixels per lane) hit distinct banks
+__device__ __forceinline__ int tcol(int ox) { return ox + (ox >> 4); }
+
+__device__ __forceinline__ bool empty2(int lo0, int hi0, int lo1, int hi1) { return hi0 < lo0 && hi1 < lo1; }
+
+template <int DT, int VEC>
+__global__ void __launch_bounds__(kBwdThreads) crop_bwd_gather_kernel(const void* __restrict__ gout, const float* __restrict__ boxes,
+                                                                      float* __restrict__ gfeat, Geo g, BwdPlan p) {
+  extern __shared__ __align__(16) unsigned char bsm[];
+  float* T = reinterpret_cast<float*>(bsm);                        // [KL][R*cchunk][owp]
+  float* wx = reinterpret_cast<float*>(bsm + p.off_wx);            // [KL][ow]   weight of tap 1 along x
+  float* wy = reinterpret_cast<float*>(bsm + p.off_wy);            // [KL][oh]
+  short2* ax = reinterpret_cast<short2*>(bsm + p.off_ax);          // [KL][ow]   {tap 0, tap 1} source columns
+  short2* ay = reinterpret_cast<short2*>(bsm + p.off_ay);          // [KL][oh]
+  short4* xr = reinterpret_cast<short4*>(bsm + p.off_xr);          // [KL][W]    {lo0, hi0, lo1, hi1} output columns per source column
+  int4* yr = reinterpret_cast<int4*>(bsm + p.off_yr);              // [KL][R]    idem, output rows per source row of the band
+  int* list = reinterpret_cast<int*>(bsm + p.off_list);            // [K]        boxes that touch the band, ascending
+  int* flag = reinterpret_cast<int*>(bsm + p.off_flag);            // [K] + count
+  const int tid = threadIdx.x;
+  const int band = blockIdx.x % p.bands;
+  const int64_t b = blockIdx.x / p.bands;
+  const int y0 = band * p.R, rows = min(p.R, g.H - y0);
+  const int cbeg = blockIdx.y * p.csplit, cend = min(cbeg + p.csplit, g.C);
+  const float4* bxs = reinterpret_cast<const float4*>(boxes) + b * g.K;
+  constexpr int E = DT == MSF_F32 ? 4 : 2;
+
+  // boxes whose source rows [tap 0 of the first output row, tap 1 of the last] meet the band
+  for (int k = tid; k < g.K; k += kBwdThreads) {
+    const float4 bx = __ldg(bxs + k);
+    int lo, hi, u;
+    float w;
+    axis_taps(bx.x, bx.z - bx.x, 0, g.oh, g.H, lo, u, w);
+    axis_taps(bx.x, bx.z - bx.x, g.oh - 1, g.oh, g.H, u, hi, w);
+    flag[k] = lo <= y0 + rows - 1 && hi >= y0;
   }
+  __syncthreads();
+  if (tid == 0) {
+    int n = 0;
+    for (int k = 0; k < g.K; ++k)
+      if (flag[k]) list[n++] = k;
+    flag[g.K] = n;
+  }
+  __syncthreads();
+  const int nlist = flag[g.K];
+
+  int g0 = 0;
+  do {
+    const int gn = min(p.KL, nlist - g0);
+    // ---- tables of this group of boxes
+    for (int i = tid; i < gn * g.ow; i += kBwdThreads) {
+      const int j = i / g.ow, o = i - j * g.ow;
+      const float4 bx = __ldg(bxs + list[g0 + j]);
+      int a0, a1;
+      float w;
+      axis_taps(bx.y, bx.w - bx.y, o, g.ow, g.W, a0, a1, w);
+      ax[i] = make_short2(static_cast<short>(a0), static_cast<short>(a1));
+      wx[i] = w;
+    }
+    for (int i = tid; i < gn * g.oh; i += kBwdThreads) {
+      const int j = i / g.oh, o = i - j * g.oh;
+      const float4 bx = __ldg(bxs + list[g0 + j]);
+      int a0, a1;
+      float w;
+      axis_taps(bx.x, bx.z - bx.x, o, g.oh, g.H, a0, a1, w);
+      ay[i] = make_short2(static_cast<short>(a0), static_cast<short>(a1));
+      wy[i] = w;
+    }
+    for (int i = tid; i < gn * g.W; i += kBwdThreads) xr[i] = make_short4(1, 0, 1, 0);
+    for (int i = tid; i < gn * p.R; i += kBwdThreads) yr[i] = make_int4(1, 0, 1, 0);
+    __syncthreads();
+    // range ends: an output owns the start (end) of a range when its predecessor (successor) taps another source index.
+    // Tap-1 ranges ignore the weight (so they stay contiguous); zero-weight outputs are skipped when the range is walked.
+    for (int i = tid; i < gn * g.ow; i += kBwdThreads) {
+      const int j = i / g.ow, o = i - j * g.ow;
+      const short2 a = ax[i];
+      const short2 pr = o ? ax[i - 1] : make_short2(-1, -1), nx = o + 1 < g.ow ? ax[i + 1] : make_short2(-1, -1);
+      short* e0 = reinterpret_cast<short*>(xr + j * g.W + a.x);
+      short* e1 = reinterpret_cast<short*>(xr + j * g.W + a.y);
+      if (pr.x != a.x) e0[0] = static_cast<short>(o);
+      if (nx.x != a.x) e0[1] = static_cast<short>(o);
+      if (pr.y != a.y) e1[2] = static_cast<short>(o);
+      if (nx.y != a.y) e1[3] = static_cast<short>(o);
+    }
+    for (int i = tid; i < gn * g.oh; i += kBwdThreads) {
+      const int j = i / g.oh, o = i - j * g.oh;
+      const short2 a = ay[i];
+      const short2 pr = o ? ay[i - 1] : make_short2(-1, -1), nx = o + 1 < g.oh ? ay[i + 1] : make_short2(-1, -1);
+      const int r0 = a.x - y0, r1 = a.y - y0;
+      if (r0 >= 0 && r0 < rows) {
+        int* e = reinterpret_cast<int*>(yr + j * p.R + r0);
+        if (pr.x != a.x) e[0] = o;
+        if (nx.x != a.x) e[1] = o;
+      }
+      if (r1 >= 0 && r1 < rows) {
+        int* e = reinterpret_cast<int*>(yr + j * p.R + r1);
+        if (pr.y != a.y) e[2] = o;
+        if (nx.y != a.y) e[3] = o;
+      }
+    }
+    __syncthreads();
+
+    // per thread: which boxes of the group reach which band row (bit r*4+j), and the boxes' source-column extents
+    unsigned rowmask = 0;
+    int xlo[kBwdMaxGroup], xhi[kBwdMaxGroup];
+#pragma unroll
+    for (int j = 0; j < kBwdMaxGroup; ++j) {
+      xlo[j] = 1;
+      xhi[j] = 0;
+      if (j < gn) {
+        xlo[j] = ax[j * g.ow].x;
+        xhi[j] = ax[j * g.ow + g.ow - 1].y;
+        for (int r = 0; r < rows; ++r) {
+          const int4 yy = yr[j * p.R + r];
+          if (!empty2(yy.x, yy.y, yy.z, yy.w)) rowmask |= 1u << (r * kBwdMaxGroup + j);
+        }
+      }
+    }
+    for (int c0 = cbeg; c0 < cend; c0 += p.cchunk) {
+      const int cn = min(p.cchunk, cend - c0);
+      const int rc_n = rows * cn;
+      const int tstride = p.R * p.cchunk * p.owp;  // floats of T per box
+      // ---- vertical: T[j][r][c][ox] for every box of the group
+      const int owv = g.ow / VEC;
+      const float inv_owv = 1.f / owv;
+      for (int j = 0; j < gn; ++j) {
+        const int64_t plane0 = ((b * g.K + list[g0 + j]) * g.C + c0) * static_cast<int64_t>(g.oh) * g.ow;
+        const float* wyj = wy + j * g.oh;
+        for (int i = tid; i < rc_n * owv; i += kBwdThreads) {
+          const int rc = __float2int_rz((i + 0.5f) * inv_owv), v = i - rc * owv;
+          const int r = (rc >= cn) + (rc >= 2 * cn) + (rc >= 3 * cn), c = rc - r * cn;
+          if (!((rowmask >> (r * kBwdMaxGroup + j)) & 1u)) continue;
+          const int4 yy = yr[j * p.R + r];
+          const char* src = static_cast<const char*>(gout) + (plane0 + static_cast<int64_t>(c) * g.oh * g.ow + static_cast<int64_t>(v) * VEC) * E;
+          float t[VEC];
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) t[q] = 0.f;
+#pragma unroll
+          for (int tap = 0; tap < 2; ++tap) {
+            const int lo = tap ? yy.z : yy.x, hi = tap ? yy.w : yy.y;
+            if constexpr (VEC == 1) {
+#pragma unroll 1
+              for (int oy = lo; oy <= hi; ++oy) {
+                const float w1 = wyj[oy];
+                if (tap && w1 == 0.f) continue;
+                t[0] = fmaf(ld1<DT>(src + static_cast<int64_t>(oy) * g.ow * E, 0), tap ? w1 : 1.f - w1, t[0]);
+              }
+            } else {
+              // four rows per trip: the loads are issued together (the walk is latency-bound otherwise)
+#pragma unroll 1
+              for (int oy = lo; oy <= hi; oy += 4) {
+                uint4 raw[4];
+                float w[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const bool on = oy + u <= hi;
+                  const float w1 = on ? wyj[oy + u] : 0.f;
+                  w[u] = on ? (tap ? w1 : 1.f - w1) : 0.f;
+                  // a zero weight (tap 1 of an output that sits exactly on a source row, or past the range) reads nothing
+                  raw[u] = (on && !(tap && w1 == 0.f)) ? ldg_stream(src + static_cast<int64_t>(oy + u) * g.ow * E) : make_uint4(0, 0, 0, 0);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  float f[VEC];
+                  Elem<DT>::unpack(raw[u], f);
+#pragma unroll
+                  for (int q = 0; q < VEC; ++q) t[q] = fmaf(f[q], w[u], t[q]);
+                }
+              }
+            }
+          }
+          float* dst = T + j * tstride + (r * p.cchunk + c) * p.owp;
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) dst[tcol(v * VEC + q)] = t[q];
+        }
+      }
+      __syncthreads();
+      // ---- horizontal: one thread per source pixel (r, c, x) of the band walks the boxes in order; consecutive lanes own
+      // consecutive columns, so a warp diverges only where a box ends
+      const float inv_w = 1.f / g.W;
+      for (int i = tid; i < rc_n * g.W; i += kBwdThreads) {
+        const int rc = __float2int_rz((i + 0.5f) * inv_w), x = i - rc * g.W;
+        const int r = (rc >= cn) + (rc >= 2 * cn) + (rc >= 3 * cn), c = rc - r * cn;
+        float* out = gfeat + ((b * g.C + c0 + c) * static_cast<int64_t>(g.H) + y0 + r) * g.W + x;
+        float a = g0 ? *out : 0.f;  // what the earlier groups of boxes left (same owner thread every time)
+        const unsigned live = (rowmask >> (r * kBwdMaxGroup)) & ((1u << kBwdMaxGroup) - 1u);
+#pragma unroll
+        for (int j = 0; j < kBwdMaxGroup; ++j) {
+          if (!((live >> j) & 1u) || x > xhi[j] || x < xlo[j]) continue;
+          const short4 xx = xr[j * g.W + x];
+          const float* trow = T + j * tstride + (r * p.cchunk + c) * p.owp;
+          const float* wxj = wx + j * g.ow;
+          float s = 0.f;
+#pragma unroll 1
+          for (int ox = xx.x; ox <= xx.y; ++ox) s = fmaf(trow[tcol(ox)], 1.f - wxj[ox], s);
+#pragma unroll 1
+          for (int ox = xx.z; ox <= xx.w; ++ox) {
+            const float w1 = wxj[ox];
+            if (w1 != 0.f) s = fmaf(trow[tcol(ox)], w1, s);
+          }
+          a += s;
+        }
+        *out = a;
+      }
+      __syncthreads();  // T is rewritten by the next channel pass
+    }
+    g0 += p.KL;
+  } while (g0 < nlist);
+}
+
+// Shared-memory plan of the backward: band height R (<= 4), channels per pass, boxes per table group.
+bool plan_bwd_in(const Geo& g, BwdPlan& p, size_t kBudget) {
+  auto up16 = [](size_t v) { return (v + 15) & ~static_cast<size_t>(15); };
+  p.owp = g.ow + (g.ow >> 4) + 1;
+  const size_t fixed = up16(static_cast<size_t>(g.K) * 4) + up16(static_cast<size_t>(g.K) * 4 + 4);
+  for (int R = 4; R >= 1; R >>= 1) {
+    // per box: tap weights + tap indices of both axes, column ranges, row ranges; plus its slab of T per channel
+    const size_t per_box = 2 * up16(static_cast<size_t>(g.ow) * 4) + 2 * up16(static_cast<size_t>(g.oh) * 4) + up16(static_cast<size_t>(g.W) * 8) +
+                           static_cast<size_t>(R) * 16;
+    const size_t t_chan = static_cast<size_t>(R) * p.owp * 4;  // T of one box and one channel
+    if (fixed + per_box + t_chan > kBudget) continue;
+    // boxes per group: the boxes that meet one band (4 for a 4x4 grid of footprints); more run as further groups
+    int KL = std::min(g.K, kBwdMaxGroup);
+    while (KL > 1 && fixed + KL * (per_box + t_chan) > kBudget) --KL;
+    const size_t room = kBudget - fixed - KL * per_box;
+    const int cchunk = static_cast<int>(std::max<size_t>(1, std::min<size_t>(static_cast<size_t>(g.C), room / (KL * t_chan))));
+    p.R = R;
+    p.cchunk = cchunk;
+    p.KL = KL;
+    size_t o = up16(static_cast<size_t>(KL) * R * cchunk * p.owp * 4);
+    p.off_wx = o; o += static_cast<size_t>(KL) * up16(static_cast<size_t>(g.ow) * 4);
+    p.off_wy = o; o += static_cast<size_t>(KL) * up16(static_cast<size_t>(g.oh) * 4);
+    p.off_ax = o; o += static_cast<size_t>(KL) * up16(static_cast<size_t>(g.ow) * 4);
+    p.off_ay = o; o += static_cast<size_t>(KL) * up16(static_cast<size_t>(g.oh) * 4);
+    p.off_xr = o; o += static_cast<size_t>(KL) * up16(static_cast<size_t>(g.W) * 8);
+    p.off_yr = o; o += static_cast<size_t>(KL) * R * 16;
+    p.off_list = o; o += up16(static_cast<size_t>(g.K) * 4);
+    p.off_flag = o; o += up16(static_cast<size_t>(g.K) * 4 + 4);
+    p.smem = o;
+    return o <= kBudget;
+  }
+  return false;
+}
+
+// 48 KB keeps 4 CTAs per SM (the two phases of different CTAs overlap); very wide maps need more room for their tables
+bool plan_bwd(const Geo& g, BwdPlan& p) {
+  for (size_t budget : {static_cast<size_t>(48) << 10, static_cast<size_t>(96) << 10, static_cast<size_t>(200) << 10})
+    if (plan_bwd_in(g, p, budget)) return true;
+  return false;
 }
 
 int check(const void* a, const float* boxes, const void* o, int64_t B, int C, int H, int W, int K, int oh, int ow, int dtype) {
@@ -416,10 +658,35 @@ extern "C" int msf_crop_resample_bwd(const void* grad_out, int64_t B, int C, int
                                      int oh, int ow, int dtype, float* grad_feat, void* stream) {
   if (int rc = check(grad_out, boxes, grad_feat, B, C, H, W, K, oh, ow, dtype)) return rc;
   if (B == 0) return MSF_OK;
+  MSF_REQUIRE(oh < 32768 && ow < 32768 && H < 32768 && W < 32768, MSF_ERR_UNSUPPORTED, "crop backward: sides must be < 32768");
   const Geo g{B, C, H, W, K, oh, ow};
+  const int vec = 16 / static_cast<int>(dtype_size(dtype));
+  const bool vec_ok = ow % vec == 0 && aligned16(grad_out);
+  BwdPlan p{};
+  MSF_REQUIRE(plan_bwd(g, p), MSF_ERR_UNSUPPORTED, "crop backward: the tap tables of one box (W=%d, oh=%d, ow=%d, K=%d) exceed shared memory", W, oh, ow, K);
+  p.bands = (H + p.R - 1) / p.R;
+  MSF_REQUIRE(B * p.bands < (1ll << 31), MSF_ERR_UNSUPPORTED, "crop backward: B * H too large");
+  // channel ranges per CTA: as few as fill the machine ~8 CTAs deep (the tables are rebuilt per CTA)
+  int64_t splits = (static_cast<int64_t>(kNumSMs) * 8 + B * p.bands - 1) / (B * p.bands);
+  const int64_t max_splits = (C + p.cchunk - 1) / p.cchunk;
+  splits = std::max<int64_t>(1, std::min<int64_t>({splits, max_splits, 65535}));
+  p.csplit = static_cast<int>(((C + splits - 1) / splits + p.cchunk - 1) / p.cchunk) * p.cchunk;
+  const dim3 grid(static_cast<unsigned>(B * p.bands), static_cast<unsigned>((C + p.csplit - 1) / p.csplit));
   const int64_t total = B * K * static_cast<int64_t>(C) * oh * ow;
   ProfScope prof(stream, MSF_K_CROP_BWD, static_cast<double>(total) * dtype_size(dtype) + 4.0 * B * C * H * W + 16.0 * B * K);
-  MSF_DISPATCH_DTYPE(dtype, (crop_bwd_kernel<DT><<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(grad_out, boxes, grad_feat, g, total)));
-  MSF_LAUNCH_OK("crop_bwd_kernel");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // the packed tables assume 4-byte rows of shorts pairs; the transposed accumulator layouts need no alignment beyond 16 B slabs
+  MSF_DISPATCH_DTYPE(dtype, {
+    if (vec_ok) {
+      auto kern = crop_bwd_gather_kernel<DT, Elem<DT>::VEC>;
+      if (p.smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem));
+      kern<<<grid, kBwdThreads, p.smem, st>>>(grad_out, boxes, grad_feat, g, p);
+    } else {
+      auto kern = crop_bwd_gather_kernel<DT, 1>;
+      if (p.smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem));
+      kern<<<grid, kBwdThreads, p.smem, st>>>(grad_out, boxes, grad_feat, g, p);
+    }
+  });
+  MSF_LAUNCH_OK("crop_bwd_gather_kernel");
   return MSF_OK;
 }

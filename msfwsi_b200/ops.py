@@ -608,7 +608,7 @@ class _CropResample(torch.autograd.Function):
         B, Cc, H, W, K, oh, ow, dt = ctx.meta
         (boxes,) = ctx.saved_tensors
         go = _contig(grad_out.to(dt))
-        gfeat = torch.zeros((B, Cc, H, W), dtype=torch.float32, device=go.device)
+        gfeat = torch.empty((B, Cc, H, W), dtype=torch.float32, device=go.device)  # every element is written (gather form)
         L.check(L.lib().msf_crop_resample_bwd(L.ptr(go), B, Cc, H, W, L.ptr(boxes), K, oh, ow, L.dtype_code(dt), L.ptr(gfeat),
                                               L.stream_ptr()), "msf_crop_resample_bwd")
         L.launch_count += 1

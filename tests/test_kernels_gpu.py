@@ -287,6 +287,64 @@ def test_crop_resample_backward_matches_autograd():
     assert torch.allclose(x.grad, x2.grad, rtol=1e-4, atol=1e-5)
 
 
+def _crop_ref_grad(x, boxes, oh, ow, w):
+    """fp64 autograd through the oracle's definition (F.interpolate on each crop; boxes must lie inside the map here)."""
+    x2 = x.detach().double().clone().requires_grad_(True)
+    tot = 0
+    for b in range(boxes.shape[0]):
+        for k in range(boxes.shape[1]):
+            y0, x0, y1, x1 = [int(v) for v in boxes[b, k].tolist()]
+            it = torch.nn.functional.interpolate(x2[b:b + 1, :, y0:y1, x0:x1], size=(oh, ow), mode="bilinear", align_corners=False)
+            tot = tot + (it[0] * w[b, k].double()).sum()
+    tot.backward()
+    return x2.grad
+
+
+@pytest.mark.parametrize("B,Cc,H,W,K,oh,ow", [(2, 5, 24, 20, 6, 12, 16), (1, 3, 16, 16, 3, 40, 7), (3, 8, 32, 32, 16, 8, 8), (1, 2, 9, 4100, 5, 3, 33)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_crop_resample_backward_overlapping_boxes_deterministic(B, Cc, H, W, K, oh, ow, dtype):
+    """Gather-form backward: arbitrary (overlapping, up- and down-sampling) integer boxes against fp64 autograd, and bit-identical
+    run to run.  The last case has source rows wide enough that the tap tables are built a few boxes at a time."""
+    g_ = torch.Generator().manual_seed(B * 100 + K)
+    x = torch.randn(B, Cc, H, W, generator=g_).to(dtype).to(DEV).requires_grad_(True)
+    y0 = torch.randint(0, H - 2, (B, K), generator=g_)
+    x0 = torch.randint(0, W - 2, (B, K), generator=g_)
+    y1 = (y0 + 1 + (torch.rand(B, K, generator=g_) * (H - y0 - 1)).long()).clamp(max=H)
+    x1 = (x0 + 1 + (torch.rand(B, K, generator=g_) * (W - x0 - 1)).long()).clamp(max=W)
+    boxes = torch.stack((y0, x0, y1, x1), dim=2).float().to(DEV)
+    w = torch.randn(B, K, Cc, oh, ow, generator=g_).to(dtype).to(DEV)
+    grads = []
+    for _ in range(2):
+        x.grad = None
+        (ops.crop_resample(x, boxes, (oh, ow)) * w).sum().backward()
+        grads.append(x.grad.clone())
+    assert torch.equal(grads[0], grads[1])
+    ref = _crop_ref_grad(x, boxes.cpu(), oh, ow, w)
+    # source coordinates are fp32 (like ATen's for fp32 tensors): a 4100-wide crop resolves them to ~2e-4 of a pixel, which is
+    # the error of the tap weights there
+    tol = (1e-5 if W < 1000 else 2e-4) if dtype == torch.float32 else 8e-3
+    err = float((grads[0].double() - ref).norm() / ref.norm())
+    assert err <= tol, err
+
+
+def test_crop_resample_backward_is_adjoint_of_forward_with_clamped_boxes():
+    """Fractional boxes partly outside the map (taps clamp to the border): <crop(x), w> == <x, crop^T(w)> in fp32."""
+    B, Cc, H, W, K, oh, ow = 2, 4, 18, 22, 7, 10, 14
+    g_ = torch.Generator().manual_seed(5)
+    x = torch.randn(B, Cc, H, W, generator=g_).to(DEV).requires_grad_(True)
+    c = torch.rand(B, K, 2, generator=g_) * torch.tensor([H, W]) - 2.0
+    sz = torch.rand(B, K, 2, generator=g_) * 12 + 1.5
+    boxes = torch.cat((c, c + sz), dim=2).to(DEV)
+    w = torch.randn(B, K, Cc, oh, ow, generator=g_).to(DEV)
+    out = ops.crop_resample(x, boxes, (oh, ow))
+    (out * w).sum().backward()
+    # linear map: <A x, w> = <x, A^T w>, and A^T w must reproduce <A e, w> for random probes e
+    e = torch.randn(B, Cc, H, W, generator=g_).to(DEV)
+    lhs = (ops.crop_resample(e, boxes, (oh, ow)).double() * w.double()).sum()
+    rhs = (e.double() * x.grad.double()).sum()
+    assert abs(float(lhs - rhs)) <= 1e-5 * max(1.0, abs(float(lhs)))
+
+
 # ------------------------------------------------------------------ E1 EMA
 @pytest.mark.parametrize("tdt,sdt", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16), (torch.bfloat16, torch.bfloat16)])
 def test_ema_multi_tensor(tdt, sdt):
