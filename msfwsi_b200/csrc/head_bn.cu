@@ -47,29 +47,34 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 }
 
 // Symmetric workspace (one per rank, every rank's copy mapped into every process):
-//   flags [2 parities][MSF_HEAD_SYNC_MAX_CTAS][MSF_PEER_MAX_WORLD] uint64 | slots [2 parities][capacity] doubles
+//   flags [2 parities][MSF_HEAD_SYNC_MAX_CTAS][MSF_PEER_MAX_WORLD] uint64 | slots [2 parities][world][capacity] doubles
 constexpr size_t kFlagBytes = 2ull * MSF_HEAD_SYNC_MAX_CTAS * MSF_PEER_MAX_WORLD * sizeof(uint64_t);
 
 struct Sync {
   char* const* peers;  // device array of `world` workspace pointers (peers[rank] is the local one), or null
   int world, rank;
   uint64_t seq;        // 1, 2, 3, ... identical on all ranks (like any collective)
-  size_t capacity;     // doubles per parity
+  size_t capacity;     // doubles per parity and source rank
   uint64_t timeout_ns;
 };
 
 // All-reduce (sum, rank order: bit-identical everywhere) of 4 doubles per thread; slot index = blockIdx.x * kThreads +
-// threadIdx.x.  CTA b of every rank pairs with CTA b of the other ranks only (its own flags), so no grid-wide step is
-// needed.  Two parities suffice: a rank enters exchange k+2 only after every peer published k+1, which a peer does
-// after its kernel of exchange k has finished reading.  The wait is bounded: a lost peer traps (CUDA error), not a hang.
+// threadIdx.x.  PUSH protocol: every thread stores its 4 doubles into slot [parity][my rank] of EVERY rank's workspace
+// (NVLink stores), the CTA then raises its flag everywhere, waits for the peers' flags and sums the slots from LOCAL
+// memory -- one NVLink one-way trip per exchange.  CTA b of every rank pairs with CTA b of the other ranks only (its own
+// flags), so no grid-wide step is needed.  Two parities suffice: a rank enters exchange k+2 only after every peer
+// published k+1, which a peer does after its kernel of exchange k has finished reading.  The wait is bounded: a lost peer
+// traps (CUDA error), not a hang.
 __device__ __forceinline__ void head_exchange(const Sync& sy, double v[4]) {
   if (sy.world <= 1) return;
   const size_t par = sy.seq & 1;
-  const size_t slot_off = kFlagBytes + par * sy.capacity * sizeof(double);
+  const size_t par_off = kFlagBytes + par * sy.world * sy.capacity * sizeof(double);
   const size_t idx = (static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x) * 4;
-  double* mine = reinterpret_cast<double*>(sy.peers[sy.rank] + slot_off) + idx;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) mine[i] = v[i];
+  for (int r = 0; r < sy.world; ++r) {
+    double2* dst = reinterpret_cast<double2*>(reinterpret_cast<double*>(sy.peers[r] + par_off) + static_cast<size_t>(sy.rank) * sy.capacity + idx);
+    dst[0] = make_double2(v[0], v[1]);
+    dst[1] = make_double2(v[2], v[3]);
+  }
   __threadfence_system();
   __syncthreads();
   const size_t flag_base = (par * MSF_HEAD_SYNC_MAX_CTAS + blockIdx.x) * MSF_PEER_MAX_WORLD;
@@ -88,11 +93,11 @@ __device__ __forceinline__ void head_exchange(const Sync& sy, double v[4]) {
     }
   }
   __syncthreads();
+  const double* slots = reinterpret_cast<const double*>(sy.peers[sy.rank] + par_off) + idx;
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
   for (int r = 0; r < sy.world; ++r) {
-    const double* src = reinterpret_cast<const double*>(sy.peers[r] + slot_off) + idx;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) acc[i] += ld_volatile_f64(src + i);
+    for (int i = 0; i < 4; ++i) acc[i] += ld_volatile_f64(slots + static_cast<size_t>(r) * sy.capacity + i);
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) v[i] = acc[i];
@@ -436,7 +441,7 @@ using namespace msf;
 
 extern "C" size_t msf_head_sync_workspace_bytes(int64_t capacity_doubles) {
   if (capacity_doubles <= 0) return 0;
-  return kFlagBytes + 2 * static_cast<size_t>(capacity_doubles) * sizeof(double);
+  return kFlagBytes + 2 * static_cast<size_t>(MSF_PEER_MAX_WORLD) * static_cast<size_t>(capacity_doubles) * sizeof(double);
 }
 
 extern "C" int msf_head_bn_finalize(const msf_head_bn_item* items, int n_items, float eps, float momentum, int training, void* const* peers,

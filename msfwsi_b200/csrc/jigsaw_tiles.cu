@@ -217,6 +217,182 @@ __global__ void __launch_bounds__(256) view_crops_s2d_kernel(const unsigned char
   }
 }
 
+
+// ---- D1b, staged form --------------------------------------------------------------------------------------------
+// CTA = one view x kS2dBlockRows rows of the space-to-depth grid.  The source rows those output rows tap are copied
+// into shared memory with aligned 128-bit loads (every source byte crosses L1 once per CTA, coalesced), then each thread
+// produces whole s2d pixels (2x2 view pixels x 3 channels -> 32 bytes of bf16) from byte reads of shared memory.
+// The resampling is exact integer arithmetic: the source coordinate of output o is N/d with N = max((2o+1)*crop - out, 0),
+// d = 2*out, so tap = N div d and the weight is the integer remainder rx (ry) out of dx (dy); one output value is
+//   ((b00*(dx-rx) + b01*rx)*(dy-ry) + (b10*(dx-rx) + b11*rx)*ry) / (dx*dy)
+// -- six integer multiply-adds on the raw bytes, ONE conversion and one FMA (normalise); no double precision, no per-byte
+// int->float conversions.  Column taps are tabulated once per CTA, row taps once per staged sub-block.
+constexpr int kS2dBlockRows = 8;            // s2d rows per CTA (16 view rows)
+constexpr int kS2dStageBytes = 43 * 1024;   // shared-memory budget of the staged source rows (+ 4 KB column table + row table <= 48 KB)
+constexpr int kS2dMaxCols = 1024;           // padded view columns (ow + 6) the column table holds (4 KB after the stage)
+
+struct AxisTapI {
+  int i0;    // crop-relative first tap (the second is i0 + 1, or i0 again at the crop's last pixel, where rem = 0)
+  int rem;   // weight of the second tap, out of 2*out
+  bool last;
+};
+
+__device__ __forceinline__ AxisTapI axis_tap_int(int o, int out, int crop, float inv_d) {
+  const int d = 2 * out;
+  const int n = max((2 * o + 1) * crop - out, 0);
+  int q = __float2int_rz(__int2float_rz(n) * inv_d);  // estimate of n / d, off by at most one for n < 2^24
+  int rem = n - q * d;
+  if (rem < 0) { --q; rem += d; } else if (rem >= d) { ++q; rem -= d; }
+  AxisTapI t;
+  t.last = q >= crop - 1;
+  t.i0 = min(q, crop - 1);
+  t.rem = t.last ? 0 : rem;
+  return t;
+}
+
+template <int ODT>
+__global__ void __launch_bounds__(256) view_crops_s2d_staged_kernel(const unsigned char* __restrict__ src, int64_t src_bytes,
+                                                                    const msf_view_crop* __restrict__ crops, void* __restrict__ out, CropGeo g, int64_t B,
+                                                                    float a0, float a1, float a2, float b0, float b1, float b2, int* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char stage[];
+  uint32_t* xtab = reinterpret_cast<uint32_t*>(stage + kS2dStageBytes);  // [ow + 6]  byte offset of tap 0 | rx << 16   (0xffffffff: zero padding)
+  __shared__ __align__(16) uint2 ytab[2 * kS2dBlockRows];                           // {stage offset of tap row 0 | tap row 1 << 16, ry}  (ry = 0xffffffff: padding)
+  const int row_blocks = (g.sh + kS2dBlockRows - 1) / kS2dBlockRows;
+  const int64_t view = blockIdx.x / row_blocks;
+  const int rb = static_cast<int>(blockIdx.x % row_blocks);
+  msf_view_crop c = crops[view];
+  if (c.sample < 0 || c.sample >= B || c.y0 < 0 || c.x0 < 0 || c.y1 > g.H || c.x1 > g.W || c.y1 <= c.y0 || c.x1 <= c.x0) {
+    if (status && threadIdx.x == 0) atomicOr(status, 1);
+    c.sample = min(max(c.sample, 0), static_cast<int>(B - 1));
+    c.y0 = min(max(c.y0, 0), g.H - 1); c.x0 = min(max(c.x0, 0), g.W - 1);
+    c.y1 = min(max(c.y1, c.y0 + 1), g.H); c.x1 = min(max(c.x1, c.x0 + 1), g.W);
+  }
+  const int ch = c.y1 - c.y0, cw = c.x1 - c.x0;
+  const int dy = 2 * g.oh, dx = 2 * g.ow;
+  const float inv_dy = 1.f / dy, inv_dx = 1.f / dx;
+  const int64_t pitch = static_cast<int64_t>(g.W) * 3;
+  const unsigned char* base = src + ((static_cast<int64_t>(c.sample) * g.H + c.y0) * g.W + c.x0) * 3;  // crop origin
+  const unsigned char* end = src + src_bytes;
+  const int row_bytes = cw * 3;
+  const int sp = ((row_bytes + 15 + 15) & ~15) + 16;  // staged row pitch: the row + its misalignment + the 3 bytes read past the last pixel
+  const int fit = kS2dStageBytes / sp;                // source rows that fit
+  const float norm = 1.f / (static_cast<float>(dx) * static_cast<float>(dy));
+  const float sc[3] = {a0 * norm, a1 * norm, a2 * norm}, sf[3] = {b0, b1, b2};
+  const int sr_end = min((rb + 1) * kS2dBlockRows, g.sh);
+
+  // column taps of the whole view (padded column xp = x + 3)
+  for (int xp = threadIdx.x; xp < g.ow + 6; xp += 256) {
+    int x = xp - 3;
+    uint32_t e = 0xffffffffu;
+    if (x >= 0 && x < g.ow) {
+      if (c.flip) x = g.ow - 1 - x;
+      const AxisTapI t = axis_tap_int(x, g.ow, cw, inv_dx);
+      e = static_cast<uint32_t>(t.i0 * 3) | (static_cast<uint32_t>(t.rem) << 16);
+    }
+    xtab[xp] = e;
+  }
+
+  // s2d rows per staged sub-block: view rows [ya, yb] tap at most floor((yb - ya) * ch / oh) + 3 source rows
+  const int sub = max(1, min(kS2dBlockRows, ((fit - 3) * g.oh / ch + 1) / 2));
+  const int64_t view_row0 = view * g.sh;
+
+  for (int sr0 = rb * kS2dBlockRows; sr0 < sr_end;) {
+    const int sr1 = min(sr0 + sub, sr_end);
+    const int first = axis_tap_int(min(max(2 * sr0 - 3, 0), g.oh - 1), g.oh, ch, inv_dy).i0;
+    const AxisTapI tl = axis_tap_int(min(max(2 * sr1 - 4, 0), g.oh - 1), g.oh, ch, inv_dy);  // last view row of the sub-block
+    const int nrows = (tl.last ? tl.i0 : tl.i0 + 1) - first + 1;
+    // row taps of the sub-block (padded row yp = y + 3 = 2*sr + dy)
+    if (threadIdx.x < 2 * (sr1 - sr0)) {
+      const int y = 2 * sr0 + static_cast<int>(threadIdx.x) - 3;
+      uint2 e = make_uint2(0u, 0xffffffffu);
+      if (y >= 0 && y < g.oh) {
+        const AxisTapI t = axis_tap_int(y, g.oh, ch, inv_dy);
+        const int r0 = t.i0 - first, r1 = (t.last ? t.i0 : t.i0 + 1) - first;
+        const uint32_t m0 = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(base + t.i0 * pitch) & 15);
+        const uint32_t m1 = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(base + (first + r1) * pitch) & 15);
+        e = make_uint2((r0 * sp + m0) | ((r1 * sp + m1) << 16), static_cast<uint32_t>(t.rem));
+      }
+      ytab[threadIdx.x] = e;
+    }
+    // ---- stage source rows [first, last] of the crop: aligned 16-byte chunks, misalignment kept (byte j of row i sits at i*sp + m_i + j)
+    {
+      const int chunks_max = sp >> 4, total = nrows * chunks_max;
+      const float inv_cm = 1.f / chunks_max;
+      for (int i0 = threadIdx.x; i0 < total; i0 += 4 * 256) {  // four loads in flight per thread
+        uint4 v[4];
+        int dst[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * 256;
+          dst[u] = -1;
+          if (i >= total) continue;
+          const int r = __float2int_rz((i + 0.5f) * inv_cm), k = i - r * chunks_max;
+          const unsigned char* row = base + (first + r) * pitch;
+          const int m = static_cast<int>(reinterpret_cast<uintptr_t>(row) & 15);
+          if (k * 16 >= m + row_bytes) continue;
+          const unsigned char* gp = row - m + k * 16;
+          dst[u] = r * sp + k * 16;
+          if (gp + 16 <= end) {
+            v[u] = ldg_stream(gp);
+          } else {  // the last chunk of the buffer: bytes
+            unsigned char tmp[16];
+            for (int q = 0; q < 16; ++q) tmp[q] = gp + q < end ? __ldg(gp + q) : 0;
+            v[u] = *reinterpret_cast<uint4*>(tmp);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (dst[u] >= 0) *reinterpret_cast<uint4*>(stage + dst[u]) = v[u];
+      }
+    }
+    __syncthreads();
+    // ---- produce the s2d pixels of rows [sr0, sr1)
+    const int items = (sr1 - sr0) * g.sw;
+    const float inv_sw = 1.f / g.sw;
+    for (int p = threadIdx.x; p < items; p += 256) {
+      const int r = __float2int_rz((p + 0.5f) * inv_sw), ox = p - r * g.sw;
+      const uint2 xe = *reinterpret_cast<const uint2*>(xtab + 2 * ox);  // the two columns of this s2d pixel
+      const uint4 ye = *reinterpret_cast<const uint4*>(ytab + 2 * r);   // the two rows
+      float v[3][4];  // [channel][dy*2 + dx]
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t xw = (q & 1) ? xe.y : xe.x;
+        const uint32_t yo = (q >> 1) ? ye.z : ye.x, yr = (q >> 1) ? ye.w : ye.y;
+        if (xw == 0xffffffffu || yr == 0xffffffffu) {  // the stem convolution's zero padding
+          v[0][q] = v[1][q] = v[2][q] = 0.f;
+          continue;
+        }
+        const int rx = static_cast<int>(xw >> 16), cx = dx - rx, ry = static_cast<int>(yr), cy = dy - ry;
+        const unsigned char* s0 = stage + (yo & 0xffffu) + (xw & 0xffffu);
+        const unsigned char* s1 = stage + (yo >> 16) + (xw & 0xffffu);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          // the second column tap is read at +3 even at the crop's last pixel, where rx = 0 cancels whatever byte sits there
+          const int top = static_cast<int>(s0[k]) * cx + static_cast<int>(s0[k + 3]) * rx;
+          const int bot = static_cast<int>(s1[k]) * cx + static_cast<int>(s1[k + 3]) * rx;
+          v[k][q] = fmaf(__int2float_rn(top * cy + bot * ry), sc[k], sf[k]);
+        }
+      }
+      const int64_t e = static_cast<int64_t>(view_row0 + sr0 + r) * g.sw + ox;
+      if constexpr (ODT == MSF_F32) {
+        float4* dst = reinterpret_cast<float4*>(static_cast<float*>(out) + e * 16);
+        dst[0] = make_float4(v[0][0], v[0][1], v[0][2], v[0][3]);
+        dst[1] = make_float4(v[1][0], v[1][1], v[1][2], v[1][3]);
+        dst[2] = make_float4(v[2][0], v[2][1], v[2][2], v[2][3]);
+        dst[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        float f0[8] = {v[0][0], v[0][1], v[0][2], v[0][3], v[1][0], v[1][1], v[1][2], v[1][3]};
+        float f1[8] = {v[2][0], v[2][1], v[2][2], v[2][3], 0.f, 0.f, 0.f, 0.f};
+        char* dst = static_cast<char*>(out) + e * 32;
+        stg_stream(dst, Elem<ODT>::pack(f0));
+        stg_stream(dst + 16, Elem<ODT>::pack(f1));
+      }
+    }
+    sr0 = sr1;
+    if (sr0 < sr_end) __syncthreads();  // the stage and the row table are rewritten
+  }
+}
+
 }  // namespace
 }  // namespace msf
 
@@ -228,14 +404,30 @@ extern "C" int msf_view_crops_s2d(const uint8_t* src, int64_t B, int H, int W, c
   if (n_views == 0) return MSF_OK;
   MSF_REQUIRE(src && crops && out && aligned16(out) && n_views > 0, MSF_ERR_INVALID, "NULL or misaligned pointer");
   const CropGeo g{H, W, oh, ow, (oh + 6) / 2, (ow + 6) / 2};
-  const int64_t blocks = n_views * ((g.sh + kS2dRowsPerCta - 1) / kS2dRowsPerCta);
-  MSF_REQUIRE(blocks < (int64_t{1} << 31), MSF_ERR_UNSUPPORTED, "%lld CTAs must be < 2^31", static_cast<long long>(blocks));
   float a[3], b[3];
   for (int c = 0; c < 3; ++c) { a[c] = 1.f / (255.f * std3[c]); b[c] = -mean3[c] / std3[c]; }
   // algorithmic bytes: ~0.75 of each crop's maximal source area is not known here; count the output (the dominant term) + 3 source bytes
   // per output pixel (a 1:1 resample reads what it writes; the context views read ~4.6x that, 6 % of the launch)
   ProfScope prof(stream, MSF_K_JIGSAW_TILES, static_cast<double>(n_views) * (static_cast<double>(g.sh) * g.sw * 16 * dtype_size(out_dtype) + 3.0 * oh * ow));
-  MSF_DISPATCH_DTYPE(out_dtype, (view_crops_s2d_kernel<DT><<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // staged form: the source rows of ONE s2d row of the largest possible crop (the whole tile) must fit the stage, and the exact integer
+  // coordinates need (2*out + 1) * crop < 2^24
+  const int64_t worst_rows = (2 * static_cast<int64_t>(H) + oh - 1) / oh + 3;
+  const int64_t worst_pitch = ((static_cast<int64_t>(W) * 3 + 30) & ~static_cast<int64_t>(15)) + 16;
+  const bool staged = aligned16(src) && worst_rows * worst_pitch <= kS2dStageBytes && (2 * static_cast<int64_t>(oh) + 1) * H < (1 << 24) &&
+                      (2 * static_cast<int64_t>(ow) + 1) * W < (1 << 24) && ow + 6 <= kS2dMaxCols && static_cast<int64_t>(W) * 3 + 3 < 65536 &&
+                      255ll * 4 * oh * ow < (1ll << 31);  // the integer numerator of one output value
+  if (staged) {
+    const int64_t blocks = n_views * ((g.sh + kS2dBlockRows - 1) / kS2dBlockRows);
+    MSF_REQUIRE(blocks < (int64_t{1} << 31), MSF_ERR_UNSUPPORTED, "%lld CTAs must be < 2^31", static_cast<long long>(blocks));
+    MSF_DISPATCH_DTYPE(out_dtype, (view_crops_s2d_staged_kernel<DT><<<static_cast<unsigned>(blocks), 256, kS2dStageBytes + kS2dMaxCols * 4, st>>>(
+                                      src, B * static_cast<int64_t>(H) * W * 3, crops, out, g, B, a[0], a[1], a[2], b[0], b[1], b[2], status_flag)));
+    MSF_LAUNCH_OK("view_crops_s2d_staged_kernel");
+    return MSF_OK;
+  }
+  const int64_t blocks = n_views * ((g.sh + kS2dRowsPerCta - 1) / kS2dRowsPerCta);
+  MSF_REQUIRE(blocks < (int64_t{1} << 31), MSF_ERR_UNSUPPORTED, "%lld CTAs must be < 2^31", static_cast<long long>(blocks));
+  MSF_DISPATCH_DTYPE(out_dtype, (view_crops_s2d_kernel<DT><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
                                     src, B * static_cast<int64_t>(H) * W * 3, crops, out, g, B, a[0], a[1], a[2], b[0], b[1], b[2], status_flag)));
   MSF_LAUNCH_OK("view_crops_s2d_kernel");
   return MSF_OK;

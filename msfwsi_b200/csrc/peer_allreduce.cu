@@ -4,13 +4,15 @@
 // (SyncBatchNorm, tools/ssl_train.py:160): 352 tiny collectives per step, each a ~30 us NCCL ring kernel plus two
 // cross-stream hops.  Here each rank owns a SYMMETRIC workspace (same layout on every GPU, every rank's copy mapped into
 // every process: torch.distributed._symmetric_memory) and one single-CTA kernel does the whole exchange:
-//   1. copy the local vector into my workspace slot (two slots, alternating with the call sequence number),
-//   2. __threadfence_system(), then store `seq` into flags[my_rank] of EVERY rank's workspace (NVLink stores),
+//   1. PUSH the local vector into slot [parity][my rank] of EVERY rank's workspace (NVLink stores: fire and forget),
+//   2. __threadfence_system(), then store `seq` into flags[my_rank] of every rank's workspace,
 //   3. spin (bounded by the caller's timeout, ld.acquire.sys) until my flags[r] >= seq for all r,
-//   4. sum the peers' slots in rank order (NVLink loads) -- fixed order, so all ranks get bit-identical results.
-// Two slots suffice: a rank enters call k+2 only after passing the wait of call k+1, which needs every peer's flag
+//   4. sum the slots of all ranks from LOCAL memory in rank order -- fixed order, so all ranks get bit-identical results.
+// One NVLink one-way trip (data, then flag) per exchange; the first version pulled the peers' slots after the flag, i.e. a
+// second round trip per peer, issued one after the other.
+// Two parities suffice: a rank enters call k+2 only after passing the wait of call k+1, which needs every peer's flag
 // k+1, which a peer publishes only after it has finished reading the slots of call k.
-// Workspace layout: flags[MSF_PEER_MAX_WORLD] (uint64) | pad to 256 B | slot 0 (capacity doubles) | slot 1.
+// Workspace layout: flags[MSF_PEER_MAX_WORLD] (uint64) | pad to 256 B | slots [2 parities][MSF_PEER_MAX_WORLD][capacity] doubles.
 #include "common.cuh"
 
 namespace msf {
@@ -41,9 +43,11 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 __global__ void __launch_bounds__(kThreads) peer_allreduce_kernel(double* __restrict__ vec, int n, char* const* __restrict__ peers, int world,
                                                                   int rank, uint64_t seq, size_t capacity, uint64_t timeout_ns) {
   char* mine = peers[rank];
-  const size_t slot_off = kFlagBytes + (seq & 1) * capacity * sizeof(double);
-  double* my_slot = reinterpret_cast<double*>(mine + slot_off);
-  for (int i = threadIdx.x; i < n; i += kThreads) my_slot[i] = vec[i];
+  const size_t par_off = kFlagBytes + (seq & 1) * MSF_PEER_MAX_WORLD * capacity * sizeof(double);
+  for (int i = threadIdx.x; i < n; i += kThreads) {
+    const double v = vec[i];
+    for (int r = 0; r < world; ++r) reinterpret_cast<double*>(peers[r] + par_off)[static_cast<size_t>(rank) * capacity + i] = v;
+  }
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x < world)  // publish: my flag in every rank's workspace
@@ -61,9 +65,17 @@ __global__ void __launch_bounds__(kThreads) peer_allreduce_kernel(double* __rest
     }
   }
   __syncthreads();
+  const double* slots = reinterpret_cast<const double*>(mine + par_off);
   for (int i = threadIdx.x; i < n; i += kThreads) {
     double acc = 0.0;
-    for (int r = 0; r < world; ++r) acc += ld_volatile_f64(reinterpret_cast<const double*>(peers[r] + slot_off) + i);
+    for (int r0 = 0; r0 < world; r0 += 8) {  // eight loads in flight, added in rank order
+      double t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t[u] = r0 + u < world ? ld_volatile_f64(slots + static_cast<size_t>(r0 + u) * capacity + i) : 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (r0 + u < world) acc += t[u];
+    }
     vec[i] = acc;
   }
 }
@@ -75,7 +87,7 @@ using namespace msf;
 
 extern "C" size_t msf_peer_workspace_bytes(int64_t capacity_doubles) {
   if (capacity_doubles <= 0) return 0;
-  return kFlagBytes + 2 * static_cast<size_t>(capacity_doubles) * sizeof(double);
+  return kFlagBytes + 2 * static_cast<size_t>(MSF_PEER_MAX_WORLD) * static_cast<size_t>(capacity_doubles) * sizeof(double);
 }
 
 extern "C" int msf_peer_allreduce_f64(double* vec, int n, void* const* peers, int world, int rank, uint64_t seq, int64_t capacity_doubles,

@@ -42,7 +42,7 @@ class HeadSync:
     ``msf_head_bn_bwd_finalize``: every rank's copy is mapped into every process, and the kernels exchange the batch-norm
     sums of a whole depth with NVLink loads / stores -- no NCCL launch.  Creating one is a collective."""
 
-    CAPACITY = 1 << 17  # doubles per parity: 4 per (head, column) of a depth = 42240 for the reference widths
+    CAPACITY = 1 << 16  # doubles per parity and source rank: 4 per (head, column) of a depth = 42240 for the reference widths
     TIMEOUT_MS = int(float(os.environ.get("MSFWSI_PEER_TIMEOUT_S", "120")) * 1000)
     _cache = {}
 

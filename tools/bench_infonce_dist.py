@@ -1,7 +1,7 @@
 """c5 microbench at G GPUs (BASELINE.json configs[4]): fused InfoNCE fwd+bwd with the queries sharded N/G per rank and
 the keys global (NCCL all-gather of the normalised bf16 keys, rank-major, positives at rank*N/G + i -- SURVEY 8e).
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 tools/bench_infonce_dist.py [--n 65536] [--d 128 256]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 tools/bench_infonce_dist.py [--rows 65536] [--dims 128 256]
 
 One timed iteration per rank = row-normalise local q and k, all-gather the keys, forward (loss + O partials), backward
 (grad_q).  CUDA events on the launching stream, L2 flushed between iterations, MAX over ranks; whole-job TFLOP/s =
@@ -22,8 +22,8 @@ from msfwsi_b200 import ops  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, nargs="+", default=[16384, 65536])
-    ap.add_argument("--d", type=int, nargs="+", default=[128, 256])
+    ap.add_argument("--rows", dest="n", type=int, nargs="+", default=[16384, 65536])
+    ap.add_argument("--dims", dest="d", type=int, nargs="+", default=[128, 256])
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--tau", type=float, default=0.07)
     ap.add_argument("--out", default=None)
