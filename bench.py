@@ -607,19 +607,23 @@ def infonce_microbench(torch, ops, _lib, dev, peaks, traffic):
             L.check(L.lib().msf_nce_grouped_bwd(pr, 1, L.MSF_BF16, 0.07, 1e-8, gout.data_ptr(), ws.data_ptr(), wsb, st), "bwd")
 
         out = {"N": n, "D": d, "flops": 4.0 * n * n * d}
-        for name, fn in (("fwd", fwd), ("fwd_bwd", chain)):
-            for _ in range(3):
-                fn()
-            ts = []
-            for _ in range(7):
+        # the two measurements alternate, so both see the same clock / power state (a dense-MMA kernel repeated for a second
+        # drops from the burst to the sustained clock: timing one after the other would compare different GPUs)
+        for _ in range(3):
+            fwd()
+            chain()
+        ts = {"fwd": [], "fwd_bwd": []}
+        for _ in range(7):
+            for name, fn in (("fwd", fwd), ("fwd_bwd", chain)):
                 flush.zero_()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
                 fn()
                 b.record()
                 torch.cuda.synchronize()
-                ts.append(a.elapsed_time(b))
-            out[f"ms_{name}"] = statistics.median(ts)
+                ts[name].append(a.elapsed_time(b))
+        for name in ts:
+            out[f"ms_{name}"] = statistics.median(ts[name])
             out[f"tflops_{name}"] = out["flops"] / out[f"ms_{name}"] / 1e9
             out[f"frac_{name}"] = out[f"tflops_{name}"] / peak
         rows.append(out)
@@ -638,7 +642,7 @@ def infonce_microbench(torch, ops, _lib, dev, peaks, traffic):
                                                     f"{t.get('algorithmic_bytes_per_launch'):.4g} algorithmic B (ratio {t.get('ratio_to_algorithmic'):.3f}); "
                                                     f"{t.get('source')}"),
             "timing": "torch.cuda.Event pair on the current stream = the stream the C-ABI call launches on; median of 7 after 3 warm-ups, "
-                      "256 MB L2 flush between iterations"}
+                      "256 MB L2 flush between iterations; forward-only and chain iterations alternate (same clock state)"}
     return {"rows": rows, "roofline": roof}
 
 

@@ -449,6 +449,11 @@ __global__ void __launch_bounds__(256) nce_grouped_sum_kernel(const float* __res
   if (threadIdx.x == 0) *out = static_cast<float>(sm[0]);
 }
 
+__device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
+  const uint4 r = ldg_stream(p);
+  return make_float4(__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z), __uint_as_float(r.w));
+}
+
 // dq = g * coef/(nq tau) * J^T (O/sum - k_pos),  J = d(q/||q||)/dq:  dq = (dq_hat - q_hat (q_hat . dq_hat)) / ||q||
 template <int DT>
 __global__ void __launch_bounds__(256) nce_grouped_bwd_kernel(const __grid_constant__ PairParams P, const float* __restrict__ grad_out) {
@@ -469,31 +474,68 @@ __global__ void __launch_bounds__(256) nce_grouped_bwd_kernel(const __grid_const
   const float inn = valid ? q.row_stat[2 * row + 1] : 0.f;
   const char* qrow = static_cast<const char*>(q.q) + row * row_bytes;
   const char* krow = static_cast<const char*>(q.k_local) + row * row_bytes;
+  // d[i] = gs * (O_i / sum - k_pos,i): the O partials of the key splits are summed in fixed order, read as 128-bit vectors
+  auto load_d = [&](uint32_t c, float* fq, float* d) {
+    float fk[V];
+    Elem<DT>::unpack(ldg_keep(qrow + static_cast<size_t>(c) * 16), fq);
+    Elem<DT>::unpack(ldg_keep(krow + static_cast<size_t>(c) * 16), fk);
+    float o[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) o[i] = 0.f;
+    for (int s = 0; s < q.splits; ++s) {
+      const float4* src = reinterpret_cast<const float4*>(q.o_part + (static_cast<int64_t>(s) * q.nq_pad + row) * q.D + c * V);
+#pragma unroll
+      for (int i = 0; i < V; i += 4) {
+        const float4 v = ldg_stream_f4(src + i / 4);
+        o[i] += v.x; o[i + 1] += v.y; o[i + 2] += v.z; o[i + 3] += v.w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) d[i] = gs * (o[i] * inv_sum - fk[i]);
+  };
+  constexpr int kKeep = 4;  // chunks per lane kept in registers between the two passes (every flash width: D <= 256)
+  if (cpr <= lanes * kKeep) {
+    float fq[kKeep][V], d[kKeep][V];
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < kKeep; ++j) {
+      const uint32_t c = lane + j * lanes;
+      if (valid && c < cpr) {
+        load_d(c, fq[j], d[j]);
+#pragma unroll
+        for (int i = 0; i < V; ++i) t = fmaf(fq[j][i] * inn, d[j][i], t);
+      }
+    }
+    t = group_sum(t, lanes);
+    if (!valid) return;
+#pragma unroll
+    for (int j = 0; j < kKeep; ++j) {
+      const uint32_t c = lane + j * lanes;
+      if (c < cpr) {
+        float g[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) g[i] = (d[j][i] - fq[j][i] * inn * t) * inn;
+        stg_stream(static_cast<char*>(q.grad_q) + row * row_bytes + static_cast<size_t>(c) * 16, Elem<DT>::pack(g));
+      }
+    }
+    return;
+  }
+  // wide rows (the fuser widths): two passes over the row, the second one served by L2
   float t = 0.f;
   if (valid)
     for (uint32_t c = lane; c < cpr; c += lanes) {
-      float fq[V], fk[V];
-      Elem<DT>::unpack(ldg_keep(qrow + static_cast<size_t>(c) * 16), fq);
-      Elem<DT>::unpack(ldg_keep(krow + static_cast<size_t>(c) * 16), fk);
+      float fq[V], d[V];
+      load_d(c, fq, d);
 #pragma unroll
-      for (int i = 0; i < V; ++i) {
-        float o = 0.f;
-        for (int s = 0; s < q.splits; ++s) o += __ldg(q.o_part + (static_cast<int64_t>(s) * q.nq_pad + row) * q.D + c * V + i);
-        t = fmaf(fq[i] * inn, gs * (o * inv_sum - fk[i]), t);
-      }
+      for (int i = 0; i < V; ++i) t = fmaf(fq[i] * inn, d[i], t);
     }
   t = group_sum(t, lanes);
   if (!valid) return;
   for (uint32_t c = lane; c < cpr; c += lanes) {
-    float fq[V], fk[V], g[V];
-    Elem<DT>::unpack(ldg_keep(qrow + static_cast<size_t>(c) * 16), fq);
-    Elem<DT>::unpack(ldg_keep(krow + static_cast<size_t>(c) * 16), fk);
+    float fq[V], d[V], g[V];
+    load_d(c, fq, d);
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      float o = 0.f;
-      for (int s = 0; s < q.splits; ++s) o += __ldg(q.o_part + (static_cast<int64_t>(s) * q.nq_pad + row) * q.D + c * V + i);
-      g[i] = (gs * (o * inv_sum - fk[i]) - fq[i] * inn * t) * inn;
-    }
+    for (int i = 0; i < V; ++i) g[i] = (d[i] - fq[i] * inn * t) * inn;
     stg_stream(static_cast<char*>(q.grad_q) + row * row_bytes + static_cast<size_t>(c) * 16, Elem<DT>::pack(g));
   }
 }
