@@ -55,7 +55,7 @@ struct alignas(64) DevProblem {
   const float* a_scale;     // [K] or null (no prologue)
   const float* a_shift;     // [K]
   const float* row_scale;   // EXP epilogue: per-row factor of the exponent (1 / ||q_i||) or null
-  float* ws;                // split-K partials [tiles][k_splits][128][bn] fp32
+  float* ws;                // split-K partials [tiles][k_splits][bn/4][128 rows][4] fp32 (a warp's 128-bit accesses are contiguous)
   int32_t* counters;        // [tiles], zero between launches (self-cleaning)
   int64_t ldc;
   int32_t M, N, K, bn, tiles_m, tiles_n, k_splits, kb_per_split, num_kb, unit_start, unit_end;
@@ -259,6 +259,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
       const DevProblem& q = P.p[w.p];
       if (q.a_scale == nullptr) { it += static_cast<uint32_t>(w.kb1 - w.kb0); continue; }
       const bool relu = (q.flags & F_A_RELU) != 0;
+      const float* const a_scale = q.a_scale;
+      const float* const a_shift = q.a_shift;
+      const int kdim = q.K;
       for (int kb = w.kb0; kb < w.kb1; ++kb, ++it) {
         const int s = it % kStages;
         mbar_wait(pfull + s, (ppar >> s) & 1);
@@ -267,11 +270,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int k0 = kb * GBK + j * 8;
-          if (k0 >= q.K) break;  // K is a multiple of 8: whole chunks; columns past K stay zero (TMA fill)
+          if (k0 >= kdim) break;  // K is a multiple of 8: whole chunks; columns past K stay zero (TMA fill)
           uint4* cp = reinterpret_cast<uint4*>(rowp + ((j ^ (r & 7)) << 4));
           const uint4 v = *cp;
-          const float4 s0 = __ldg(reinterpret_cast<const float4*>(q.a_scale + k0)), s1 = __ldg(reinterpret_cast<const float4*>(q.a_scale + k0 + 4));
-          const float4 h0 = __ldg(reinterpret_cast<const float4*>(q.a_shift + k0)), h1 = __ldg(reinterpret_cast<const float4*>(q.a_shift + k0 + 4));
+          const float4 s0 = __ldg(reinterpret_cast<const float4*>(a_scale + k0)), s1 = __ldg(reinterpret_cast<const float4*>(a_scale + k0 + 4));
+          const float4 h0 = __ldg(reinterpret_cast<const float4*>(a_shift + k0)), h1 = __ldg(reinterpret_cast<const float4*>(a_shift + k0 + 4));
           const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w}, sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
           const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
           uint32_t o[4];
@@ -311,14 +314,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
       bool from_ws = false;
       if (q.k_splits > 1) {
         // ---- split-K: park the fp32 partial; the last CTA to arrive for this tile reduces all of them in split order ----
-        float* part = q.ws + ((static_cast<size_t>(tile_idx) * q.k_splits + w.ks) * BM + row_in_tile) * q.bn;
+        // layout [column quad][row][4]: the 32 rows of a warp write 512 contiguous bytes per store instruction
+        float* part = q.ws + (static_cast<size_t>(tile_idx) * q.k_splits + w.ks) * BM * q.bn + row_in_tile * 4;
 #pragma unroll 1
         for (int c = 0; c < n_chunks; ++c) {
           uint32_t v[32];
           tmem_ld32(lane_base + buf * 256 + c * 32, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) __stcg(reinterpret_cast<uint4*>(part + c * 32 + i), make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+          for (int i = 0; i < 32; i += 4) __stcg(reinterpret_cast<uint4*>(part + (c * 8 + (i >> 2)) * (BM * 4)), make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]));
         }
         tc_fence_before();
         mbar_arrive(acc_empty + buf);  // TMEM buffer is free again
@@ -353,11 +357,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) x[i] = 0.f;
-          for (int s = 0; s < q.k_splits; ++s) {  // fixed order: deterministic
-            const float* part = q.ws + ((static_cast<size_t>(tile_idx) * q.k_splits + s) * BM + row_in_tile) * q.bn + c * 32;
+          const int ks_n = q.k_splits, bn_w = q.bn;
+          const float* const ws0 = q.ws;
+          for (int s = 0; s < ks_n; ++s) {  // fixed order: deterministic
+            const float* part = ws0 + (static_cast<size_t>(tile_idx) * ks_n + s) * BM * bn_w + row_in_tile * 4 + c * 8 * (BM * 4);
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              const float4 t = __ldcg(reinterpret_cast<const float4*>(part + i));
+              const float4 t = __ldcg(reinterpret_cast<const float4*>(part + (i >> 2) * (BM * 4)));
               x[i] += t.x; x[i + 1] += t.y; x[i + 2] += t.z; x[i + 3] += t.w;
             }
           }
@@ -365,15 +371,24 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
         const int col = n0 + c * 32;  // first global column of this chunk
         // ---- alpha, bias (or the InfoNCE exponential), rounding to the output dtype ----
         if (q.exp_a != 0.f) {
-          const float ea = q.exp_a * (q.row_scale ? (row_ok ? __ldg(q.row_scale + row) : 0.f) : 1.f);
+          const float exp_a = q.exp_a;
+          const float ea = exp_a * (q.row_scale ? (row_ok ? __ldg(q.row_scale + row) : 0.f) : 1.f);
+          const int ncol = q.N - col;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) x[i] = col + i < q.N ? ex2_approx(fmaf(x[i], ea, -q.exp_a)) : 0.f;  // |cos| <= 1: never overflows
+          for (int i = 0; i < 32; ++i) x[i] = i < ncol ? ex2_approx(fmaf(x[i], ea, -exp_a)) : 0.f;  // |cos| <= 1: never overflows
         } else {
+          // q.* are indexed loads from the kernel-parameter space: read once per chunk, not once per element (with the
+          // per-element form the compiler kept 32 predicates + addresses live: 167 registers and an 11 us epilogue per
+          // 128x256 tile -- 3.5x the tile's MMA time at K = 512; now 133 registers and the epilogue hides behind the MMAs)
+          const float alpha = q.alpha;
+          const float* const bias = q.bias;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float t = x[i] * q.alpha;
-            if (q.bias && col + i < q.N) t += __ldg(q.bias + col + i);
-            x[i] = t;
+          for (int i = 0; i < 32; ++i) x[i] *= alpha;
+          if (bias) {
+            const int ncol = q.N - col;  // valid columns of this chunk
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < ncol) x[i] += __ldg(bias + col + i);
           }
         }
         uint32_t u16[16];
