@@ -161,6 +161,25 @@ int msf_infonce_bwd(const void* q_hat, const void* k_hat, const float* q_inv_nor
                     int dim, int64_t pos_offset, float tau, int precision, const float* grad_out, float scale,
                     const void* workspace, size_t workspace_bytes, void* grad_q, int grad_dtype, void* stream);
 
+/* Key gradient -- the variant of BASELINE.json:north_star (4) in which the keys are NOT detached (the reference detaches
+ * every key, backbone.py:188-191, so MSFWSI itself never calls this; ops.infonce_loss(..., detach_keys=False) does):
+ *   dk_hat_j = *grad_out * scale / tau * ( sum_{i local} softmax_ij q_hat_i  -  q_hat_{i : pos(i) = j} ).
+ * Step 5  msf_infonce_dk: dk_out (n_keys, dim) fp32 = *grad_out * scale / tau * sum_{i local} softmax_ij q_hat_i for EVERY
+ *         global key j -- the flash pass with the roles swapped (rows = keys, columns = this rank's queries; 1/sum_i from
+ *         the forward workspace becomes a per-column exponent term), 4 * nq * n_keys * dim FLOP.  fwd_workspace is the
+ *         workspace msf_infonce_fwd filled for the same (q_hat, k_hat).
+ * Step 6  (multi-GPU) the caller reduce-scatters dk_out over the ranks (NCCL, rank-major like the all-gather): every rank
+ *         receives the summed rows of its own keys.
+ * Step 7  msf_infonce_dk_finish: subtracts the positive term (local: key j's query is row j of this rank's q_hat, j < nq)
+ *         and applies the normalise Jacobian: grad_z_j = (d - k_hat_j (k_hat_j . d)) * k_inv_norm[j], in grad_dtype. */
+size_t msf_infonce_dk_workspace_bytes(int64_t nq, int64_t n_keys, int dim, int precision);
+int msf_infonce_dk(const void* q_hat, const void* k_hat, int64_t nq, int64_t n_keys, int dim, int64_t pos_offset, float tau,
+                   int precision, const float* grad_out, float scale, const void* fwd_workspace, size_t fwd_workspace_bytes,
+                   float* dk_out, void* workspace, size_t workspace_bytes, void* stream);
+int msf_infonce_dk_finish(const float* dk_local, const void* q_hat, const void* k_hat_local, const float* k_inv_norm,
+                          int64_t rows, int64_t nq, int dim, float tau, int precision, const float* grad_out, float scale,
+                          void* grad_z, int grad_dtype, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * L1 (infonce mode, grouped)  the InfoNCE terms of ALL (branch, level, direction) pairs of the loss block in a handful of
  * launches: one flash launch per width class D in {64, 128, 256}, two grouped GEMM launches per chunk of rank blocks for
@@ -552,7 +571,7 @@ typedef enum {
   MSF_K_NCE_SIMT, MSF_K_NCE_BWD, MSF_K_GEMM, MSF_K_CROP_FWD, MSF_K_CROP_BWD, MSF_K_EMA, MSF_K_BN_STATS, MSF_K_BN_APPLY,
   MSF_K_BN_APPLY_RES, MSF_K_BN_BWD_REDUCE, MSF_K_BN_BWD_ELEMT, MSF_K_BN_APPLY_POOL, MSF_K_BN_POOL_BWD_ELEMT,
   MSF_K_ADAM, MSF_K_GRAD_CHECK, MSF_K_STEM_S2D, MSF_K_PEER_ALLREDUCE, MSF_K_JIGSAW_TILES, MSF_K_GEMM_GROUPED, MSF_K_HEAD_BN_FINALIZE,
-  MSF_K_HEAD_BN_ELEMWISE, MSF_K_GEMM_F32, MSF_K_COUNT
+  MSF_K_HEAD_BN_ELEMWISE, MSF_K_GEMM_F32, MSF_K_NCE_DK, MSF_K_COUNT
 } msf_kernel_id;
 typedef struct {
   int32_t kernel;   /* msf_kernel_id */

@@ -47,7 +47,7 @@ class ProfRecord(C.Structure):
     _fields_ = [("kernel", C.c_int32), ("launches", C.c_int32), ("work", C.c_double), ("ms", C.c_double)]
 
 
-MSF_K_COUNT = 29
+MSF_K_COUNT = 30
 MSF_NCE_MAX_PAIRS = 32
 
 
@@ -127,6 +127,11 @@ _SIGS = {
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
     "msf_infonce_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.c_float,
                                   C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]),
+    "msf_infonce_dk_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int, C.c_int]),
+    "msf_infonce_dk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.c_float, C.c_int, C.c_void_p, C.c_float,
+                                 C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "msf_infonce_dk_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_float, C.c_int,
+                                        C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_void_p]),
     "msf_gemm_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                 C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
     "msf_gemm_grouped_workspace_bytes": (C.c_size_t, [C.POINTER(GemmProblem), C.c_int]),

@@ -50,9 +50,9 @@ const char* const kKernelNames[MSF_K_COUNT] = {
     "infonce_twopass_fwd", "infonce_simt_fwd", "infonce_bwd", "gemm_bf16", "crop_resample_fwd", "crop_resample_bwd", "ema_multi",
     "bn2d_stats", "bn2d_apply", "bn2d_apply_res", "bn2d_bwd_reduce", "bn2d_bwd_elemt", "bn2d_apply_pool", "bn2d_pool_bwd_elemt",
     "adam_multi", "grad_check_multi", "stem_s2d", "peer_allreduce_f64", "jigsaw_tiles", "gemm_grouped", "head_bn_finalize",
-    "head_bn_elementwise", "gemm_grouped_f32"};
+    "head_bn_elementwise", "gemm_grouped_f32", "infonce_key_grad"};
 const char kKernelBound[MSF_K_COUNT] = {'h', 'h', 'h', 'h', 'h', 't', 't', 'f', 'h', 't', 'h', 'h', 'h',
-                                        'h', 'h', 'h', 'h', 'h', 'h', 'h', 'h', 'h', 'h', 'l', 'h', 't', 'l', 'h', 'f'};
+                                        'h', 'h', 'h', 'h', 'h', 'h', 'h', 'h', 'h', 'h', 'l', 'h', 't', 'l', 'h', 'f', 't'};
 }  // namespace
 
 ProfScope::ProfScope(void* stream, int kernel, double work) : slot_(-1), stream_(stream) {

@@ -7,6 +7,7 @@
 // taps of neighbouring outputs overlap, so input traffic is the footprint once (L1/L2 hits after).
 // Algorithmic bytes: B*C*(union of footprints)*e read + B*K*C*oh*ow*e written + 16 B per box.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -238,8 +239,8 @@ __global__ void __launch_bounds__(kFastThreads) crop_fwd_fast_kernel(const void*
 // memory traffic on the row path, no warp synchronisation; the row taps (shared by the whole box) sit in shared memory.
 // Weights equal to zero short-circuit, so an integer box of the output size is a bit-exact copy (and takes a pure
 // 128-bit copy loop when the source is 16-byte aligned).
-template <int DT>
-__global__ void __launch_bounds__(256) crop_fwd_strip_kernel(const void* __restrict__ feat, const float* __restrict__ boxes,
+template <int DT, int MINB>
+__global__ void __launch_bounds__(256, MINB) crop_fwd_strip_kernel(const void* __restrict__ feat, const float* __restrict__ boxes,
                                                              void* __restrict__ out, Geo g, int strips) {
   constexpr int VEC = Elem<DT>::VEC;
   constexpr int ES = 16 / VEC;
@@ -254,8 +255,26 @@ __global__ void __launch_bounds__(256) crop_fwd_strip_kernel(const void* __restr
   const int sx = static_cast<int>(threadIdx.x) % strips;
   const int64_t b = bk / g.K;
   const float4 bx = __ldg(reinterpret_cast<const float4*>(boxes) + bk);  // y0,x0,y1,x1
+  int* seg = reinterpret_cast<int*>(y_w + g.oh);  // [nseg + 1] first output row of every segment, then oh
+  __shared__ int nseg_s;
   for (int o = threadIdx.x; o < g.oh; o += 256) axis_taps(bx.x, bx.z - bx.x, o, g.oh, g.H, y_i0[o], y_i1[o], y_w[o]);
   __syncthreads();
+  if (threadIdx.x < 32) {  // ordered compaction of the segment starts by one warp
+    int count = 0;
+    for (int base = 0; base < g.oh; base += 32) {
+      const int o = base + static_cast<int>(threadIdx.x);
+      const bool st = o < g.oh && (o == 0 || y_i0[o] != y_i0[o - 1] || y_i1[o] != y_i1[o - 1] || (y_w[o] != 0.f) != (y_w[o - 1] != 0.f));
+      const unsigned m = __ballot_sync(0xffffffffu, st);
+      if (st) seg[count + __popc(m & ((1u << threadIdx.x) - 1u))] = o;
+      count += __popc(m);
+    }
+    if (threadIdx.x == 0) {
+      seg[count] = g.oh;
+      nseg_s = count;
+    }
+  }
+  __syncthreads();
+  const int nseg = nseg_s;
   if (c >= g.C) return;
   const char* src = static_cast<const char*>(feat) + (b * g.C + c) * static_cast<int64_t>(g.H) * g.W * ES;
   char* dst = static_cast<char*>(out) + ((bk * g.C + c) * static_cast<int64_t>(g.oh) * g.ow + sx * VEC) * ES;
@@ -268,6 +287,7 @@ __global__ void __launch_bounds__(256) crop_fwd_strip_kernel(const void* __restr
     const char* sp = src + (static_cast<int64_t>(bx.x) * g.W + static_cast<int64_t>(bx.y) + sx * VEC) * ES;
     if (((reinterpret_cast<uintptr_t>(sp) | static_cast<uintptr_t>(src_pitch)) & 15u) == 0) {
       int oy = 0;
+#pragma unroll 1
       for (; oy + 4 <= g.oh; oy += 4) {  // four independent 128-bit loads in flight
         uint4 v[4];
 #pragma unroll
@@ -280,23 +300,32 @@ __global__ void __launch_bounds__(256) crop_fwd_strip_kernel(const void* __restr
     }
   }
 
+  // column taps of this strip
   int xa[VEC], xb[VEC];
   float xw[VEC];
 #pragma unroll
-  for (int v = 0; v < VEC; ++v) axis_taps(bx.y, bx.w - bx.y, sx * VEC + v, g.ow, g.W, xa[v], xb[v], xw[v]);
+  for (int v = 0; v < VEC; ++v) {
+    axis_taps(bx.y, bx.w - bx.y, sx * VEC + v, g.ow, g.W, xa[v], xb[v], xw[v]);
+  }
   auto hpass = [&](int y, float* h) {
     const char* row = src + static_cast<int64_t>(y) * src_pitch;
+    float a[VEC], b2[VEC];
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      const float a = ld1<DT>(row, xa[v]);
-      h[v] = xw[v] == 0.f ? a : fmaf(ld1<DT>(row, xb[v]), xw[v], a * (1.f - xw[v]));
+    for (int v = 0; v < VEC; ++v) {  // all 2*VEC loads in flight before the first use
+      a[v] = ld1<DT>(row, xa[v]);
+      b2[v] = ld1<DT>(row, xb[v]);
     }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) h[v] = xw[v] == 0.f ? a[v] : fmaf(b2[v], xw[v], a[v] * (1.f - xw[v]));
   };
+  // Walk the SEGMENTS: maximal runs of output rows that blend the same two source rows (and agree on wy != 0) -- at
+  // zoom z a segment has ~z rows.  Per segment at most one horizontal pass (the bottom row of one segment is the top row
+  // of the next); per output row only the vertical blend, the pack and one 128-bit store remain.
   float h_top[VEC], h_bot[VEC];
   int cur0 = -1, cur1 = -1;  // source rows held in h_top / h_bot
-  for (int oy = 0; oy < g.oh; ++oy) {
-    const int i0 = y_i0[oy], i1 = y_i1[oy];
-    const float wy = y_w[oy];
+  for (int s = 0; s < nseg; ++s) {
+    const int ra = seg[s], rb = seg[s + 1];
+    const int i0 = y_i0[ra], i1 = y_i1[ra];
     if (i0 != cur0) {
       if (i0 == cur1) {
 #pragma unroll
@@ -306,26 +335,31 @@ __global__ void __launch_bounds__(256) crop_fwd_strip_kernel(const void* __restr
       }
       cur0 = i0;
     }
-    float res[VEC];
-    if (wy != 0.f) {
+    char* drow = dst + ra * dst_pitch;
+    if (y_w[ra] != 0.f) {
       if (i1 != cur1) {
         hpass(i1, h_bot);
         cur1 = i1;
       }
-      // packed fp32x2 multiply / fma: same roundings as the scalar fmaf(h_bot, wy, h_top * om), half the issue slots
-      const float2 wy2 = make_float2(wy, wy), om2 = make_float2(1.f - wy, 1.f - wy);
+#pragma unroll 2
+      for (int oy = ra; oy < rb; ++oy, drow += dst_pitch) {
+        const float wy = y_w[oy];
+        // packed fp32x2 multiply / fma: same roundings as the scalar fmaf(h_bot, wy, h_top * om), half the issue slots
+        const float2 wy2 = make_float2(wy, wy), om2 = make_float2(1.f - wy, 1.f - wy);
+        float res[VEC];
 #pragma unroll
-      for (int v = 0; v < VEC; v += 2) {
-        const float2 t = __fmul2_rn(make_float2(h_top[v], h_top[v + 1]), om2);
-        const float2 r = __ffma2_rn(make_float2(h_bot[v], h_bot[v + 1]), wy2, t);
-        res[v] = r.x;
-        res[v + 1] = r.y;
+        for (int v = 0; v < VEC; v += 2) {
+          const float2 t = __fmul2_rn(make_float2(h_top[v], h_top[v + 1]), om2);
+          const float2 r = __ffma2_rn(make_float2(h_bot[v], h_bot[v + 1]), wy2, t);
+          res[v] = r.x;
+          res[v + 1] = r.y;
+        }
+        stg_stream(drow, Elem<DT>::pack(res));
       }
     } else {
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) res[v] = h_top[v];
+      const uint4 packed = Elem<DT>::pack(h_top);
+      for (int oy = ra; oy < rb; ++oy, drow += dst_pitch) stg_stream(drow, packed);
     }
-    stg_stream(dst + oy * dst_pitch, Elem<DT>::pack(res));
   }
 }
 
@@ -638,8 +672,17 @@ extern "C" int msf_crop_resample_fwd(const void* feat, int64_t B, int C, int H, 
   if (strip_ok) {
     const int planes_cta = 256 / owv;
     const int64_t ctas = B * K * ((C + planes_cta - 1) / planes_cta);
-    const size_t smem = static_cast<size_t>(3) * oh * 4;
-    MSF_DISPATCH_DTYPE(dtype, (crop_fwd_strip_kernel<DT><<<static_cast<unsigned>(ctas), 256, smem, st>>>(feat, boxes, out, g, owv)));
+    const size_t smem = (static_cast<size_t>(4) * oh + 1) * 4;  // row taps + weights + segment starts
+    // 16-bit elements: 64 registers (4 CTAs per SM) against the natural 76 (3 CTAs); MSF_CROP_STRIP_MINB picks for measurements
+    static const int minb = [] {
+      const char* e = getenv("MSF_CROP_STRIP_MINB");
+      return e && atoi(e) == 3 ? 3 : 4;
+    }();
+    if (minb == 4) {
+      MSF_DISPATCH_DTYPE(dtype, (crop_fwd_strip_kernel<DT, 4><<<static_cast<unsigned>(ctas), 256, smem, st>>>(feat, boxes, out, g, owv)));
+    } else {
+      MSF_DISPATCH_DTYPE(dtype, (crop_fwd_strip_kernel<DT, 3><<<static_cast<unsigned>(ctas), 256, smem, st>>>(feat, boxes, out, g, owv)));
+    }
   } else if (fast_ok) {
     const int64_t ctas = B * K * ((C + 7) / 8);
     MSF_DISPATCH_DTYPE(dtype, (crop_fwd_fast_kernel<DT><<<static_cast<unsigned>(ctas), kFastThreads, fast_smem, st>>>(feat, boxes, out, g, kroll)));

@@ -75,7 +75,8 @@ constexpr int SM_ = 64, SN_ = 64, SK_ = 32;
 __global__ void __launch_bounds__(256) infonce_simt_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                            int64_t nq, int64_t n_keys, int dim, float a, float c,
                                                            int64_t tiles_per_split, int64_t nq_pad,
-                                                           float* __restrict__ rowsum, float* __restrict__ o_part) {
+                                                           float* __restrict__ rowsum, float* __restrict__ o_part,
+                                                           const float* __restrict__ col_scale) {
   __shared__ float Qs[SM_][SK_ + 1];
   __shared__ float Ks[SN_][SK_ + 1];
   __shared__ float Ps[SM_][SN_ + 1];
@@ -118,7 +119,8 @@ __global__ void __launch_bounds__(256) infonce_simt_kernel(const float* __restri
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const bool ok = key0 + tx * 4 + j < n_keys;
-        const float e = ok ? exp2f(fmaf(s[i][j], a, -c)) : 0.f;
+        float e = ok ? exp2f(fmaf(s[i][j], a, -c)) : 0.f;
+        if (col_scale && ok) e *= col_scale[key0 + tx * 4 + j];  // transposed pass of msf_infonce_dk: 1 / row sum of that query
         rs[i] += e;
         Ps[ty * 4 + i][tx * 4 + j] = e;
       }
@@ -287,6 +289,141 @@ __global__ void __launch_bounds__(256) nce_bwd_kernel(const char* __restrict__ q
   }
 }
 
+
+// --------------------------------------------------------------------------------------------
+// key gradient (keys NOT detached -- north_star (4); the reference detaches every key, backbone.py:188-191)
+//   dk_hat_j = g/tau * ( sum_i softmax_ij q_hat_i  -  q_hat_{i : pos(i) = j} )
+// The sum over the LOCAL queries is the same flash pass with the roles swapped (rows = all keys, columns = local queries);
+// softmax_ij = e_ij / sum_i turns the per-query 1/sum_i into a per-COLUMN term of that pass.  The partial over this rank's
+// queries covers every global key; the caller reduce-scatters it to the keys' owners (NCCL), then msf_infonce_dk_finish
+// subtracts the positives (local by construction) and applies the normalise Jacobian of z.
+// --------------------------------------------------------------------------------------------
+// mode 0: exponent bias -(a + log2 sum_i) for the tcgen05 pass (padding -1e30 -> exp2 = 0); mode 1: 1 / sum_i (fp32 SIMT pass)
+__global__ void __launch_bounds__(256) nce_col_terms_kernel(const float* __restrict__ sum_tot, int64_t nq, int64_t n_pad, float a, int mode,
+                                                            float* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n_pad) return;
+  if (mode == 0) out[i] = i < nq ? -(a + log2f(sum_tot[i])) : -1e30f;
+  else out[i] = i < nq ? 1.f / sum_tot[i] : 0.f;
+}
+
+// two-pass widths: Qs_i = q_hat_i / sum_i in bf16 (the B operand of dK = P^T Qs)
+__global__ void __launch_bounds__(256) nce_scale_rows_kernel(const char* __restrict__ qh, const float* __restrict__ sum_tot, int64_t nq,
+                                                             uint32_t cpr, char* __restrict__ out) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= nq * cpr) return;
+  const int64_t row = idx / cpr;
+  float f[8];
+  Elem<MSF_BF16>::unpack(ldg_keep(qh + idx * 16), f);
+  const float inv = 1.f / sum_tot[row];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] *= inv;
+  *reinterpret_cast<uint4*>(out + idx * 16) = Elem<MSF_BF16>::pack(f);
+}
+
+// dk_out[j] = g * scale / tau * sum_splits O^T partials (fixed order)
+__global__ void __launch_bounds__(256) nce_dk_combine_kernel(const float* __restrict__ o_part, int splits, int64_t n_pad, int64_t n_keys,
+                                                             uint32_t dim4, const float* __restrict__ grad_out, float scale_inv_tau,
+                                                             float* __restrict__ dk_out) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= n_keys * dim4) return;
+  const float gs = __ldg(grad_out) * scale_inv_tau;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < splits; ++s) {
+    const float4 v = *reinterpret_cast<const float4*>(o_part + (static_cast<int64_t>(s) * n_pad * dim4 + idx) * 4);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  *reinterpret_cast<float4*>(dk_out + idx * 4) = make_float4(acc.x * gs, acc.y * gs, acc.z * gs, acc.w * gs);
+}
+
+// grad_z_j = J_normalize(z_j)^T (dk_j - [j < nq] g scale/tau q_hat_j);  J^T d = (d - k_hat (k_hat . d)) / max(||z||, eps)
+template <int DT, int GDT>
+__global__ void __launch_bounds__(256) nce_dk_finish_kernel(const float* __restrict__ dk, const char* __restrict__ qh, const char* __restrict__ kh,
+                                                            const float* __restrict__ inv_norm, int64_t rows, int64_t nq, uint32_t dim,
+                                                            const float* __restrict__ grad_out, float scale_inv_tau, char* __restrict__ grad_z,
+                                                            uint32_t lanes) {
+  constexpr int V = Elem<DT>::VEC;
+  const uint32_t lane = threadIdx.x & (lanes - 1), grp = threadIdx.x / lanes, groups = 256 / lanes;
+  const uint32_t cpr = dim / V;
+  const size_t row_bytes = static_cast<size_t>(cpr) * 16;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * groups + grp;
+  const bool valid = row < rows;
+  const float gs = (valid && row < nq) ? __ldg(grad_out) * scale_inv_tau : 0.f;
+  auto load_d = [&](uint32_t c, float* fk, float* d) {
+    float fq[V];
+    Elem<DT>::unpack(ldg_keep(kh + row * row_bytes + static_cast<size_t>(c) * 16), fk);
+    if (row < nq) {
+      Elem<DT>::unpack(ldg_keep(qh + row * row_bytes + static_cast<size_t>(c) * 16), fq);
+    } else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) fq[i] = 0.f;
+    }
+    const float* src = dk + row * dim + static_cast<int64_t>(c) * V;
+#pragma unroll
+    for (int i = 0; i < V; i += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(src + i);
+      d[i] = v.x - gs * fq[i]; d[i + 1] = v.y - gs * fq[i + 1]; d[i + 2] = v.z - gs * fq[i + 2]; d[i + 3] = v.w - gs * fq[i + 3];
+    }
+  };
+  float t = 0.f;
+  if (valid)
+    for (uint32_t c = lane; c < cpr; c += lanes) {
+      float fk[V], d[V];
+      load_d(c, fk, d);
+#pragma unroll
+      for (int i = 0; i < V; ++i) t = fmaf(fk[i], d[i], t);
+    }
+  t = group_sum(t, lanes);
+  if (!valid) return;
+  const float inn = inv_norm ? inv_norm[row] : 1.f;
+  for (uint32_t c = lane; c < cpr; c += lanes) {
+    float fk[V], d[V], g[V];
+    load_d(c, fk, d);
+#pragma unroll
+    for (int i = 0; i < V; ++i) g[i] = (d[i] - fk[i] * t) * inn;
+    constexpr int GV = Elem<GDT>::VEC;
+    char* dst = grad_z + (row * dim + static_cast<int64_t>(c) * V) * (16 / GV);
+    if constexpr (GV == V) {
+      stg_stream(dst, Elem<GDT>::pack(g));
+    } else if constexpr (GV < V) {
+      stg_stream(dst, Elem<GDT>::pack(g));
+      stg_stream(dst + 16, Elem<GDT>::pack(g + 4));
+    } else {
+      float tmp[8] = {g[0], g[1], g[2], g[3], 0.f, 0.f, 0.f, 0.f};
+      const uint4 pk = Elem<GDT>::pack(tmp);
+      *reinterpret_cast<uint2*>(dst) = make_uint2(pk.x, pk.y);
+    }
+  }
+}
+
+// workspace of msf_infonce_dk: [column terms | the transposed pass's own plan (flash / SIMT) or {Qs, O^T} (two-pass)]
+struct DkPlan {
+  int mode;
+  NcePlan t;        // transposed problem: "queries" = all keys, "keys" = local queries (modes 0 / 1)
+  int64_t col_pad;  // floats of column terms
+  size_t off_col, off_t, off_qs, off_o, total;
+};
+inline DkPlan make_dk_plan(int64_t nq, int64_t n_keys, int dim, int precision) {
+  DkPlan d{};
+  auto align = [](size_t v) { return (v + 255) & ~static_cast<size_t>(255); };
+  d.t = make_nce_plan(n_keys, nq, dim, precision);
+  d.mode = d.t.mode;
+  d.col_pad = (nq + 127) / 128 * 128;
+  size_t off = 0;
+  d.off_col = off;
+  off = align(off + static_cast<size_t>(d.col_pad) * sizeof(float));
+  d.off_t = d.off_qs = d.off_o = off;
+  if (d.mode == 2) {
+    off = align(off + static_cast<size_t>(nq) * dim * 2);
+    d.off_o = off;
+    off = align(off + static_cast<size_t>(n_keys) * dim * sizeof(float));
+  } else {
+    off += d.t.total;
+  }
+  d.total = off;
+  return d;
+}
+
 inline uint32_t lanes_for(uint32_t cpr) {  // ~4 chunks per lane: few shuffle rounds per row, several loads in flight
   uint32_t lanes = 1;
   while (lanes < 32 && lanes * 4 < cpr) lanes <<= 1;
@@ -398,7 +535,7 @@ extern "C" int msf_infonce_fwd_timed(const void* q_hat, const void* k_hat, int64
   } else {
     dim3 grid(static_cast<unsigned>(plan.q_tiles), static_cast<unsigned>(plan.splits));
     infonce_simt_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(q_hat), static_cast<const float*>(k_hat), nq,
-                                              n_keys, dim, a, a, plan.tiles_per_split, plan.nq_pad, rowsum, o_part);
+                                              n_keys, dim, a, a, plan.tiles_per_split, plan.nq_pad, rowsum, o_part, nullptr);
     MSF_LAUNCH_OK("infonce_simt_kernel");
   }
   }
@@ -451,5 +588,95 @@ extern "C" int msf_infonce_bwd(const void* q_hat, const void* k_hat, const float
   MSF_NB(MSF_F32, MSF_F32) MSF_NB(MSF_F32, MSF_BF16) MSF_NB(MSF_F32, MSF_F16)
   MSF_NB(MSF_BF16, MSF_F32) MSF_NB(MSF_BF16, MSF_BF16) MSF_NB(MSF_BF16, MSF_F16)
 #undef MSF_NB
+  return MSF_ERR_UNSUPPORTED;
+}
+
+
+extern "C" size_t msf_infonce_dk_workspace_bytes(int64_t nq, int64_t n_keys, int dim, int precision) {
+  if (nq <= 0 || n_keys <= 0 || dim <= 0) return 0;
+  return make_dk_plan(nq, n_keys, dim, precision).total;
+}
+
+extern "C" int msf_infonce_dk(const void* q_hat, const void* k_hat, int64_t nq, int64_t n_keys, int dim, int64_t pos_offset, float tau,
+                              int precision, const float* grad_out, float scale, const void* fwd_workspace, size_t fwd_workspace_bytes,
+                              float* dk_out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_nce(q_hat, k_hat, nq, n_keys, dim, pos_offset, tau, precision)) return rc;
+  MSF_REQUIRE(grad_out && dk_out && aligned16(dk_out), MSF_ERR_INVALID, "grad_out / dk_out NULL or misaligned");
+  const NcePlan fwd = make_nce_plan(nq, n_keys, dim, precision);
+  MSF_REQUIRE(fwd_workspace && fwd_workspace_bytes >= fwd.total, MSF_ERR_WORKSPACE, "forward workspace of %zu bytes < %zu required",
+              fwd_workspace_bytes, fwd.total);
+  const DkPlan dp = make_dk_plan(nq, n_keys, dim, precision);
+  MSF_REQUIRE(workspace && aligned16(workspace) && workspace_bytes >= dp.total, MSF_ERR_WORKSPACE, "workspace of %zu bytes < %zu required",
+              workspace_bytes, dp.total);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const char* fws = static_cast<const char*>(fwd_workspace);
+  const float* sum_tot = reinterpret_cast<const float*>(fws + fwd.off_sum);
+  char* ws = static_cast<char*>(workspace);
+  float* col = reinterpret_cast<float*>(ws + dp.off_col);
+  const float a = kLog2e / tau;
+  const float* o_part = nullptr;
+  int splits = 1;
+  int64_t n_pad = n_keys;
+  ProfScope prof(stream, MSF_K_NCE_DK, 4.0 * static_cast<double>(nq) * static_cast<double>(n_keys) * dim);
+  if (dp.mode == 2) {
+    // dK = P^T Qs with the forward's 16-bit P = exp2(a s - a) still in its workspace and Qs_i = q_hat_i / sum_i
+    char* qs = ws + dp.off_qs;
+    const uint32_t cpr = dim / 8;
+    nce_scale_rows_kernel<<<static_cast<unsigned>((nq * cpr + 255) / 256), 256, 0, st>>>(static_cast<const char*>(q_hat), sum_tot, nq, cpr, qs);
+    MSF_LAUNCH_OK("nce_scale_rows_kernel");
+    float* o = reinterpret_cast<float*>(ws + dp.off_o);
+    if (int rc = launch_gemm_tc(fws + fwd.off_p, fwd.ld_p, qs, dim, o, dim, n_keys, dim, nq, 1, 0 /*EPI_F32*/, 1.f, nullptr, nullptr, 0, st, 1))
+      return rc;
+    o_part = o;
+  } else {
+    nce_col_terms_kernel<<<static_cast<unsigned>((dp.col_pad + 255) / 256), 256, 0, st>>>(sum_tot, nq, dp.col_pad, a, dp.mode == 0 ? 0 : 1, col);
+    MSF_LAUNCH_OK("nce_col_terms_kernel");
+    char* tws = ws + dp.off_t;
+    float* rowsum = reinterpret_cast<float*>(tws + dp.t.off_rowsum);
+    float* o = reinterpret_cast<float*>(tws + dp.t.off_o);
+    if (dp.mode == 0) {
+      if (int rc = launch_infonce_dk_flash(k_hat, q_hat, n_keys, nq, dim, tau, dp.t, col, rowsum, o, st)) return rc;
+    } else {
+      dim3 grid(static_cast<unsigned>(dp.t.q_tiles), static_cast<unsigned>(dp.t.splits));
+      infonce_simt_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(k_hat), static_cast<const float*>(q_hat), n_keys, nq, dim, a, a,
+                                                dp.t.tiles_per_split, dp.t.nq_pad, rowsum, o, col);
+      MSF_LAUNCH_OK("infonce_simt_kernel");
+    }
+    o_part = o;
+    splits = dp.t.splits;
+    n_pad = dp.t.nq_pad;
+  }
+  const uint32_t dim4 = dim / 4;
+  nce_dk_combine_kernel<<<static_cast<unsigned>((n_keys * dim4 + 255) / 256), 256, 0, st>>>(o_part, splits, n_pad, n_keys, dim4, grad_out, scale / tau,
+                                                                                          dk_out);
+  MSF_LAUNCH_OK("nce_dk_combine_kernel");
+  return MSF_OK;
+}
+
+extern "C" int msf_infonce_dk_finish(const float* dk_local, const void* q_hat, const void* k_hat_local, const float* k_inv_norm, int64_t rows,
+                                     int64_t nq, int dim, float tau, int precision, const float* grad_out, float scale, void* grad_z,
+                                     int grad_dtype, void* stream) {
+  MSF_REQUIRE(precision == MSF_F32 || precision == MSF_BF16, MSF_ERR_INVALID, "precision must be MSF_F32 or MSF_BF16");
+  MSF_REQUIRE(rows > 0 && nq >= 0 && nq <= rows && dim > 0 && dim % (precision == MSF_BF16 ? 8 : 4) == 0, MSF_ERR_INVALID,
+              "bad shape rows=%lld nq=%lld dim=%d", static_cast<long long>(rows), static_cast<long long>(nq), dim);
+  MSF_REQUIRE(dk_local && q_hat && k_hat_local && grad_out && grad_z && aligned16(dk_local) && aligned16(q_hat) && aligned16(k_hat_local) &&
+                  aligned16(grad_z) && dtype_ok(grad_dtype) && tau > 0.f,
+              MSF_ERR_INVALID, "NULL / misaligned pointer or bad dtype");
+  const uint32_t cpr = dim / (precision == MSF_BF16 ? 8 : 4);
+  const uint32_t lanes = lanes_for(cpr), groups = 256 / lanes;
+  const unsigned blocks = static_cast<unsigned>((rows + groups - 1) / groups);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const char* qh = static_cast<const char*>(q_hat);
+  const char* kh = static_cast<const char*>(k_hat_local);
+  char* gz = static_cast<char*>(grad_z);
+#define MSF_NF(P, G)                                                                                                                       \
+  if (precision == P && grad_dtype == G) {                                                                                                 \
+    nce_dk_finish_kernel<P, G><<<blocks, 256, 0, st>>>(dk_local, qh, kh, k_inv_norm, rows, nq, dim, grad_out, scale / tau, gz, lanes);     \
+    MSF_LAUNCH_OK("nce_dk_finish_kernel");                                                                                                 \
+    return MSF_OK;                                                                                                                         \
+  }
+  MSF_NF(MSF_F32, MSF_F32) MSF_NF(MSF_F32, MSF_BF16) MSF_NF(MSF_F32, MSF_F16)
+  MSF_NF(MSF_BF16, MSF_F32) MSF_NF(MSF_BF16, MSF_BF16) MSF_NF(MSF_BF16, MSF_F16)
+#undef MSF_NF
   return MSF_ERR_UNSUPPORTED;
 }

@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <vector>
 
+#include "infonce_plan.cuh"
 #include "tc_common.cuh"
 
 namespace msf {
@@ -57,7 +58,7 @@ struct alignas(64) FlashProblem {
   float* rowsum;            // [splits][nq_pad]
   float* o_part;            // [splits][nq_pad][D]
   int32_t nq, rows_per_rank, world, tiles_per_rank, k_tiles, tiles_per_split, splits, nq_pad, cta_start, cta_end;
-  int32_t pad_[2];
+  const float* col_bias;    // COLB kernels: [k_tiles * 128] additive exponent term per KEY column (see msf_infonce_dk)
 };
 struct alignas(64) FlashParams {
   FlashProblem p[kMaxFlash];
@@ -74,7 +75,17 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
       : "memory");
 }
 
-template <int D>
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+constexpr uint32_t kColBiasBytes = BN * sizeof(float);
+
+// COLB = true is the transposed pass behind msf_infonce_dk (gradient of the KEYS, north_star (4)): the exponent of logit
+// (row, col) is a * s + col_bias[col] instead of a_row * s - a, the bias travelling with each key tile (one 512-byte bulk copy
+// on the tile's own mbarrier).  Everything else -- pipeline, TMEM map, issue order -- is the same kernel.
+template <int D, bool COLB>
 __global__ void __launch_bounds__(kThreads, 1) infonce_grouped_kernel(const __grid_constant__ FlashParams P) {
   using C = Cfg<D>;
   extern __shared__ uint8_t smem_raw[];
@@ -90,6 +101,7 @@ __global__ void __launch_bounds__(kThreads, 1) infonce_grouped_kernel(const __gr
   uint64_t* o_full = p_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
   float* rs_xchg = reinterpret_cast<float*>(bars + 32);  // 128 floats
+  float* sCB = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + C::kBarBytes);  // COLB: [kStages][128] column biases
 
   int pi = 0;
 #pragma unroll 1
@@ -138,9 +150,10 @@ __global__ void __launch_bounds__(kThreads, 1) infonce_grouped_kernel(const __gr
       for (int t = 0; t < T; ++t) {
         const int stage = t % C::kStages;
         mbar_wait(k_empty + stage, ((t / C::kStages) & 1) ^ 1);
-        mbar_expect_tx(k_full + stage, C::kTileBytes);
+        mbar_expect_tx(k_full + stage, C::kTileBytes + (COLB ? kColBiasBytes : 0u));
         uint8_t* dst = sK + stage * C::kTileBytes;
         const int row = tile_in_rank * BN;
+        if constexpr (COLB) bulk_load_1d(sCB + stage * BN, q.col_bias + static_cast<size_t>(kt0 + t) * BN, kColBiasBytes, k_full + stage);
         for (int s = 0; s < C::kSlabs; ++s) tma_load_3d(dst + s * kSlabBytes, &q.tk, s * 64, row, rank, k_full + stage);
         if (++tile_in_rank == tpr) { tile_in_rank = 0; ++rank; }
       }
@@ -230,10 +243,12 @@ __global__ void __launch_bounds__(kThreads, 1) infonce_grouped_kernel(const __gr
     }
     float2 rs2 = make_float2(0.f, 0.f);
     const float2 a2 = make_float2(a_row, a_row), na2 = make_float2(-a, -a);
-    auto chunk = [&](const uint32_t* v, uint32_t* u, int col0, int valid, bool mask) {
+    auto chunk = [&](const uint32_t* v, uint32_t* u, int col0, int valid, bool mask, const float* cb) {
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
-        const float2 y = __ffma2_rn(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), a2, na2);
+        float2 nb = na2;
+        if constexpr (COLB) nb = *reinterpret_cast<const float2*>(cb + col0 + i);  // same address in every lane: a broadcast
+        const float2 y = __ffma2_rn(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), a2, nb);
         float2 e = make_float2(ex2_approx(y.x), ex2_approx(y.y));
         if (mask) {
           if (col0 + i >= valid) e.x = 0.f;
@@ -274,8 +289,10 @@ __global__ void __launch_bounds__(kThreads, 1) infonce_grouped_kernel(const __gr
       }
     };
     const int tpr_s = q.tiles_per_rank, rows_s = q.rows_per_rank;
-    const bool ragged = (rows_s % BN) != 0;
-    const bool fast = P.exp_mode != 0;
+    // COLB: the bias of the padding columns is -1e30 (their exponential is 0), and the polynomial exponential is off -- its
+    // exponent-field arithmetic assumes y >= -126, which log2(softmax) does not guarantee
+    const bool ragged = !COLB && (rows_s % BN) != 0;
+    const bool fast = !COLB && P.exp_mode != 0;
     const int mix_mask = P.exp_mode == 2 ? 1 : 3;
     for (int t = wg; t < T; t += 2) {
       mbar_wait(s_full + wg, (t >> 1) & 1);
@@ -287,6 +304,7 @@ __global__ void __launch_bounds__(kThreads, 1) infonce_grouped_kernel(const __gr
         valid = min(BN, rows_s - krow0);
       }
       uint32_t v0[32], v1[32], u[16];
+      const float* cb = sCB + (t % C::kStages) * BN;  // stays valid until gemm2(t), which waits for this warpgroup's p_full
       tmem_ld32(s_addr, v0);
       if (valid == BN && fast) {
         tmem_ld_wait();
@@ -307,25 +325,25 @@ __global__ void __launch_bounds__(kThreads, 1) infonce_grouped_kernel(const __gr
       } else if (valid == BN) {
         tmem_ld_wait();
         tmem_ld32(s_addr + 32, v1);
-        chunk(v0, u, 0, BN, false);
+        chunk(v0, u, 0, BN, false, cb);
         tmem_st16(s_addr, u);
         tmem_ld_wait();
         tmem_ld32(s_addr + 64, v0);
-        chunk(v1, u, 32, BN, false);
+        chunk(v1, u, 32, BN, false, cb);
         tmem_st16(s_addr + 16, u);
         tmem_ld_wait();
         tmem_ld32(s_addr + 96, v1);
-        chunk(v0, u, 64, BN, false);
+        chunk(v0, u, 64, BN, false, cb);
         tmem_st16(s_addr + 32, u);
         tmem_ld_wait();
-        chunk(v1, u, 96, BN, false);
+        chunk(v1, u, 96, BN, false, cb);
         tmem_st16(s_addr + 48, u);
       } else {
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           if (c > 0) tmem_ld32(s_addr + c * 32, v0);
           tmem_ld_wait();
-          chunk(v0, u, c * 32, valid, true);
+          chunk(v0, u, c * 32, valid, true, cb);
           tmem_st16(s_addr + c * 16, u);
         }
       }
@@ -673,11 +691,12 @@ inline int make_map_keys(CUtensorMap* map, const void* base, int D, int rows, in
 // loses 3 % to the extra issue slots, so it keeps one MUFU op per logit.
 inline int kDefaultExpMode(int D) { return D <= 128 ? 1 : 0; }
 
-template <int D>
+template <int D, bool COLB = false>
 int launch_flash(const FlashParams& FP, int ctas, cudaStream_t st) {
-  static const cudaError_t attr = cudaFuncSetAttribute(infonce_grouped_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<D>::kSmem);
+  constexpr uint32_t smem = Cfg<D>::kSmem + (COLB ? Cfg<D>::kStages * kColBiasBytes : 0u);
+  static const cudaError_t attr = cudaFuncSetAttribute(infonce_grouped_kernel<D, COLB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   MSF_REQUIRE(attr == cudaSuccess, MSF_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr));
-  infonce_grouped_kernel<D><<<ctas, kThreads, Cfg<D>::kSmem, st>>>(FP);
+  infonce_grouped_kernel<D, COLB><<<ctas, kThreads, smem, st>>>(FP);
   MSF_LAUNCH_OK("infonce_grouped_kernel");
   return MSF_OK;
 }
@@ -722,6 +741,40 @@ int fill_pairs(PairParams& PP, const msf_nce_pair* pr, int n, const Plan& pl, ch
 }
 
 }  // namespace
+
+// The transposed pass of msf_infonce_dk (infonce.cu): one "pair" whose query rows are ALL keys (n_keys, contiguous) and whose
+// key columns are this rank's normalised queries (one block, world = 1), exponent a * s + col_bias[column].
+int launch_infonce_dk_flash(const void* k_all, const void* q_hat, int64_t n_keys, int64_t nq, int dim, float tau, const NcePlan& planT,
+                            const float* col_bias, float* rowsum, float* o_part, cudaStream_t st) {
+  MSF_REQUIRE(flash_dim(dim) && n_keys < (1ll << 31) - 128 && nq < (1ll << 31) - 128, MSF_ERR_UNSUPPORTED, "key-gradient flash pass: bad shape");
+  MSF_REQUIRE(planT.q_tiles * planT.splits < (1ll << 31), MSF_ERR_UNSUPPORTED, "key-gradient flash pass: too many CTAs");
+  static thread_local FlashParams FP;
+  FlashProblem& f = FP.p[0];
+  f = FlashProblem{};
+  if (int rc = make_map_bf16(&f.tq, k_all, n_keys, dim, dim, 64, 128)) return rc;
+  if (int rc = make_map_keys(&f.tk, q_hat, dim, static_cast<int>(nq), 1, 0)) return rc;
+  f.q_rowsq = nullptr;
+  f.rowsum = rowsum;
+  f.o_part = o_part;
+  f.nq = static_cast<int32_t>(n_keys);
+  f.rows_per_rank = static_cast<int32_t>(nq);
+  f.world = 1;
+  f.tiles_per_rank = f.k_tiles = static_cast<int32_t>(planT.k_tiles);
+  f.tiles_per_split = static_cast<int32_t>(planT.tiles_per_split);
+  f.splits = planT.splits;
+  f.nq_pad = static_cast<int32_t>(planT.nq_pad);
+  f.cta_start = 0;
+  f.cta_end = static_cast<int32_t>(planT.q_tiles * planT.splits);
+  f.col_bias = col_bias;
+  FP.n = 1;
+  FP.a = kLog2e / tau;
+  FP.eps = 1e-8f;
+  FP.issue_policy = dim == 256 ? 1 : 0;
+  FP.exp_mode = 0;
+  return dim == 64 ? launch_flash<64, true>(FP, f.cta_end, st) : dim == 128 ? launch_flash<128, true>(FP, f.cta_end, st)
+                                                                          : launch_flash<256, true>(FP, f.cta_end, st);
+}
+
 }  // namespace msf
 
 using namespace msf;

@@ -81,6 +81,11 @@ inline NcePlan make_nce_plan(int64_t nq, int64_t n_keys, int dim, int precision)
 int launch_infonce_tc(const void* q_hat, const void* k_hat, int64_t nq, int64_t n_keys, int dim, float tau,
                       const NcePlan& plan, float* rowsum, float* o_part, cudaStream_t st);
 
+// implemented in infonce_grouped.cu: the transposed flash pass of msf_infonce_dk -- rows = all keys, columns = the local
+// queries, exponent a * s + col_bias[column]; planT = make_nce_plan(n_keys, nq, dim, MSF_BF16)
+int launch_infonce_dk_flash(const void* k_all, const void* q_hat, int64_t n_keys, int64_t nq, int dim, float tau, const NcePlan& planT,
+                            const float* col_bias, float* rowsum, float* o_part, cudaStream_t st);
+
 // implemented in gemm_tc.cu
 int launch_gemm_tc(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
                    int b_mn_major, int epi, float alpha, const float* bias, float* rowsum_part, int64_t m_pad, cudaStream_t st,

@@ -294,13 +294,13 @@ def all_gather_keys(k_hat: torch.Tensor, group=None) -> Tuple[torch.Tensor, int]
 
 class _InfoNCE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, p, z, tau: float, precision: torch.dtype, eps: float, group):
+    def forward(ctx, p, z, tau: float, precision: torch.dtype, eps: float, group, detach_keys: bool):
         L.require_cuda(p, z)
         if p.dim() != 2 or p.shape != z.shape:
             raise ValueError(f"infonce: p {tuple(p.shape)} and z {tuple(z.shape)} must be equal 2-D shapes")
         nq, dim = p.shape
         q_hat, q_inv = rownorm(p, precision, eps)
-        k_hat, _ = rownorm(z.detach(), precision, eps)
+        k_hat, k_inv = rownorm(z.detach(), precision, eps)
         k_all, pos_offset = all_gather_keys(k_hat, group)
         n_keys = k_all.shape[0]
         prec = L.dtype_code(precision)
@@ -310,30 +310,61 @@ class _InfoNCE(torch.autograd.Function):
         L.check(L.lib().msf_infonce_fwd(L.ptr(q_hat), L.ptr(k_all), nq, n_keys, dim, pos_offset, tau, prec, L.ptr(loss_sum), 0,
                                         L.ptr(ws), ws_bytes, L.stream_ptr()), "msf_infonce_fwd")
         L.launch_count += 3
-        ctx.save_for_backward(q_hat, k_all, q_inv, ws)
-        ctx.meta = (nq, n_keys, dim, pos_offset, tau, prec, ws_bytes, p.dtype)
+        ctx.save_for_backward(q_hat, k_all, q_inv, ws, k_hat, k_inv)
+        ctx.meta = (nq, n_keys, dim, pos_offset, tau, prec, ws_bytes, p.dtype, z.dtype, group, detach_keys)
         return loss_sum / nq  # per-rank mean, like the reference's per-rank .mean() under DDP
 
     @staticmethod
     def backward(ctx, grad_out):
-        nq, n_keys, dim, pos_offset, tau, prec, ws_bytes, p_dtype = ctx.meta
-        q_hat, k_all, q_inv, ws = ctx.saved_tensors
+        nq, n_keys, dim, pos_offset, tau, prec, ws_bytes, p_dtype, z_dtype, group, detach_keys = ctx.meta
+        q_hat, k_all, q_inv, ws, k_hat, k_inv = ctx.saved_tensors
         g = _contig(grad_out.to(torch.float32))
         grad_q = torch.empty((nq, dim), dtype=p_dtype, device=q_hat.device)
         L.check(L.lib().msf_infonce_bwd(L.ptr(q_hat), L.ptr(k_all), L.ptr(q_inv), nq, n_keys, dim, pos_offset, tau, prec, L.ptr(g),
                                         1.0 / nq, L.ptr(ws), ws_bytes, L.ptr(grad_q), L.dtype_code(p_dtype), L.stream_ptr()),
                 "msf_infonce_bwd")
         L.launch_count += 1
-        return grad_q, None, None, None, None, None
+        grad_z = None
+        if not detach_keys and ctx.needs_input_grad[1]:
+            grad_z = _infonce_key_grad(q_hat, k_all, k_hat, k_inv, ws, ws_bytes, g, nq, n_keys, dim, pos_offset, tau, prec, z_dtype, group)
+        return grad_q, grad_z, None, None, None, None, None
+
+
+def _infonce_key_grad(q_hat, k_all, k_hat, k_inv, ws, ws_bytes, g, nq, n_keys, dim, pos_offset, tau, prec, z_dtype, group):
+    """north_star (4), keys NOT detached: this rank's queries contribute to the gradient of EVERY global key
+    (``msf_infonce_dk``: the flash pass with the roles swapped); the partials are reduce-scattered to the keys' owners over
+    NCCL (the backward of the rank-major all-gather), where ``msf_infonce_dk_finish`` subtracts the positives and applies the
+    normalise Jacobian of z."""
+    dev = q_hat.device
+    dk_ws_bytes = L.lib().msf_infonce_dk_workspace_bytes(nq, n_keys, dim, prec)
+    dk_ws = torch.empty(dk_ws_bytes, dtype=torch.uint8, device=dev)
+    dk_all = torch.empty((n_keys, dim), dtype=torch.float32, device=dev)
+    L.check(L.lib().msf_infonce_dk(L.ptr(q_hat), L.ptr(k_all), nq, n_keys, dim, pos_offset, tau, prec, L.ptr(g), 1.0 / nq, L.ptr(ws), ws_bytes,
+                                   L.ptr(dk_all), L.ptr(dk_ws), dk_ws_bytes, L.stream_ptr()), "msf_infonce_dk")
+    L.launch_count += 3
+    rows = k_hat.shape[0]
+    if n_keys != rows:  # keys were gathered: sum the partials of all ranks, every rank keeps the rows of its own keys
+        dk_local = torch.empty((rows, dim), dtype=torch.float32, device=dev)
+        dist.reduce_scatter_tensor(dk_local, dk_all, op=dist.ReduceOp.SUM, group=group if group is not False else None)
+    else:
+        dk_local = dk_all
+    grad_z = torch.empty((rows, dim), dtype=z_dtype, device=dev)
+    L.check(L.lib().msf_infonce_dk_finish(L.ptr(dk_local), L.ptr(q_hat), L.ptr(k_hat), L.ptr(k_inv), rows, nq, dim, tau, prec, L.ptr(g), 1.0 / nq,
+                                          L.ptr(grad_z), L.dtype_code(z_dtype), L.stream_ptr()), "msf_infonce_dk_finish")
+    L.launch_count += 1
+    return grad_z
 
 
 def infonce_loss(p: torch.Tensor, z: torch.Tensor, tau: float = 0.07, precision: Optional[torch.dtype] = None,
-                 eps: float = COS_EPS, group=None) -> torch.Tensor:
+                 eps: float = COS_EPS, group=None, detach_keys: bool = True) -> torch.Tensor:
     """mean_i [logsumexp_j(p_hat_i . z_hat_j / tau) - p_hat_i . z_hat_pos(i) / tau] with keys all-gathered over
-    ``group`` (rank-major) and detached.  Positive of local row i on rank r is global row r*rows+i."""
+    ``group`` (rank-major).  Positive of local row i on rank r is global row r*rows+i.
+    ``detach_keys=True`` (default) is the reference's semantics (every z is detached, backbone.py:188-191): z receives no
+    gradient.  ``detach_keys=False`` is the non-detached variant of north_star (4): z receives the gradient of the losses of
+    ALL ranks (each rank's loss being its local mean, as DDP sums them before averaging), reduce-scattered over ``group``."""
     if precision is None:
         precision = infonce_precision_for(p.shape[1], p.dtype)
-    return _InfoNCE.apply(p, z, float(tau), precision, float(eps), group)
+    return _InfoNCE.apply(p, z, float(tau), precision, float(eps), group, bool(detach_keys))
 
 
 class _InfoNCEGrouped(torch.autograd.Function):

@@ -35,6 +35,13 @@ def _worker(rank, world, port, q):
         grad_single = O.infonce_grad(p_all, z_all, tau)[rank * rows:(rank + 1) * rows]
         assert abs(loss_ddp.item() - loss_single.item()) < 1e-12
         assert torch.allclose(grad_local / world, grad_single, rtol=1e-10, atol=1e-14)
+        # keys NOT detached (north_star (4)): every rank's queries touch every key; the reduce-scatter (backward of the
+        # rank-major all-gather, as ops._infonce_key_grad issues it) hands each rank the summed rows of its own keys
+        part = O.infonce_key_grad(p, keys, tau, off, n_rows_global=rows).contiguous()
+        mine = torch.empty((rows, dim), dtype=part.dtype)
+        dist.reduce_scatter_tensor(mine, part, op=dist.ReduceOp.SUM)
+        single = O.infonce_key_grad(p_all, z_all, tau)[rank * rows:(rank + 1) * rows]
+        assert torch.allclose(mine / world, single, rtol=1e-10, atol=1e-14)
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))
