@@ -468,8 +468,9 @@ def ours(args):
 # multi-GPU parity, checked on the box before anything is timed (N > 1)
 # ------------------------------------------------------------------------------------------------------------
 def check_dist_parity(torch, dist, M, ops, dev, rank, world):
-    """Max errors of the three cross-rank pieces of the path against their single-process definitions:
-    (a) sharded InfoNCE (local queries x all-gathered keys) vs the loss / gradient of the gathered problem on one rank,
+    """Max errors of the cross-rank pieces of the path against their single-process definitions:
+    (a) sharded InfoNCE (local queries x all-gathered keys) vs the loss / gradient of the gathered problem on one rank, and
+    the reduce-scattered key gradient of the non-detached variant,
     (b) the NVLink peer all-reduce vs NCCL's, (c) batch norm with synced statistics vs batch norm of the concatenated batch.
     Raises if a bound is exceeded; the numbers go into the JSON line."""
     out = {}
@@ -494,6 +495,17 @@ def check_dist_parity(torch, dist, M, ops, dev, rank, world):
         out[f"infonce_d{dim}_grad_cos"] = float((a @ b) / (a.norm() * b.norm()))
         out[f"infonce_d{dim}_grad_rel"] = float((a - b).norm() / b.norm())
         assert out[f"infonce_d{dim}_loss_rel"] <= 1e-5 and out[f"infonce_d{dim}_grad_cos"] >= 0.9999, out
+        # keys NOT detached (north_star (4)): msf_infonce_dk partials of every rank reduce-scattered over NCCL vs the key
+        # gradient of the gathered problem on one rank (x world: the ranks' local-mean losses add up before DDP averages)
+        pk = p_all[sl].clone().requires_grad_(True)
+        zk = z_all[sl].clone().requires_grad_(True)
+        ops.infonce_loss(pk, zk, tau=tau, group=dist.group.WORLD, detach_keys=False).backward()
+        pf2, zf2 = p_all.clone().requires_grad_(True), z_all.clone().requires_grad_(True)
+        ops.infonce_loss(pf2, zf2, tau=tau, group=False, detach_keys=False).backward()
+        a, b = (zk.grad.double() / world).flatten(), zf2.grad[sl].double().flatten()
+        out[f"infonce_d{dim}_keygrad_cos"] = float((a @ b) / (a.norm() * b.norm()))
+        out[f"infonce_d{dim}_keygrad_rel"] = float((a - b).norm() / b.norm())
+        assert out[f"infonce_d{dim}_keygrad_cos"] >= 0.9999, out
     red = ops.PeerReducer.get(dist.group.WORLD, dev) if ops.USE_PEER_ALLREDUCE else None
     v = torch.randn(9217, device=dev, dtype=torch.float64, generator=torch.Generator(device=dev).manual_seed(rank))
     want = v.clone()

@@ -39,6 +39,15 @@ def _worker(rank, world, port, q):
             assert abs(t.item() / world - ref.item()) <= tol * abs(ref.item()), (dim, t.item() / world, ref.item())
             assert cos >= 0.9999, (dim, cos)
             res[dim] = (t.item() / world, ref.item(), cos)
+            # keys NOT detached (north_star (4)): per-rank msf_infonce_dk partials, NCCL reduce-scatter, finish on the owner
+            p2 = p_all[rank * rows:(rank + 1) * rows].cuda().requires_grad_(True)
+            z2 = k_all[rank * rows:(rank + 1) * rows].cuda().requires_grad_(True)
+            ops.infonce_loss(p2, z2, tau=0.07, detach_keys=False).backward()
+            kref = O.infonce_key_grad(p_all.double(), k_all.double(), 0.07)[rank * rows:(rank + 1) * rows]
+            gotk = z2.grad.double().cpu() / world
+            cosk = float((gotk.flatten() @ kref.flatten()) / (gotk.norm() * kref.norm()))
+            assert cosk >= 0.9999, (dim, "key gradient", cosk)
+            assert torch.equal(p2.grad, p.grad)  # the query gradient does not depend on the flag
         # encoder BatchNorm (fused kernels): self-synchronising statistics == BatchNorm2d over the concatenated batch
         import msfwsi_b200.resnet as R
         g = torch.Generator().manual_seed(3)

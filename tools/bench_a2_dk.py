@@ -57,7 +57,15 @@ def main():
             cr = lambda: L.check(L.lib().msf_crop_resample_fwd(feat.data_ptr(), Bq, Cc, H, W, boxes.data_ptr(), 16, oh, ow, L.dtype_code(dt),
                                                                outp.data_ptr(), L.stream_ptr()), "crop")
             ms = timeit(cr)
-            res["a2"].append({"case": f"{tag} {str(dt).split('.')[-1]}", "bytes": nbytes, "ms": ms, "GBps": nbytes / ms / 1e6, "frac": nbytes / ms / 1e6 / hbm})
+            res["a2"].append({"case": f"fwd {tag} {str(dt).split('.')[-1]}", "bytes": nbytes, "ms": ms, "GBps": nbytes / ms / 1e6, "frac": nbytes / ms / 1e6 / hbm})
+            gfeat = torch.empty((Bq, Cc, H, W), dtype=torch.float32, device=dev)
+            bw = lambda: L.check(L.lib().msf_crop_resample_bwd(outp.data_ptr(), Bq, Cc, H, W, boxes.data_ptr(), 16, oh, ow, L.dtype_code(dt),
+                                                               gfeat.data_ptr(), L.stream_ptr()), "crop bwd")
+            nb = Bq * 16 * Cc * oh * ow * e + gfeat.numel() * 4 + Bq * 16 * 16
+            ms = timeit(bw)
+            res["a2"].append({"case": f"bwd {tag} {str(dt).split('.')[-1]}", "bytes": nb, "ms": ms, "GBps": nb / ms / 1e6, "frac": nb / ms / 1e6 / hbm,
+                              "form": "gather"})
+            del gfeat
             del feat, outp
     if not args.skip_dk:
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
