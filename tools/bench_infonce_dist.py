@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--tau", type=float, default=0.07)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--key-grad", action="store_true",
+                    help="also time the NON-detached variant (north_star (4)): forward + dq + msf_infonce_dk + NCCL reduce-scatter + finish")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -96,6 +98,63 @@ def main():
             flops = 4.0 * n * n * d
             row = {"gpus": world, "N": n, "Nq_per_gpu": nq, "D": d, "mean_loss": float(total.item()) / world, "ms_fwd_bwd": ms,
                    "tflops_whole_job": flops / ms / 1e9, "frac_of_peak": flops / ms / 1e9 / (peak1 * world), "peak_tflops_per_gpu": peak1}
+            if args.key_grad:
+                prec = L.MSF_BF16
+                n_keys = world * nq
+                wsb = L.lib().msf_infonce_workspace_bytes(nq, n_keys, d, prec)
+                ws2 = torch.empty(wsb, dtype=torch.uint8, device=dev)
+                dwb = L.lib().msf_infonce_dk_workspace_bytes(nq, n_keys, d, prec)
+                dws = torch.empty(dwb, dtype=torch.uint8, device=dev)
+                dk_all = torch.empty((n_keys, d), dtype=torch.float32, device=dev)
+                dk_loc = torch.empty((nq, d), dtype=torch.float32, device=dev)
+                gz = torch.empty_like(k)
+                off = rank * nq
+
+                def step_kg():
+                    qh, qi = ops.rownorm(q, torch.bfloat16)
+                    kh, ki = ops.rownorm(k, torch.bfloat16)
+                    if world > 1:
+                        dist.all_gather_into_tensor(kgath, kh)
+                        keys = kgath
+                    else:
+                        keys = kh
+                    lib = L.lib()
+                    L.check(lib.msf_infonce_fwd(qh.data_ptr(), keys.data_ptr(), nq, n_keys, d, off, args.tau, prec, loss.data_ptr(), 0, ws2.data_ptr(), wsb, st), "fwd")
+                    L.check(lib.msf_infonce_bwd(qh.data_ptr(), keys.data_ptr(), qi.data_ptr(), nq, n_keys, d, off, args.tau, prec, gout.data_ptr(), 1.0 / nq,
+                                                ws2.data_ptr(), wsb, gq.data_ptr(), L.MSF_BF16, st), "bwd")
+                    L.check(lib.msf_infonce_dk(qh.data_ptr(), keys.data_ptr(), nq, n_keys, d, off, args.tau, prec, gout.data_ptr(), 1.0 / nq, ws2.data_ptr(), wsb,
+                                               dk_all.data_ptr(), dws.data_ptr(), dwb, st), "dk")
+                    if world > 1:
+                        dist.reduce_scatter_tensor(dk_loc, dk_all)
+                        mine = dk_loc
+                    else:
+                        mine = dk_all
+                    L.check(lib.msf_infonce_dk_finish(mine.data_ptr(), qh.data_ptr(), kh.data_ptr(), ki.data_ptr(), nq, nq, d, args.tau, prec, gout.data_ptr(),
+                                                      1.0 / nq, gz.data_ptr(), L.MSF_BF16, st), "finish")
+
+                for _ in range(3):
+                    step_kg()
+                ts = []
+                for _ in range(args.iters):
+                    flush.zero_()
+                    if world > 1:
+                        dist.barrier()
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    step_kg()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+                    if world > 1:
+                        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    ts.append(float(t.item()))
+                ts.sort()
+                ms_kg = ts[len(ts) // 2]
+                row["key_grad"] = {"ms_fwd_dq_dk_reduce_scatter": ms_kg, "reduce_scatter_bytes_per_rank": n_keys * d * 4,
+                                   "frac_of_peak_6NND_algorithmic": 6.0 * n * n * d / ms_kg / 1e9 / (peak1 * world),
+                                   "frac_of_peak_8NND_executed": 8.0 * n * n * d / ms_kg / 1e9 / (peak1 * world)}
+                del ws2, dws, dk_all, dk_loc
             rows.append(row)
             if rank == 0:
                 print(json.dumps(row), flush=True)

@@ -1,4 +1,5 @@
-"""Development tool: torch.profiler breakdown of one bench step on rank 0 (run under torchrun for N>1)."""
+"""Development tool: torch.profiler breakdown of one bench.py step (same model, optimizer and bf16 NHWC inputs as bench.py's
+resident-input step) on rank 0; run under torchrun for N > 1.  Prints the kernel table sorted by device time."""
 import os, sys, warnings
 import torch, torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -18,12 +19,14 @@ if world > 1 or os.environ.get("FORCE_SYNCBN"):
 model = model.to(dev).to(memory_format=torch.channels_last).train()
 class LossStep(torch.nn.Module):
     def __init__(s, m): super().__init__(); s.model = m
-    def forward(s, x1, x2, rev): return s.model.forward_loss(x1, x2, rev, M.DEFAULT_FUSER_WEIGHTS, mode=os.environ.get("LOSS", "infonce"))
+    def forward(s, x1, x2, rev): return s.model.forward_loss(x1, x2, rev, M.DEFAULT_FUSER_WEIGHTS, mode=os.environ.get("LOSS", "cosine"))
 sm = LossStep(model)
 if world > 1:
     sm = torch.nn.parallel.DistributedDataParallel(sm, device_ids=[local], broadcast_buffers=False, gradient_as_bucket_view=True, bucket_cap_mb=128)
-opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
-mk = lambda n: torch.randn(n, 3, 224, 224, device=dev).contiguous(memory_format=torch.channels_last)
+groups = [{"params": [p for n, p in model.named_parameters() if n.startswith(pre)]} for pre in ("context_", "target_", "inter_")]
+opt = M.FusedAdam(groups, lr=1e-3)
+M.bind_optimizer(model, opt)
+mk = lambda n: torch.randn(n, 3, 224, 224, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
 c1, c2, t1, t2 = mk(B), mk(B), mk(16 * B), mk(16 * B)
 rev = [torch.stack([torch.randperm(16) for _ in range(B)]).to(dev) for _ in range(2)]
 def step():
@@ -40,6 +43,8 @@ from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     step(); torch.cuda.synchronize()
 if rank == 0:
-    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=int(os.environ.get("ROWS", "18")), max_name_column_width=70))
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=int(os.environ.get("ROWS", "45")), max_name_column_width=90))
+    if os.environ.get("TRACE"):
+        prof.export_chrome_trace(os.environ["TRACE"])
 if world > 1:
     dist.destroy_process_group()
