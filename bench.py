@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--heads-only", action="store_true",
                     help="time the hot path alone (gather/concat + heads + loss + backward + Adam on the head parameters) from "
                          "synthetic pooled features: the c4 regime (--batch 1024) does not fit one GPU with the encoders attached")
+    ap.add_argument("--cuda-graph", action="store_true",
+                    help="N = 1: capture the whole step (forward, backward, optimizer) in ONE CUDA graph after the warm-up and time its replays; "
+                         "`value` / `e2e` are then the replayed step, the eager step is reported beside it (`eager_step`)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true")
     ap.add_argument("--no-microbench", action="store_true")
@@ -332,8 +335,49 @@ def ours(args):
     ms, launches, prof, prof_dropped, clk, last_loss = main["ms"], main["launches"], main["prof"], main["prof_dropped"], main["clocks"], main["loss"]
     value = B * world * args.steps / (ms / 1e3)
 
+    # ---- the same step as ONE CUDA graph (launch-bound regime: the heads-only hot path spends its time in Python / autograd /
+    # launch overhead, not on the GPU).  Nothing in the step syncs with the host, every kernel argument is a device pointer
+    # from the graph's private pool or a value fixed at capture, the optimizer's pointer table is uploaded from pinned memory:
+    # the capture needs no special path.  Single GPU only: the cross-rank exchanges carry host-side sequence numbers.
+    eager_step = None
+    if args.cuda_graph:
+        if world > 1:
+            raise SystemExit("--cuda-graph is single-GPU (N = 1)")
+        eager_step = {"value": value, "unit": UNIT, "ms_per_step": ms / args.steps, "gpu_launches": launches}
+        eager_fn = step
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):  # PyTorch's whole-network capture recipe: warm up on a side stream first
+            for _ in range(3):
+                eager_fn(resident)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        opt.zero_grad(set_to_none=True)  # the gradients of the replayed step live in the graph's pool
+        l0 = _lib.launch_count
+        with torch.cuda.graph(graph):
+            static_loss = eager_fn(resident)
+        per_replay = _lib.launch_count - l0
+        static_in = resident
+
+        def step(d):  # noqa: F811 -- from here on a step is a replay (inputs copied into the captured tensors first)
+            if d is not static_in:
+                for k, v in d.items():
+                    for dst, src in zip(static_in[k] if isinstance(v, list) else [static_in[k]], v if isinstance(v, list) else [v]):
+                        dst.copy_(src, non_blocking=True)
+            graph.replay()
+            _lib.launch_count += per_replay
+            return static_loss
+
+        for _ in range(3):
+            step(resident)
+        main = timed(args.steps, False)
+        ms, launches, last_loss = main["ms"], main["launches"], main["loss"]
+        value = B * world * args.steps / (ms / 1e3)
+        eager_step["speedup_graph_over_eager"] = value / eager_step["value"]
+
     other = None
-    if not args.no_second_loss:
+    if not args.no_second_loss and not args.cuda_graph:
         loss_step.mode = "infonce" if args.loss == "cosine" else "cosine"
         for _ in range(3):
             step(resident)
@@ -345,7 +389,8 @@ def ours(args):
     # ---- timed region 2: end to end from pinned host memory, loss read back every step -------------------
     # Every step's inputs are copied host -> device inside the timed region (K copies for K steps); the copy of step
     # i+1 is issued on a side stream while step i computes (double buffering), the first copy is exposed.
-    del resident
+    if not args.cuda_graph:
+        del resident
     copy_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream(dev)
 
@@ -446,6 +491,9 @@ def ours(args):
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline, "loss": last_loss,
                 "encoder_images_per_sec": None if args.heads_only else value * 34}
+        if eager_step:
+            line["eager_step"] = eager_step
+            line["config"]["execution"] = "one CUDA graph per step (captured after warm-up, replayed)"
         if other:
             line[other["loss_mode"] + "_step"] = other
         if gpu_eager:
