@@ -341,34 +341,12 @@ def ours(args):
     # the capture needs no special path.  Single GPU only: the cross-rank exchanges carry host-side sequence numbers.
     eager_step = None
     if args.cuda_graph:
-        if world > 1:
-            raise SystemExit("--cuda-graph is single-GPU (N = 1)")
+        if world > 1 or not args.heads_only:
+            # the full step keeps the GPU busy for ~193 ms against ~46 ms of host time: nothing to gain from a capture there
+            raise SystemExit("--cuda-graph times the launch-bound hot path: use it with --heads-only at N = 1")
         eager_step = {"value": value, "unit": UNIT, "ms_per_step": ms / args.steps, "gpu_launches": launches}
-        eager_fn = step
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):  # PyTorch's whole-network capture recipe: warm up on a side stream first
-            for _ in range(3):
-                eager_fn(resident)
-        torch.cuda.current_stream(dev).wait_stream(side)
-        torch.cuda.synchronize(dev)
-        graph = torch.cuda.CUDAGraph()
-        opt.zero_grad(set_to_none=True)  # the gradients of the replayed step live in the graph's pool
-        l0 = _lib.launch_count
-        with torch.cuda.graph(graph):
-            static_loss = eager_fn(resident)
-        per_replay = _lib.launch_count - l0
-        static_in = resident
-
-        def step(d):  # noqa: F811 -- from here on a step is a replay (inputs copied into the captured tensors first)
-            if d is not static_in:
-                for k, v in d.items():
-                    for dst, src in zip(static_in[k] if isinstance(v, list) else [static_in[k]], v if isinstance(v, list) else [v]):
-                        dst.copy_(src, non_blocking=True)
-            graph.replay()
-            _lib.launch_count += per_replay
-            return static_loss
-
+        graphed = M.GraphedStep(step, resident, opt, warmup=3)
+        step = graphed  # noqa: F811 -- from here on a step is a replay (inputs are copied into the captured tensors first)
         for _ in range(3):
             step(resident)
         main = timed(args.steps, False)

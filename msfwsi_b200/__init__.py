@@ -8,6 +8,7 @@ not a legal Python identifier.  Public surface:
   ops.gather_concat / cosine_loss / infonce_loss / crop_resample / bn_act2d / EmaUpdater   the C-ABI operators
   FusedAdam                             torch.optim.Adam with the step (+ unscale, overflow skip, EMA) in one launch
   checkpoint                            the reference driver's checkpoint layout (save / resume / fine-tune key surgery)
+  GraphedStep                           one whole training step captured in ONE CUDA graph and replayed (single GPU)
 
 Importing the package never touches the GPU; the first operator call loads
 lib/libmsfwsi_b200.so and raises if it has not been built (no CPU fallback).
@@ -16,7 +17,8 @@ from . import ops  # noqa: F401
 from .module import DEFAULT_FUSER_WEIGHTS, MSFWSI, TCLinear, bind_optimizer, make_predictor, make_projector, ssl_loss  # noqa: F401
 from . import checkpoint  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
+from .graph import GraphedStep  # noqa: F401
 from .resnet import resnet18, resnet34  # noqa: F401
 
 __all__ = ["MSFWSI", "ssl_loss", "resnet18", "resnet34", "ops", "make_projector", "make_predictor",
-           "DEFAULT_FUSER_WEIGHTS", "FusedAdam", "bind_optimizer", "checkpoint"]
+           "DEFAULT_FUSER_WEIGHTS", "FusedAdam", "bind_optimizer", "checkpoint", "GraphedStep"]

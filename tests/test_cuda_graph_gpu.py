@@ -47,21 +47,14 @@ def test_whole_step_replays_bit_identically_from_a_cuda_graph(mode):
         return step
 
     step_a, step_b = make(ma, oa), make(mb, ob)
-    for _ in range(6):  # eager: 3 + 1 + 2 steps
+    for _ in range(6):  # eager: 3 + 1 (warm-up inside GraphedStep) + 2 steps
         la = step_a()
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        for _ in range(3):
-            step_b()
-    torch.cuda.current_stream().wait_stream(side)
-    torch.cuda.synchronize()
-    graph = torch.cuda.CUDAGraph()
-    ob.zero_grad(set_to_none=True)
-    with torch.cuda.graph(graph):  # the capture itself does not execute the step
-        lb = step_b()
-    for _ in range(3):
-        graph.replay()
+    for _ in range(3):  # same history as the eager twin before the capture
+        step_b()
+    graphed = M.GraphedStep(lambda _inputs: step_b(), {}, ob, warmup=1)  # one more warm-up step, then the capture
+    lb = graphed.loss
+    for _ in range(2):
+        graphed()
     torch.cuda.synchronize()
     assert torch.isfinite(la) and la.item() == lb.item()
     for (n, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
