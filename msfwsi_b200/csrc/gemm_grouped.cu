@@ -25,6 +25,7 @@
 // Tensor-bound for the target heads at large batch, weight-streaming (HBM) bound for the fuser heads at small batch:
 // 2*M*N*K FLOP; bytes (M*K + N*K)*2 read (re-reads served by L2) + M*N*e written.
 #include <algorithm>
+#include <cmath>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
@@ -551,36 +552,69 @@ Plan plan_of(const msf_gemm_problem& g) {
   return pl;
 }
 
-// Launch-wide plan.  Units of one launch share the 148 SMs, so the launch takes about max(total work / 148, longest unit):
-// every problem first gets the widest N tile (least bytes staged per MAC), then problems whose single unit would outlast
-// the balanced share T0 = work / 148 get narrower tiles and, if that is not enough, a deterministic split-K.  Work is
-// counted in staged bytes per k-block (128 + bn rows of 128 bytes), which is what bounds this kernel (L2 -> SM feed).
+// Launch-wide plan.  Work is counted in shared-memory rows of 128 bytes, which is what bounds this kernel (L2 -> SM feed and
+// its latency): a k-block stages 128 + bn rows, a split-K partial is 4 * bn rows written by every unit and ks * 4 * bn rows
+// read back by the last arriver, and every unit pays ~3 k-blocks of pipeline fill / epilogue.  A WIDE tile stages the fewest
+// bytes per MAC (a 256-row fuser problem with bn = 64 re-reads its A panel 72 times), so the plan prefers splitting K over
+// narrowing the tile:
+//   one problem    every (bn, ks) is scored by the makespan  ceil(units / 148) * unit_cost + reduction  and the best wins;
+//   many problems  the units share the 148 SMs, so the launch takes about max(total / 148, longest unit): per problem the
+//                  (bn, ks) with the least total cost among those whose unit (+ reduction) fits under that balanced share.
+struct Choice {
+  int bn, ks;
+};
+inline double fill_rows() { return 3.0 * (BM + 256); }
+inline int kb_per_split_of(int num_kb, int ks) { return (num_kb + ks - 1) / ks; }
+inline double unit_rows(int num_kb, int bn, int ks) {
+  return static_cast<double>(kb_per_split_of(num_kb, ks)) * (BM + bn) + fill_rows() + (ks > 1 ? 4.0 * bn : 0.0);
+}
+inline double reduce_rows(int bn, int ks) { return ks > 1 ? 4.0 * bn * ks : 0.0; }
+inline int max_splits(int num_kb) { return std::max(1, std::min(32, num_kb / 4)); }  // at least 4 k-blocks per split
+
 void plan_launch(const msf_gemm_problem* problems, int n, Plan* plans) {
-  auto unit_cost = [](int kb, int bn) { return static_cast<double>(kb) * (BM + bn) + 3.0 * (BM + 256); };  // + pipeline fill / epilogue
   double work = 0.0;
   for (int i = 0; i < n; ++i) {
     const msf_gemm_problem& g = problems[i];
     const int tiles_m = (g.M + BM - 1) / BM, num_kb = (g.K + GBK - 1) / GBK;
     const int bn = g.N <= 64 ? 64 : (g.N <= 128 ? 128 : 256);
-    work += static_cast<double>(tiles_m) * ((g.N + bn - 1) / bn) * unit_cost(num_kb, bn);
+    work += static_cast<double>(tiles_m) * ((g.N + bn - 1) / bn) * unit_rows(num_kb, bn, 1);
   }
-  const double cap = std::max(work / kNumSMs, unit_cost(24, 256));
+  const double cap = std::max(work / kNumSMs, unit_rows(24, 256, 1));
   for (int i = 0; i < n; ++i) {
     msf_gemm_problem g = problems[i];
-    const int num_kb = (g.K + GBK - 1) / GBK;
-    if (g.tile_n != 64 && g.tile_n != 128 && g.tile_n != 256) {
-      g.tile_n = 64;
-      for (int bn : {256, 128}) {
-        if (bn / 2 >= g.N) continue;  // a tile twice as wide as the problem only stages zeros
-        if (unit_cost(num_kb, bn) <= cap) { g.tile_n = bn; break; }
+    const int num_kb = (g.K + GBK - 1) / GBK, tiles_m = (g.M + BM - 1) / BM;
+    const bool bn_forced = g.tile_n == 64 || g.tile_n == 128 || g.tile_n == 256;
+    const bool ks_forced = g.split_k != 0;
+    Choice best{bn_forced ? g.tile_n : 64, ks_forced ? std::max(1, g.split_k) : 1};
+    double best_score = 1e300;
+    bool best_fits = false;
+    for (int bn : {256, 128, 64}) {
+      if (bn_forced ? bn != g.tile_n : (bn > 64 && bn / 2 >= g.N)) continue;  // a tile twice as wide as the problem only stages zeros
+      const int64_t tiles = static_cast<int64_t>(tiles_m) * ((g.N + bn - 1) / bn);
+      const int ks_hi = ks_forced ? std::max(1, g.split_k) : max_splits(num_kb);
+      for (int ks = ks_forced ? ks_hi : 1; ks <= ks_hi; ++ks) {
+        const int kbps = kb_per_split_of(num_kb, ks);
+        const int ks_eff = (num_kb + kbps - 1) / kbps;  // no empty split
+        if (!ks_forced && ks_eff != ks) continue;
+        const double unit = unit_rows(num_kb, bn, ks_eff), red = reduce_rows(bn, ks_eff);
+        const double units = static_cast<double>(tiles) * ks_eff;
+        double score;
+        bool fits = true;
+        if (n == 1) {
+          score = std::ceil(units / kNumSMs) * unit + red;  // makespan of the launch
+        } else {
+          fits = unit + red <= cap;
+          score = fits ? units * unit + red * tiles : unit + red;  // least total work among the fitting plans, else the shortest unit
+        }
+        if ((fits && !best_fits) || (fits == best_fits && score < best_score * 0.999)) {
+          best = Choice{bn, ks_eff};
+          best_score = score;
+          best_fits = fits;
+        }
       }
     }
-    if (g.split_k == 0) {
-      const double c = unit_cost(num_kb, g.tile_n);
-      int ks = c > cap ? static_cast<int>(c / cap + 0.999) : 1;
-      if (ks > num_kb / 4) ks = num_kb / 4;  // at least 4 k-blocks per split
-      g.split_k = ks > 1 ? ks : -1;
-    }
+    g.tile_n = best.bn;
+    g.split_k = best.ks > 1 ? best.ks : -1;
     plans[i] = plan_of(g);
   }
 }

@@ -122,6 +122,7 @@ class HeadRefs:
 
 
 N_PARAM = 12
+PRE_APPLY_MIN_WIDTH = 512  # heads wider than this materialise relu(bn(y)) instead of normalising inside the GEMM (see _HeadStage.forward)
 _W_IDX = (0, 3, 6, 7, 10)          # positions of the five Linear weights in HeadRefs.tensors()
 _G_IDX = ((1, 2), (4, 5), None, (8, 9))  # (gamma, beta) positions of BN1, BN2, BN3 (none), BN4
 
@@ -193,13 +194,21 @@ class _HeadStage(torch.autograd.Function):
         W = [[heads[h].lin[k].lowp_weight(dt) if fused else params[h * N_PARAM + _W_IDX[k]].detach() for k in range(5)] for h in range(nh)]
         widths = [[heads[h].d, heads[h].d, heads[h].d, heads[h].dq] for h in range(nh)]  # BN1..BN4 widths
 
+        # Wide heads (the fuser heads: d = 576 .. 4608 over few rows) take their normalised activations from ONE element-wise
+        # pass per depth instead of the GEMM's A prologue: a 256-row problem with N = 4608 has 36 column tiles (x split-K), and
+        # each of those units would re-normalise the same A panel -- the four transform warps then bound the launch (measured
+        # at B = 256: 201 us per projector depth with the prologue everywhere, 67 us for the same GEMMs without).  The narrow
+        # heads (context / target, d <= 512: one to four column tiles over many rows) keep the prologue, where it saves a
+        # round trip of the activation through HBM.  The materialised activations are kept for the dW GEMMs of the backward.
+        pre = [fused and heads[h].d > PRE_APPLY_MIN_WIDTH for h in range(nh)]
+
         # ---- buffers ----
         act_shapes, f32_shapes = [], []
         for h in range(nh):
             d, dq, r = heads[h].d, heads[h].dq, R[h]
             act_shapes += [(2, r, d)] * 3 + [(2, r, dq)]                      # y1, y2, y3, y4 (raw Linear outputs)
-            if not fused:
-                act_shapes += [(2, r, d)] * 2 + [(2, r, dq)]                  # a1, a2, a4 kept (no recompute on the exact path)
+            if not fused or pre[h]:
+                act_shapes += [(2, r, d)] * 2 + [(2, r, dq)]                  # a1, a2, a4 kept (exact path; wide heads)
             for k in range(4):
                 c = widths[h][k]
                 f32_shapes += [(2, (r + 31) // 32, 2, c)] + [(2, c)] * 4      # col_stats, scale, shift, mean, invstd
@@ -208,7 +217,8 @@ class _HeadStage(torch.autograd.Function):
         acts = _Carver(_Carver.size(act_shapes), dt, dev)
         f32 = _Carver(_Carver.size(f32_shapes), torch.float32, dev)
         y = [[acts.take(2, R[h], heads[h].d) for _ in range(3)] + [acts.take(2, R[h], heads[h].dq)] for h in range(nh)]
-        a_keep = None if fused else [[acts.take(2, R[h], heads[h].d), acts.take(2, R[h], heads[h].d), None, acts.take(2, R[h], heads[h].dq)] for h in range(nh)]
+        a_keep = [[acts.take(2, R[h], heads[h].d), acts.take(2, R[h], heads[h].d), None, acts.take(2, R[h], heads[h].dq)] if (not fused or pre[h]) else None
+                  for h in range(nh)]
         cs = [[None] * 4 for _ in range(nh)]
         sc, sh, mu, istd = ([[None] * 4 for _ in range(nh)] for _ in range(4))
         rowsq = [None] * nh
@@ -259,16 +269,25 @@ class _HeadStage(torch.autograd.Function):
             ops.gemm_grouped(specs)
 
         # ---- depth 1..3: projector ----
+        def pre_apply(k):  # a_k = relu(bn_k(y_k)) of the wide heads, one launch
+            items = [L.HeadApplyItem(L.ptr(y[h][k][v]), L.ptr(a_keep[h][k][v]), 0, 0, L.ptr(sc[h][k][v]), L.ptr(sh[h][k][v]), 0, R[h], widths[h][k], 1, 0)
+                     for h in range(nh) if pre[h] for v in range(2)]
+            if items:
+                apply(items)
+
         src = x0
         for k in range(3):
+            if fused and k > 0:
+                pre_apply(k - 1)
             specs = []
             for h in range(nh):
                 d = heads[h].d
                 for v in range(2):
-                    g = GemmSpec(src[h][v], W[h][k], R[h], d, d, C=y[h][k][v])
+                    a_in = a_keep[h][k - 1][v] if (fused and k > 0 and pre[h]) else src[h][v]
+                    g = GemmSpec(a_in, W[h][k], R[h], d, d, C=y[h][k][v])
                     if fused:
                         g.col_stats = cs[h][k][v] if training else None
-                        if k > 0:
+                        if k > 0 and not pre[h]:
                             g.a_scale, g.a_shift, g.a_relu = sc[h][k - 1][v], sh[h][k - 1][v], True
                     specs.append(g)
             gemm(specs)
@@ -315,12 +334,18 @@ class _HeadStage(torch.autograd.Function):
         if not fused:
             apply([L.HeadApplyItem(L.ptr(y[h][3][v]), L.ptr(a_keep[h][3][v]), 0, 0, L.ptr(sc[h][3][v]), L.ptr(sh[h][3][v]), L.ptr(mu[h][3][v]), R[h], heads[h].dq, 1, 0)
                    for h in range(nh) for v in range(2)])
+        if fused:
+            pre_apply(3)
         specs = []
         for h in range(nh):
             bias = params[h * N_PARAM + 11]
             for v in range(2):
                 if fused:
-                    g = GemmSpec(y[h][3][v], W[h][4], R[h], heads[h].d, heads[h].dq, C=p[h][v], bias=bias, a_scale=sc[h][3][v], a_shift=sh[h][3][v], a_relu=True)
+                    if pre[h]:
+                        g = GemmSpec(a_keep[h][3][v], W[h][4], R[h], heads[h].d, heads[h].dq, C=p[h][v], bias=bias)
+                    else:
+                        g = GemmSpec(y[h][3][v], W[h][4], R[h], heads[h].d, heads[h].dq, C=p[h][v], bias=bias, a_scale=sc[h][3][v], a_shift=sh[h][3][v],
+                                     a_relu=True)
                     if want_rowsq:
                         g.row_sumsq = rowsq[h][v]
                 else:
@@ -359,8 +384,8 @@ class _HeadStage(torch.autograd.Function):
         for h in range(nh):
             d, dq, r = heads[h].d, heads[h].dq, R[h]
             act_shapes += [(2, r, dq), (2, r, dq), (2, r, d), (2, r, d)]       # da4/dy4 ... reused per depth: g buffer + dy buffer at both widths
-            if fused:
-                act_shapes += [(2, r, d)] * 2 + [(2, r, dq)]                    # a1, a2, a4 rebuilt
+            if fused and a_keep[h] is None:
+                act_shapes += [(2, r, d)] * 2 + [(2, r, dq)]                    # a1, a2, a4 rebuilt (narrow heads: the forward normalised on the fly)
             rbs = (r + 255) // 256
             f32_shapes += [(2, rbs, 2, d)] * 4 + [(2, rbs, 2, dq)]              # reduce partials: BN1..3 + bias column sums (width d), BN4
             f32_shapes += [(2, d)] * 6 + [(2, dq)] * 2                          # c1, c2 per BN
@@ -373,10 +398,10 @@ class _HeadStage(torch.autograd.Function):
         for h in range(nh):
             d, dq, r = heads[h].d, heads[h].dq, R[h]
             gq[h], dyq[h], gd[h], dyd[h] = acts.take(2, r, dq), acts.take(2, r, dq), acts.take(2, r, d), acts.take(2, r, d)
-            if fused:
+            if a_keep[h] is None:
                 a[h][0], a[h][1], a[h][3] = acts.take(2, r, d), acts.take(2, r, d), acts.take(2, r, dq)
             else:
-                a[h] = a_keep[h]
+                a[h] = a_keep[h]  # exact path and wide heads: kept by the forward
             rbs = (r + 255) // 256
             for k in range(5):
                 part[h][k] = f32.take(2, rbs, 2, dq if k == 3 else d)
@@ -395,9 +420,9 @@ class _HeadStage(torch.autograd.Function):
             for lo in range(0, len(items), cap):
                 yield items[lo:lo + cap]
 
-        if fused:  # rebuild the ReLU activations the dW GEMMs read (one launch for all heads, layers and views)
+        if fused:  # rebuild the ReLU activations the dW GEMMs read (one launch for all narrow heads, layers and views)
             items = [L.HeadApplyItem(L.ptr(y[h][k][v]), L.ptr(a[h][k][v]), 0, 0, L.ptr(sc[h][k][v]), L.ptr(sh[h][k][v]), 0, R[h], widths[h][k], 1, 0)
-                     for h in range(nh) for k in (0, 1, 3) for v in range(2)]
+                     for h in range(nh) if a_keep[h] is None for k in (0, 1, 3) for v in range(2)]
             for ch in chunks(items, L.MSF_HEAD_MAX_MATS):
                 L.check(lib.msf_head_bn_apply(_arr(L.HeadApplyItem, ch), len(ch), code, ops.COS_EPS, st), "msf_head_bn_apply")
                 L.launch_count += 1

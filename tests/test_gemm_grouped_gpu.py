@@ -82,14 +82,17 @@ def test_split_k_counters_are_left_zero():
     assert int(ops._counters_for(torch.device(DEV)).abs().sum()) == 0
 
 
-@pytest.mark.parametrize("M,N,K", [(256, 64, 64), (4096, 512, 128), (96, 1152, 576), (45, 200, 72)])
-@pytest.mark.parametrize("split_k", [-1, 3])
-def test_statistics_epilogues(M, N, K, split_k):
-    if split_k > 0 and K < 192:
-        pytest.skip("needs >= 3 k-blocks")
+@pytest.mark.parametrize("M,N,K,tile_n", [(256, 64, 64, 0), (4096, 512, 128, 0), (96, 1152, 576, 0), (45, 200, 72, 0),
+                                             # every tile width x split the launch planner may choose for the head-stage shapes
+                                             (32, 1152, 4608, 64), (32, 1152, 4608, 128), (32, 1152, 4608, 256), (256, 4608, 4608, 256),
+                                             (512, 512, 512, 128), (300, 576, 1152, 256)])
+@pytest.mark.parametrize("split_k", [-1, 3, 0, 9])
+def test_statistics_epilogues(M, N, K, tile_n, split_k):
+    if split_k > 0 and K < 64 * 4 * split_k:
+        pytest.skip("needs >= 4 k-blocks per split")
     A, B = _mk((M, K), torch.bfloat16, 10), _mk((N, K), torch.bfloat16, 11, 0.3)
     bias = _mk((N,), torch.float32, 12)
-    g = ops.GemmSpec(A, B, M, N, K, bias=bias, split_k=split_k)
+    g = ops.GemmSpec(A, B, M, N, K, bias=bias, split_k=split_k, tile_n=tile_n)
     (C,) = ops.gemm_grouped([g], want_col_stats=True, want_row_sumsq=True)
     y = C.double()
     assert _rel(C, A.double() @ B.double().t() + bias.double()) <= 3e-3
