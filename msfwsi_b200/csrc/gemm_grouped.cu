@@ -26,6 +26,7 @@
 // 2*M*N*K FLOP; bytes (M*K + N*K)*2 read (re-reads served by L2) + M*N*e written.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
@@ -72,7 +73,8 @@ struct alignas(64) DevProblem {
 template <int NP>
 struct alignas(64) GroupParams {
   DevProblem p[NP];
-  int32_t n_problems, total_units, is_f16, pad_;
+  int32_t n_problems, total_units, is_f16;
+  int32_t epi2;  // no problem of the launch has an A prologue: warps 8-11 are a SECOND epilogue warpgroup (odd 64-column slabs)
 };
 static_assert(sizeof(GroupParams<MSF_GEMM_MAX_PROBLEMS>) <= 32000, "kernel parameter space (32764 bytes)");
 
@@ -85,7 +87,15 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+// named barriers of the epilogue: 2 / 3 = the 128 threads of epilogue group 0 / 1, 4 = both groups (256 threads, epi2 launches)
+__device__ __forceinline__ void epi_bar(int grp) {
+  if (grp == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
+  else asm volatile("bar.sync 3, 128;" ::: "memory");
+}
+__device__ __forceinline__ void epi_bar_all(bool both, int grp) {
+  if (both) asm volatile("bar.sync 4, 256;" ::: "memory");
+  else epi_bar(grp);
+}
 
 __device__ __forceinline__ uint32_t idesc_of(int n, bool b_mn, bool a_mn, bool f16) {
   const uint32_t fmt = f16 ? 0u : 1u;  // kind::f16 operand formats: 0 = f16, 1 = bf16
@@ -170,7 +180,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 1); mbar_init(pfull + s, 1); mbar_init(empty + s, 1); mbar_init(xformed + s, 128); }
-    for (int b = 0; b < 2; ++b) { mbar_init(acc_full + b, 1); mbar_init(acc_empty + b, 128); }
+    for (int b = 0; b < 2; ++b) { mbar_init(acc_full + b, 1); mbar_init(acc_empty + b, P.epi2 ? 256 : 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -250,7 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
         tc_commit(acc_full + buf);
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 8 && !P.epi2) {
     // ===================== A-prologue: a' = relu?(a * scale[k] + shift[k]) on the landed A tile =====================
     const int r = ((warp - 8) << 5) + lane;  // row of the 128 x 64 K-major tile: 128 bytes, 16-byte chunks XOR-swizzled by (r & 7)
     uint32_t it = 0, ppar = 0;
@@ -294,6 +304,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
     }
   } else if (warp >= 4) {
     // ===================== epilogue (one accumulator row per thread) =====================
+    // Launches without an A prologue (every backward launch: dX and dW, whose short K = rows makes the epilogue of a tile
+    // outlast its MMAs) run TWO epilogue warpgroups: group g = warps 4+4g .. 7+4g takes the 64-column slabs with (slab & 1) == g
+    // -- a warp may only read the TMEM lanes 32 * (warp % 4) .., which both groups' warps cover -- and stores through its own
+    // shared-memory slab.  Split-K bookkeeping synchronises both groups.
+    const bool epi2 = P.epi2 != 0;
+    const int grp = warp >= 8 ? 1 : 0;
     const int wq = warp & 3;
     const int row_in_tile = (wq << 5) + lane;
     const int etid = row_in_tile;  // 0..127
@@ -319,6 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
         float* part = q.ws + (static_cast<size_t>(tile_idx) * q.k_splits + w.ks) * BM * q.bn + row_in_tile * 4;
 #pragma unroll 1
         for (int c = 0; c < n_chunks; ++c) {
+          if (epi2 && ((c >> 1) & 1) != grp) continue;
           uint32_t v[32];
           tmem_ld32(lane_base + buf * 256 + c * 32, v);
           tmem_ld_wait();
@@ -328,16 +345,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
         tc_fence_before();
         mbar_arrive(acc_empty + buf);  // TMEM buffer is free again
         __threadfence();
-        epi_bar();
-        if (etid == 0) {
+        epi_bar_all(epi2, grp);
+        if (etid == 0 && grp == 0) {
           const int old = atomicAdd(q.counters + tile_idx, 1);
           const int last = old == q.k_splits - 1;
           if (last) q.counters[tile_idx] = 0;  // self-cleaning: the next launch finds zeros
           *last_flag = last;
         }
-        epi_bar();
+        epi_bar_all(epi2, grp);
         const bool last = *last_flag != 0;
-        epi_bar();  // everyone has read the flag before a later unit overwrites it
+        epi_bar_all(epi2, grp);  // everyone has read the flag before a later unit overwrites it
         if (!last) continue;
         __threadfence();
         from_ws = true;
@@ -348,6 +365,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
       float rq = 0.f;  // row sum of squares of the current 64-column block
 #pragma unroll 1
       for (int c = 0; c < n_chunks; ++c) {
+        if (epi2 && ((c >> 1) & 1) != grp) continue;
         float x[32];
         if (!from_ws) {
           uint32_t v[32];
@@ -420,10 +438,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
         // ---- store ----
         if (tma_store) {
           const int slab = c >> 1, half = c & 1;
-          uint8_t* sbuf = sC + ((slab_it + slab) & 1) * kStoreSlabBytes;
+          // one group: the two buffers alternate; two groups: each owns one buffer and waits for its previous store
+          uint8_t* sbuf = sC + (epi2 ? grp : ((slab_it + slab) & 1)) * kStoreSlabBytes;
           if (half == 0) {
-            if (etid == 0) bulk_wait_read<1>();  // the store that last read this buffer (two slabs ago) is done with it
-            epi_bar();
+            if (etid == 0) {  // the store that last read this buffer is done with it
+              if (epi2) bulk_wait_read<0>();
+              else bulk_wait_read<1>();
+            }
+            epi_bar(grp);
           }
           uint8_t* rowp = sbuf + row_in_tile * 128;
 #pragma unroll
@@ -431,7 +453,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
             *reinterpret_cast<uint4*>(rowp + (((half * 4 + j) ^ (row_in_tile & 7)) << 4)) = make_uint4(u16[4 * j], u16[4 * j + 1], u16[4 * j + 2], u16[4 * j + 3]);
           if (half == 1 || c == n_chunks - 1) {
             fence_proxy_async_smem();
-            epi_bar();
+            epi_bar(grp);
             if (etid == 0 && n0 + slab * 64 < q.N) {
               tma_store_2d(&q.tc, sbuf, n0 + slab * 64, m0);  // rows >= M and columns >= N are clipped by the tensor map
               bulk_commit();
@@ -568,6 +590,9 @@ inline int kb_per_split_of(int num_kb, int ks) { return (num_kb + ks - 1) / ks; 
 inline double unit_rows(int num_kb, int bn, int ks) {
   return static_cast<double>(kb_per_split_of(num_kb, ks)) * (BM + bn) + fill_rows() + (ks > 1 ? 4.0 * bn : 0.0);
 }
+// (A fixed ~10 us penalty per split -- what the warm-L2 sweep of tools/diag/gemm_plan_sweep.py suggests -- was tried and made
+// the training step slower: in the step the weights come from HBM, where more concurrent units win: 0.953 vs 0.899 ms of GEMM
+// time per 256-tile step.)
 inline double reduce_rows(int bn, int ks) { return ks > 1 ? 4.0 * bn * ks : 0.0; }
 inline int max_splits(int num_kb) { return std::max(1, std::min(32, num_kb / 4)); }  // at least 4 k-blocks per split
 
@@ -654,7 +679,7 @@ int launch_np(const GroupParams<MSF_GEMM_MAX_PROBLEMS>& P, bool f16, unsigned gr
   } else {
     static thread_local GroupParams<NP> Q;
     for (int i = 0; i < P.n_problems; ++i) Q.p[i] = P.p[i];
-    Q.n_problems = P.n_problems; Q.total_units = P.total_units; Q.is_f16 = P.is_f16;
+    Q.n_problems = P.n_problems; Q.total_units = P.total_units; Q.is_f16 = P.is_f16; Q.epi2 = P.epi2;
     return f16 ? launch_one<true, NP>(Q, grid, st) : launch_one<false, NP>(Q, grid, st);
   }
 }
@@ -737,6 +762,11 @@ int msf::gemm_grouped_launch(const msf_gemm_problem* problems, int n_problems, i
   P.n_problems = n_problems;
   P.total_units = unit;
   P.is_f16 = f16 ? 1 : 0;
+  static const bool epi2_off = getenv("MSF_GEMM_NO_EPI2") != nullptr;  // measurements
+  P.epi2 = 1;
+  for (int i = 0; i < n_problems; ++i)
+    if (problems[i].a_scale) P.epi2 = 0;
+  if (epi2_off) P.epi2 = 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const unsigned grid = static_cast<unsigned>(unit < kNumSMs ? unit : kNumSMs);
   ProfScope prof(stream, MSF_K_GEMM_GROUPED, flops);
