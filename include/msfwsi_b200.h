@@ -228,7 +228,7 @@ int msf_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* 
  *        apply + ReLU, backbone.py:15-16,18-19,28-29; rounded to the operand dtype before the ReLU like the reference's
  *        16-bit BatchNorm output); needs A stored [M][K]
  *   epi: + bias[n]; rounding to out_dtype; optional statistics of the ROUNDED outputs:
- *        col_stats [ceil(M/32)][2][N] fp32 = per 32-row group g: {sum_r y[r,n], sum_r y[r,n]^2} (rows past M excluded) --
+ *        col_stats [ceil(M/128)][2][N] fp32 = per 128-row M tile g: {sum_r y[r,n], sum_r y[r,n]^2} (rows past M excluded) --
  *        the batch-norm statistics of THIS layer, merged in fp64 by msf_head_bn_finalize;
  *        row_sumsq [ceil(N/64)][M] fp32 = per 64-column block: sum_n y[m,n]^2 -- the row norms the loss needs.
  * A [M,K] (a_is_km=0) or [K,M] (a_is_km=1) row-major (lda), B [N,K] (b_is_kn=0: C = A B^T) or [K,N] (b_is_kn=1: C = A B)
@@ -298,7 +298,7 @@ int msf_linear_bnstat(const void* x, const void* w, void* y, int64_t rows, int i
 #define MSF_HEAD_MAX_MATS 96       /* matrices per element-wise / reduce call */
 #define MSF_HEAD_SYNC_MAX_CTAS 256
 typedef struct {
-  const float* col_stats[2]; /* per view: [ceil(rows/32)][2][C] fp32 (msf_gemm_grouped epilogue or msf_head_bn_stats) */
+  const float* col_stats[2]; /* per view: [ceil(rows/group_rows)][2][C] fp32 (msf_gemm_grouped epilogue: 128-row groups; msf_head_bn_stats: 32) */
   float* scale[2];           /* out [C] */
   float* shift[2];           /* out [C] */
   float* mean[2];            /* out [C] or NULL */
@@ -312,6 +312,8 @@ typedef struct {
   int32_t n_views;           /* 1 or 2 */
   int32_t centered;          /* 1 (exact fp32 path): entry 1 of each col_stats group is M2 about the group mean (msf_head_bn_stats) and
                               * shift receives beta (consumers evaluate (x - mean) * scale + shift); 0: sums of squares, shift = beta - mean * scale */
+  int32_t group_rows;        /* rows per col_stats group: 128 for the msf_gemm_grouped epilogue (one group per M tile), 0 or 32 for
+                              * msf_head_bn_stats (the centered form needs 32) */
 } msf_head_bn_item;
 size_t msf_head_sync_workspace_bytes(int64_t capacity_doubles);
 int msf_head_bn_finalize(const msf_head_bn_item* items /*host*/, int n_items, float eps, float momentum, int training,

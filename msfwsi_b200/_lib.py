@@ -63,7 +63,7 @@ MSF_HEAD_SYNC_MAX_CTAS = 256
 class HeadBnItem(C.Structure):
     _fields_ = [("col_stats", C.c_void_p * 2), ("scale", C.c_void_p * 2), ("shift", C.c_void_p * 2), ("mean", C.c_void_p * 2),
                 ("invstd", C.c_void_p * 2), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("running_mean", C.c_void_p), ("running_var", C.c_void_p),
-                ("rows", C.c_int32), ("C", C.c_int32), ("n_views", C.c_int32), ("centered", C.c_int32)]
+                ("rows", C.c_int32), ("C", C.c_int32), ("n_views", C.c_int32), ("centered", C.c_int32), ("group_rows", C.c_int32)]
 
 
 class HeadMat(C.Structure):

@@ -42,7 +42,7 @@ using namespace tc;
 constexpr int GBK = 64, kStages = 4, kThreads = 384;
 constexpr uint32_t kABytes = BM * GBK * 2, kBBytesMax = 256 * GBK * 2, kStageBytes = kABytes + kBBytesMax;
 constexpr uint32_t kStoreSlabBytes = BM * 128;  // 128 rows x 64 16-bit columns, SWIZZLE_128B
-constexpr uint32_t kBarBytes = 1024;
+constexpr uint32_t kBarBytes = 2048;  // barriers (first 256 bytes) + the column-statistics hand-over of the epilogue groups
 constexpr uint32_t kSmem = 1024 + kStages * kStageBytes + 2 * kStoreSlabBytes + kBarBytes;
 static_assert(kSmem <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
 
@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
   uint64_t* acc_empty = acc_full + 2;      // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   volatile int* last_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+  float* stat_sm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2 groups][3 warps][2][32]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -489,12 +490,28 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
             s2[i] = t * t;
           }
           const float cs = warp_colsum32(s1, lane), cq = warp_colsum32(s2, lane);
-          const int grp = w.m_tile * 4 + wq;  // 32-row group index
-          if (grp * 32 < q.M && col + lane < q.N) {
-            float* dst = q.col_stats + (static_cast<size_t>(grp) * 2) * q.N + col + lane;
-            dst[0] = cs;
-            dst[q.N] = cq;
+          // one entry per 128-row tile: warps 1..3 hand their 32-row sums to warp 0 of the group (added in warp order), so the
+          // finalize kernel merges rows / 128 groups per column instead of rows / 32 (its per-column walk is a latency chain)
+          float* sx = stat_sm + grp * (3 * 2 * 32);
+          if (wq > 0) {
+            sx[((wq - 1) * 2) * 32 + lane] = cs;
+            sx[((wq - 1) * 2 + 1) * 32 + lane] = cq;
           }
+          epi_bar(grp);
+          if (wq == 0) {
+            float a = cs, b = cq;
+#pragma unroll
+            for (int w2 = 0; w2 < 3; ++w2) {
+              a += sx[(w2 * 2) * 32 + lane];
+              b += sx[(w2 * 2 + 1) * 32 + lane];
+            }
+            if (col + lane < q.N) {
+              float* dst = q.col_stats + (static_cast<size_t>(w.m_tile) * 2) * q.N + col + lane;
+              dst[0] = a;
+              dst[q.N] = b;
+            }
+          }
+          epi_bar(grp);  // the hand-over slots are reused by the next chunk
         }
       }
       if (tma_store) slab_it += static_cast<uint32_t>((n_chunks + 1) >> 1);

@@ -127,7 +127,8 @@ __global__ void __launch_bounds__(kThreads) head_bn_finalize_kernel(const __grid
   const bool ok = c < q.C;
   double v[4] = {0.0, 0.0, 0.0, 0.0};  // {sum, sum of squares} of view 0, view 1
   if (training && ok) {
-    const int groups = (q.rows + 31) / 32;
+    const int grows = q.group_rows > 0 ? q.group_rows : 32;
+    const int groups = (q.rows + grows - 1) / grows;
     for (int view = 0; view < q.n_views; ++view) {
       const float* cs = q.col_stats[view];
       double s1 = 0.0, s2 = 0.0;
@@ -510,6 +511,8 @@ extern "C" int msf_head_bn_finalize(const msf_head_bn_item* items, int n_items, 
     MSF_REQUIRE(!training || static_cast<int64_t>(q.rows) * (world > 1 ? world : 1) > 1, MSF_ERR_INVALID,
                 "item %d: Expected more than 1 value per channel when training", i);
     MSF_REQUIRE(training || (q.running_mean && q.running_var), MSF_ERR_INVALID, "item %d: eval mode needs running statistics", i);
+    MSF_REQUIRE(q.group_rows >= 0 && (!q.centered || q.group_rows == 0 || q.group_rows == 32), MSF_ERR_INVALID,
+                "item %d: group_rows %d (the centered form merges 32-row groups)", i, q.group_rows);
     T.it[i] = q;
     T.prefix[i] = blocks;
     blocks += (q.C + kThreads - 1) / kThreads;

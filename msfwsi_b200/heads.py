@@ -203,6 +203,7 @@ class _HeadStage(torch.autograd.Function):
         pre = [fused and heads[h].d > PRE_APPLY_MIN_WIDTH for h in range(nh)]
 
         # ---- buffers ----
+        grows = 128 if fused else 32  # rows per column-statistics group: one per GEMM M tile, or msf_head_bn_stats' 32-row groups
         act_shapes, f32_shapes = [], []
         for h in range(nh):
             d, dq, r = heads[h].d, heads[h].dq, R[h]
@@ -211,7 +212,7 @@ class _HeadStage(torch.autograd.Function):
                 act_shapes += [(2, r, d)] * 2 + [(2, r, dq)]                  # a1, a2, a4 kept (exact path; wide heads)
             for k in range(4):
                 c = widths[h][k]
-                f32_shapes += [(2, (r + 31) // 32, 2, c)] + [(2, c)] * 4      # col_stats, scale, shift, mean, invstd
+                f32_shapes += [(2, (r + grows - 1) // grows, 2, c)] + [(2, c)] * 4  # col_stats, scale, shift, mean, invstd
             if want_rowsq:
                 f32_shapes += [(2, (d + 63) // 64, r)]
         acts = _Carver(_Carver.size(act_shapes), dt, dev)
@@ -225,7 +226,7 @@ class _HeadStage(torch.autograd.Function):
         for h in range(nh):
             for k in range(4):
                 c = widths[h][k]
-                cs[h][k] = f32.take(2, (R[h] + 31) // 32, 2, c)
+                cs[h][k] = f32.take(2, (R[h] + grows - 1) // grows, 2, c)
                 sc[h][k], sh[h][k], mu[h][k], istd[h][k] = (f32.take(2, c) for _ in range(4))
             if want_rowsq:
                 rowsq[h] = f32.take(2, (heads[h].d + 63) // 64, R[h])
@@ -248,7 +249,7 @@ class _HeadStage(torch.autograd.Function):
                 items.append(L.HeadBnItem(_p2(L.ptr(cs[h][k][0]), L.ptr(cs[h][k][1])), _p2(L.ptr(sc[h][k][0]), L.ptr(sc[h][k][1])),
                                           _p2(L.ptr(sh[h][k][0]), L.ptr(sh[h][k][1])), _p2(L.ptr(mu[h][k][0]), L.ptr(mu[h][k][1])),
                                           _p2(L.ptr(istd[h][k][0]), L.ptr(istd[h][k][1])), L.ptr(gam), L.ptr(bet), L.ptr(bn.running_mean),
-                                          L.ptr(bn.running_var), R[h], widths[h][k], 2, 0 if fused else 1))
+                                          L.ptr(bn.running_var), R[h], widths[h][k], 2, 0 if fused else 1, grows))
             peers, world, rank, seq, cap, tmo = _sync_args(group, dev) if training else _NO_SYNC
             L.check(lib.msf_head_bn_finalize(_arr(L.HeadBnItem, items), nh, BN_EPS, BN_MOMENTUM, int(training), peers, world, rank, seq, cap, tmo, st),
                     "msf_head_bn_finalize")

@@ -500,7 +500,7 @@ def gemm_grouped(specs: Sequence[GemmSpec], want_col_stats: bool = False, want_r
             elif g.C.dtype != odt or g.C.stride(-1) != 1:
                 raise ValueError(f"gemm_grouped: problem {lo + i}: C must be {odt} with a contiguous last dimension")
             if want_col_stats and g.col_stats is None:
-                g.col_stats = torch.empty(((g.M + 31) // 32, 2, g.N), dtype=torch.float32, device=dev)
+                g.col_stats = torch.empty(((g.M + 127) // 128, 2, g.N), dtype=torch.float32, device=dev)  # one entry per 128-row M tile
             if want_row_sumsq and g.row_sumsq is None:
                 g.row_sumsq = torch.empty(((g.N + 63) // 64, g.M), dtype=torch.float32, device=dev)
             bias = None if g.bias is None else _contig(g.bias.detach().to(torch.float32))

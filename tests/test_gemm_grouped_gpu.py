@@ -96,11 +96,11 @@ def test_statistics_epilogues(M, N, K, tile_n, split_k):
     (C,) = ops.gemm_grouped([g], want_col_stats=True, want_row_sumsq=True)
     y = C.double()
     assert _rel(C, A.double() @ B.double().t() + bias.double()) <= 3e-3
-    groups = (M + 31) // 32
+    groups = (M + 127) // 128  # one entry per 128-row M tile
     assert g.col_stats.shape == (groups, 2, N) and g.row_sumsq.shape == ((N + 63) // 64, M)
-    pad = torch.zeros(groups * 32, N, dtype=torch.float64, device=DEV)
+    pad = torch.zeros(groups * 128, N, dtype=torch.float64, device=DEV)
     pad[:M] = y
-    pad = pad.view(groups, 32, N)
+    pad = pad.view(groups, 128, N)
     s1, s2 = pad.sum(1), (pad * pad).sum(1)
     scale = s2.max().item() + 1e-30
     assert float((g.col_stats[:, 0].double() - s1).abs().max()) <= 2e-6 * max(1.0, s1.abs().max().item())
@@ -183,7 +183,7 @@ def test_linear_bnstat_single_problem_abi():
     rows, fin, fout = 200, 128, 72
     x, w = _mk((rows, fin), torch.bfloat16, 300), _mk((fout, fin), torch.bfloat16, 301)
     y = torch.empty((rows, fout), dtype=torch.bfloat16, device=DEV)
-    st = torch.empty(((rows + 31) // 32, 2, fout), dtype=torch.float32, device=DEV)
+    st = torch.empty(((rows + 127) // 128, 2, fout), dtype=torch.float32, device=DEV)
     L.check(L.lib().msf_linear_bnstat(x.data_ptr(), w.data_ptr(), y.data_ptr(), rows, fin, fout, L.MSF_BF16, st.data_ptr(), 0, 0, 0, L.stream_ptr()),
             "msf_linear_bnstat")
     assert _rel(y, x.double() @ w.double().t()) <= 3e-3

@@ -16,7 +16,7 @@ def prepared(specs, want_stats=False):
     arr = (L.GemmProblem * len(specs))()
     keep = []
     for i, g in enumerate(specs):
-        cs = torch.empty(((g.M + 31) // 32, 2, g.N), dtype=torch.float32, device=dev) if want_stats else None
+        cs = torch.empty(((g.M + 127) // 128, 2, g.N), dtype=torch.float32, device=dev) if want_stats else None
         keep.append(cs)
         arr[i] = L.GemmProblem(g.A.data_ptr(), g.A.stride(0), g.B.data_ptr(), g.B.stride(0), g.C.data_ptr(), g.C.stride(0), g.M, g.N, g.K, int(g.a_is_km),
                                int(g.b_is_kn), L.dtype_code(g.C.dtype), 1.0, 0, L.ptr(cs), 0, 0, 0, 0, 0, 0, 0, 0.0, 0, 0)
