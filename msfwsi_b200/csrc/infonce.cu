@@ -247,33 +247,26 @@ __global__ void __launch_bounds__(256) nce_bwd_kernel(const char* __restrict__ q
   const float inv_sum = valid ? 1.f / sum_tot[row] : 0.f;
   const char* qrow = qh + row * row_bytes;
   const char* krow = kh + (row + pos_offset) * row_bytes;
-  // pass 1: t = q_hat . g_hat
-  float t = 0.f;
-  if (valid)
-    for (uint32_t c = lane; c < cpr; c += lanes) {
-      float fq[V], fk[V];
-      Elem<DT>::unpack(ldg_keep(qrow + static_cast<size_t>(c) * 16), fq);
-      Elem<DT>::unpack(ldg_keep(krow + static_cast<size_t>(c) * 16), fk);
-#pragma unroll
-      for (int i = 0; i < V; ++i) {
-        float o = 0.f;
-        for (int s = 0; s < splits; ++s) o += __ldg(o_part + (static_cast<int64_t>(s) * nq_pad + row) * dim + c * V + i);
-        t = fmaf(fq[i], gs * (o * inv_sum - fk[i]), t);
-      }
-    }
-  t = group_sum(t, lanes);
-  if (!valid) return;
-  const float inn = inv_norm ? inv_norm[row] : 1.f;
-  for (uint32_t c = lane; c < cpr; c += lanes) {
-    float fq[V], fk[V], g[V];
+  // d[i] = gs * (O_i / sum - k_pos,i): the O partials of the key splits are summed in fixed order, read as 128-bit vectors
+  auto load_d = [&](uint32_t c, float* fq, float* d) {
+    float fk[V];
     Elem<DT>::unpack(ldg_keep(qrow + static_cast<size_t>(c) * 16), fq);
     Elem<DT>::unpack(ldg_keep(krow + static_cast<size_t>(c) * 16), fk);
+    float o[V];
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      float o = 0.f;
-      for (int s = 0; s < splits; ++s) o += __ldg(o_part + (static_cast<int64_t>(s) * nq_pad + row) * dim + c * V + i);
-      g[i] = (gs * (o * inv_sum - fk[i]) - fq[i] * t) * inn;
+    for (int i = 0; i < V; ++i) o[i] = 0.f;
+    for (int s = 0; s < splits; ++s) {
+      const float4* src = reinterpret_cast<const float4*>(o_part + (static_cast<int64_t>(s) * nq_pad + row) * dim + c * V);
+#pragma unroll
+      for (int i = 0; i < V; i += 4) {
+        const float4 v = __ldg(src + i / 4);
+        o[i] += v.x; o[i + 1] += v.y; o[i + 2] += v.z; o[i + 3] += v.w;
+      }
     }
+#pragma unroll
+    for (int i = 0; i < V; ++i) d[i] = gs * (o[i] * inv_sum - fk[i]);
+  };
+  auto store_g = [&](uint32_t c, const float* g) {
     constexpr int GV = Elem<GDT>::VEC;
     char* dst = grad_q + (row * dim + static_cast<int64_t>(c) * V) * (16 / GV);
     if constexpr (GV == V) {
@@ -286,9 +279,54 @@ __global__ void __launch_bounds__(256) nce_bwd_kernel(const char* __restrict__ q
       const uint4 pk = Elem<GDT>::pack(tmp);
       *reinterpret_cast<uint2*>(dst) = make_uint2(pk.x, pk.y);
     }
+  };
+  const float inn = (valid && inv_norm) ? inv_norm[row] : 1.f;
+  constexpr int kKeep = 4;  // chunks per lane kept in registers between the two passes (every flash width)
+  if (cpr <= lanes * kKeep) {
+    float fq[kKeep][V], d[kKeep][V];
+    float t = 0.f;  // q_hat . d
+#pragma unroll
+    for (int j = 0; j < kKeep; ++j) {
+      const uint32_t c = lane + j * lanes;
+      if (valid && c < cpr) {
+        load_d(c, fq[j], d[j]);
+#pragma unroll
+        for (int i = 0; i < V; ++i) t = fmaf(fq[j][i], d[j][i], t);
+      }
+    }
+    t = group_sum(t, lanes);
+    if (!valid) return;
+#pragma unroll
+    for (int j = 0; j < kKeep; ++j) {
+      const uint32_t c = lane + j * lanes;
+      if (c < cpr) {
+        float g[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) g[i] = (d[j][i] - fq[j][i] * t) * inn;
+        store_g(c, g);
+      }
+    }
+    return;
+  }
+  // wide rows: two passes over the row, the second one served by L2
+  float t = 0.f;
+  if (valid)
+    for (uint32_t c = lane; c < cpr; c += lanes) {
+      float fq[V], d[V];
+      load_d(c, fq, d);
+#pragma unroll
+      for (int i = 0; i < V; ++i) t = fmaf(fq[i], d[i], t);
+    }
+  t = group_sum(t, lanes);
+  if (!valid) return;
+  for (uint32_t c = lane; c < cpr; c += lanes) {
+    float fq[V], d[V], g[V];
+    load_d(c, fq, d);
+#pragma unroll
+    for (int i = 0; i < V; ++i) g[i] = (d[i] - fq[i] * t) * inn;
+    store_g(c, g);
   }
 }
-
 
 // --------------------------------------------------------------------------------------------
 // key gradient (keys NOT detached -- north_star (4); the reference detaches every key, backbone.py:188-191)
