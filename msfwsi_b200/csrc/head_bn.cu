@@ -112,6 +112,17 @@ __device__ __forceinline__ int find_item(const Table& T, int n, int blk) {
   return i;
 }
 
+
+// V consecutive floats of a per-column vector as 128-bit loads (16-byte aligned: checked by the entry points)
+template <int V>
+__device__ __forceinline__ void load_cols(const float* p, float* out) {
+#pragma unroll
+  for (int e = 0; e < V; e += 4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p + e));
+    out[e] = v.x; out[e + 1] = v.y; out[e + 2] = v.z; out[e + 3] = v.w;
+  }
+}
+
 struct FinTable {
   msf_head_bn_item it[MSF_HEAD_MAX_ITEMS];
   int prefix[MSF_HEAD_MAX_ITEMS + 1];  // CTAs: ceil(C / 256) per item
@@ -266,13 +277,16 @@ __global__ void __launch_bounds__(kThreads) head_bn_apply_kernel(const __grid_co
   float ss = 0.f;
   if (valid)
     for (uint32_t c = lane; c < cpr; c += lanes) {
-      float f[V];
+      float f[V], sc[V], sh[V], mu[V];
       Elem<DT>::unpack(ldg_keep(src + static_cast<size_t>(c) * 16), f);
+      load_cols<V>(q.scale + c * V, sc);  // per-column vectors as 128-bit loads (C is a multiple of the chunk width)
+      load_cols<V>(q.shift + c * V, sh);
+      if (q.mean) load_cols<V>(q.mean + c * V, mu);
 #pragma unroll
       for (int e = 0; e < V; ++e) {
-        const float xc = q.mean ? f[e] - __ldg(q.mean + c * V + e) : f[e];
-        float t = round_to<DT>(fmaf(xc, __ldg(q.scale + c * V + e), __ldg(q.shift + c * V + e)));  // the 16-bit BN output ...
-        if (q.relu) t = fmaxf(t, 0.f);                                                               // ... then the ReLU on it
+        const float xc = q.mean ? f[e] - mu[e] : f[e];
+        float t = round_to<DT>(fmaf(xc, sc[e], sh[e]));  // the 16-bit BN output ...
+        if (q.relu) t = fmaxf(t, 0.f);                   // ... then the ReLU on it
         f[e] = t;
         ss = fmaf(t, t, ss);
       }
@@ -286,12 +300,15 @@ __global__ void __launch_bounds__(kThreads) head_bn_apply_kernel(const __grid_co
   if (lane == 0 && q.inv_norm) q.inv_norm[row] = inv;
   char* hat = static_cast<char*>(q.y_hat) + row * static_cast<int64_t>(q.C) * (16 / V);
   for (uint32_t c = lane; c < cpr; c += lanes) {  // second read hits L1
-    float f[V];
+    float f[V], sc[V], sh[V], mu[V];
     Elem<DT>::unpack(ldg_keep(src + static_cast<size_t>(c) * 16), f);
+    load_cols<V>(q.scale + c * V, sc);
+    load_cols<V>(q.shift + c * V, sh);
+    if (q.mean) load_cols<V>(q.mean + c * V, mu);
 #pragma unroll
     for (int e = 0; e < V; ++e) {
-      const float xc = q.mean ? f[e] - __ldg(q.mean + c * V + e) : f[e];
-      float t = round_to<DT>(fmaf(xc, __ldg(q.scale + c * V + e), __ldg(q.shift + c * V + e)));
+      const float xc = q.mean ? f[e] - mu[e] : f[e];
+      float t = round_to<DT>(fmaf(xc, sc[e], sh[e]));
       if (q.relu) t = fmaxf(t, 0.f);
       f[e] = t * inv;
     }
@@ -556,7 +573,8 @@ extern "C" int msf_head_bn_apply(const msf_head_apply_item* items, int n, int dt
   for (int i = 0; i < n; ++i) {
     const msf_head_apply_item& q = items[i];
     MSF_REQUIRE(q.x && q.y && q.scale && q.shift && q.rows > 0 && q.C > 0 && q.C % vec == 0, MSF_ERR_INVALID, "item %d: bad arguments (C %% %d)", i, vec);
-    MSF_REQUIRE(aligned16(q.x) && aligned16(q.y) && aligned16(q.y_hat), MSF_ERR_INVALID, "item %d: pointers must be 16-byte aligned", i);
+    MSF_REQUIRE(aligned16(q.x) && aligned16(q.y) && aligned16(q.y_hat) && aligned16(q.scale) && aligned16(q.shift) && aligned16(q.mean), MSF_ERR_INVALID,
+                "item %d: pointers must be 16-byte aligned", i);
     T.it[i] = q;
     T.prefix[i] = blocks;
     const uint32_t cpr = q.C / vec;
