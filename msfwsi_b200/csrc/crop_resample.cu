@@ -666,8 +666,9 @@ extern "C" int msf_crop_resample_fwd(const void* feat, int64_t B, int C, int H, 
   ProfScope prof(stream, MSF_K_CROP_FWD, (static_cast<double>(B) * C * H * W + static_cast<double>(rows) * ow) * dtype_size(dtype) + 16.0 * B * K);
   const bool fast_ok = vec_ok && ow % 32 == 0 && ow <= 32 * kMaxOxPerLane && owv <= 32 && (owv & (owv - 1)) == 0 &&
                        fast_smem <= 48 * 1024 && B * K < (1ll << 24);
-  // strip path: ow/vec strips per plane (power of two <= 256); the row taps of one box fit shared memory
-  const bool strip_ok = vec_ok && owv >= 1 && owv <= 256 && (owv & (owv - 1)) == 0 && oh <= 4000 &&
+  // strip path: ow/vec strips per plane (power of two <= 256); the row taps + segment list of one box ((4 * oh + 1) * 4 bytes) fit the
+  // 48 KB of dynamic shared memory a kernel gets without opting in
+  const bool strip_ok = vec_ok && owv >= 1 && owv <= 256 && (owv & (owv - 1)) == 0 && oh <= 3000 &&
                         B * K * static_cast<int64_t>((C + 256 / owv - 1) / (256 / owv)) < (1ll << 31);
   if (strip_ok) {
     const int planes_cta = 256 / owv;

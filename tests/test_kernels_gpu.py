@@ -272,6 +272,17 @@ def test_crop_resample_vs_oracle_and_interpolate(dtype, tol, H, W, scale, oh, ow
         assert torch.allclose(out[:, t].float(), it, rtol=tol, atol=tol)
 
 
+@pytest.mark.parametrize("oh", [3000, 3001, 4100])
+def test_crop_resample_tall_outputs_pick_a_path_that_fits_shared_memory(oh):
+    """The strip kernel keeps 4 * oh + 1 words of row taps and segment starts in dynamic shared memory: 3000 rows is the last size
+    that fits the 48 KB a kernel gets without opting in; taller outputs take the direct four-tap kernel."""
+    x = _rand((1, 2, 12, 16), 77).to(torch.bfloat16)
+    boxes = torch.tensor([[[1.0, 2.0, 11.0, 14.0]]])
+    out = ops.crop_resample(x.to(DEV), boxes.to(DEV), (oh, 8)).cpu()
+    ref = O.crop_resample(x.double(), boxes, (oh, 8))
+    assert torch.allclose(out.double(), ref, rtol=1e-2, atol=1e-2)
+
+
 def test_crop_resample_backward_matches_autograd():
     B, Cc, H, W, oh, ow = 2, 3, 16, 16, 12, 12
     x = _rand((B, Cc, H, W), 9).to(DEV).requires_grad_(True)
