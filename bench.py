@@ -731,6 +731,13 @@ def hbm_microbench(torch, ops, _lib, dev, peaks):
         nb = feat.numel() * e + outp.numel() * e + Bc * 16 * 16
         fn = lambda: L.check(L.lib().msf_crop_resample_fwd(feat.data_ptr(), Bc, Cc, H, W, boxes.data_ptr(), 16, oh, ow, L.MSF_BF16, outp.data_ptr(), st), "crop")
         rec(f"A2 crop_resample fwd bf16, {tag}", nb, timeit(fn), f"feat {tuple(feat.shape)} -> 16 footprints of {oh}x{ow}; {100 * outp.numel() * e // nb}% of the bytes are writes")
+        if tag.startswith("4x"):  # DRAM traffic of the same launch from the ncu capture (profiles/ncu_traffic.json)
+            try:
+                t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("crop_resample_fwd")
+                if t and t.get("algorithmic_bytes_per_launch") == nb:
+                    rows[-1]["traffic"] = t["dram_bytes_per_launch"]
+            except Exception:
+                pass
         gfeat = torch.empty((Bc, Cc, H, W), dtype=torch.float32, device=dev)
         nbb = outp.numel() * e + gfeat.numel() * 4 + Bc * 16 * 16
         fnb = lambda: L.check(L.lib().msf_crop_resample_bwd(outp.data_ptr(), Bc, Cc, H, W, boxes.data_ptr(), 16, oh, ow, L.MSF_BF16, gfeat.data_ptr(), st), "crop bwd")
