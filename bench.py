@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--cuda-graph", action="store_true",
                     help="N = 1: capture the whole step (forward, backward, optimizer) in ONE CUDA graph after the warm-up and time its replays; "
                          "`value` / `e2e` are then the replayed step, the eager step is reported beside it (`eager_step`)")
+    ap.add_argument("--no-hot-path", action="store_true", help="skip the heads-only eager vs CUDA-graph row of the default N = 1 run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true")
     ap.add_argument("--no-microbench", action="store_true")
@@ -447,6 +448,9 @@ def ours(args):
     import gc
     gc.collect()
     torch.cuda.empty_cache()
+    hot_path = None
+    if rank == 0 and world == 1 and not args.heads_only and not args.no_hot_path:
+        hot_path = hot_path_graph_bench(torch, M, _lib, dev, args)
     gpu_eager = None
     if not args.no_gpu_eager and not args.heads_only:
         gpu_eager = gpu_eager_baseline(torch, dist, args, dev, world, rank, barrier, max_over_ranks, value, e2e)
@@ -469,6 +473,8 @@ def ours(args):
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline, "loss": last_loss,
                 "encoder_images_per_sec": None if args.heads_only else value * 34}
+        if hot_path:
+            line["hot_path_cuda_graph"] = hot_path
         if eager_step:
             line["eager_step"] = eager_step
             line["config"]["execution"] = "one CUDA graph per step (captured after warm-up, replayed)"
@@ -612,6 +618,58 @@ def gpu_eager_baseline(torch, dist, args, dev, world, rank, barrier, max_over_ra
 # ------------------------------------------------------------------------------------------------------------
 # microbenchmarks measured in the same process
 # ------------------------------------------------------------------------------------------------------------
+def hot_path_graph_bench(torch, M, _lib, dev, args):
+    """The hot path WITHOUT the encoders (pooled pyramid features in: A1 gather/concat, the grouped head stage, the loss, their
+    backward and FusedAdam -- what SURVEY section 8 scopes) at the step's batch: eager against ONE CUDA graph per step
+    (msfwsi_b200.GraphedStep).  CUDA events, 3 warm-ups; the same numbers as `bench.py --heads-only [--cuda-graph]`."""
+    B, K = args.batch, 16
+
+    class _NoEncoder(torch.nn.Module):
+        def __init__(self, **_):
+            super().__init__()
+            self.fc = torch.nn.Identity()
+
+    model = M.MSFWSI(lambda **kw: _NoEncoder(**kw), 4, 2048, 512, 0.5, False).to(dev).train()
+    groups = [{"params": [p for n, p in model.named_parameters() if n.startswith(pre)]} for pre in ("context_", "target_", "inter_")]
+    opt = M.FusedAdam([g for g in groups if g["params"]], lr=1e-3)
+    M.bind_optimizer(model, opt)
+    g = torch.Generator().manual_seed(3407)
+    feats = lambda n: [torch.randn(n, d, generator=g).abs().to(torch.bfloat16).to(dev) for d in (64, 128, 256, 512)]
+    inputs = {"c1": feats(B), "c2": feats(B), "t1": feats(B * K), "t2": feats(B * K),
+              "r": [torch.stack([torch.randperm(K, generator=g).argsort() for _ in range(B)]).to(dev) for _ in range(2)]}
+
+    def step(d):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = model.heads_loss(d["c1"], d["c2"], d["t1"], d["t2"], d["r"], FUSER_WEIGHTS, mode=args.loss, tau=args.tau)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def timeit(fn, n):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / n
+
+    l0 = _lib.launch_count
+    ms_eager = timeit(lambda: step(inputs), 10)
+    per_step = (_lib.launch_count - l0) // 13
+    graphed = M.GraphedStep(step, inputs, opt, warmup=1)
+    ms_graph = timeit(graphed, 30)
+    return {"what": f"hot path only (no encoders), batch {B}, loss={args.loss}: gather/concat + 12 projectors + 12 predictors + loss, forward + backward + Adam",
+            "eager": {"ms_per_step": ms_eager, "tiles_per_sec": B / ms_eager * 1e3},
+            "cuda_graph": {"ms_per_step": ms_graph, "tiles_per_sec": B / ms_graph * 1e3, "launches_per_step": graphed.launches_per_replay},
+            "speedup_graph_over_eager": ms_eager / ms_graph, "eager_launches_per_step": per_step,
+            "note": "the eager step is Python / autograd / launch bound; the replayed graph is bit-identical (tests/test_cuda_graph_gpu.py)"}
+
+
 def infonce_microbench(torch, ops, _lib, dev, peaks, traffic):
     """c5 rows through the GROUPED entry points the training step calls (msf_nce_grouped_fwd / _bwd, one pair): the fused
     InfoNCE forward (flash tcgen05 launch + finalize + sum) and the whole fwd+bwd chain (row-normalise x2, forward, backward)
