@@ -32,8 +32,8 @@ struct Params {
   uint32_t total_blocks;
 };
 
-constexpr int kIlp = 4, kIter = 1, kThreads = 256;  // 16 KB per CTA: at the c4 size 5.2 k CTAs = 4.4 waves (kIter = 2: 2.2 waves, a third of the time in the tail)
-constexpr int kChunksPerBlock = kThreads * kIlp * kIter;  // 16 KB moved per CTA
+constexpr int kIlp = 4, kIter = 2, kThreads = 256;
+constexpr int kChunksPerBlock = kThreads * kIlp * kIter;  // 32 KB moved per CTA
 
 template <int DT>
 __global__ void __launch_bounds__(kThreads) row_copy_kernel(const __grid_constant__ Params P, int32_t* status) {
